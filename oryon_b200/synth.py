@@ -1,0 +1,219 @@
+"""Seeded synthetic inputs shared by tests, bench.py and oracle/make_golden.py.
+
+No dataset or checkpoint is available offline, so every parity case and
+every benchmark runs on inputs generated here from an integer seed with the CPU generator (the
+build container and the GPU box run the same torch build, so the streams are identical; the
+golden fixtures additionally store a checksum of the generated inputs).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+NOCS_INTRINSICS = (591.0125, 0.0, 322.525, 0.0, 590.16775, 244.11084, 0.0, 0.0, 1.0)  # reference datasets.py:398
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def ellipse_mask(h: int, w: int, frac: float, cy: float = 0.5, cx: float = 0.5, dtype=torch.int32) -> Tensor:
+    """Centred axis-aligned ellipse covering about ``frac`` of the ``h x w`` grid (values 0/1)."""
+    ys = (torch.arange(h, dtype=torch.float32) + 0.5) / h - cy
+    xs = (torch.arange(w, dtype=torch.float32) + 0.5) / w - cx
+    r2 = frac / math.pi  # area of ellipse with semi-axes a=b=sqrt(frac/pi) in unit square
+    m = (ys[:, None] ** 2 + xs[None, :] ** 2) <= r2
+    return m.to(dtype)
+
+
+def smooth_feature_pair(seed: int, d: int, h: int, w: int, *, coarse: int = 8, shift: Tuple[int, int] = (3, -2),
+                        noise: float = 0.05) -> Tuple[Tensor, Tensor]:
+    """Two ``[D,H,W]`` float32 maps that look like decoder output: a bilinear up-sampling of a coarse
+    random grid (neighbouring pixels are similar, so near-ties occur) and, for the query, the same
+    map rolled by ``shift`` plus white noise (so true matches exist)."""
+    g = _gen(seed)
+    ch, cw = max(2, h // coarse), max(2, w // coarse)
+    base = torch.randn(1, d, ch, cw, generator=g)
+    fa = F.interpolate(base, size=(h, w), mode="bilinear", align_corners=True)[0]
+    fa = fa + 0.02 * torch.randn(d, h, w, generator=g)
+    fq = torch.roll(fa, shifts=shift, dims=(1, 2)) + noise * torch.randn(d, h, w, generator=g)
+    return fa.contiguous(), fq.contiguous()
+
+
+def permuted_feature_batch(seed: int, b: int, d: int, h: int, w: int, noise: float = 0.1,
+                           device: str = "cpu", dtype=torch.float32) -> Tuple[Tensor, Tensor, Tensor]:
+    """BASELINE config 2 / 5 inputs: ``feat_a ~ N(0,1)`` of shape ``[B,D,H,W]``
+    and ``feat_q = perm(feat_a) + noise*N(0,1)`` with a per-pair random pixel permutation, so each
+    anchor pixel has exactly one strong match.  Returns ``(feat_a, feat_q, perm)`` where
+    ``feat_q[b,:,perm[b,i]] ~ feat_a[b,:,i]`` (flattened pixels).  Generated on ``device`` with a
+    device generator when it is CUDA (the bench needs 629 MB per batch; values are not golden)."""
+    if device == "cpu":
+        g = _gen(seed)
+        fa = torch.randn(b, d, h * w, generator=g)
+        perm = torch.stack([torch.randperm(h * w, generator=g) for _ in range(b)])
+        nz = torch.randn(b, d, h * w, generator=g)
+    else:
+        g = torch.Generator(device=device)
+        g.manual_seed(int(seed))
+        fa = torch.randn(b, d, h * w, generator=g, device=device)
+        perm = torch.stack([torch.randperm(h * w, generator=g, device=device) for _ in range(b)])
+        nz = torch.randn(b, d, h * w, generator=g, device=device)
+    fq = torch.empty_like(fa)
+    fq.scatter_(2, perm[:, None, :].expand(b, d, h * w), fa)
+    fq.add_(nz, alpha=noise)
+    return fa.view(b, d, h, w).to(dtype), fq.view(b, d, h, w).to(dtype), perm
+
+
+def random_rotation(g: torch.Generator, max_angle_deg: float = 45.0) -> Tensor:
+    axis = torch.randn(3, generator=g, dtype=torch.float64)
+    axis = axis / axis.norm()
+    ang = (torch.rand(1, generator=g, dtype=torch.float64).item() * 2 - 1) * math.radians(max_angle_deg)
+    K = torch.tensor([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]], dtype=torch.float64)
+    return torch.eye(3, dtype=torch.float64) + math.sin(ang) * K + (1 - math.cos(ang)) * (K @ K)
+
+
+def rigid_correspondences(seed: int, n: int = 500, outlier_frac: float = 0.3, noise: float = 0.002,
+                          extent: float = 0.3) -> Dict[str, Tensor]:
+    """``n`` 3-D correspondences (metres) related by a planted rigid motion, with Gaussian noise on the
+    inliers and ``outlier_frac`` of the targets replaced by uniform points: PointDSC parity input."""
+    g = _gen(seed)
+    src = (torch.rand(n, 3, generator=g, dtype=torch.float64) - 0.5) * extent
+    src[:, 2] += 1.0
+    R = random_rotation(g)
+    t = (torch.rand(3, generator=g, dtype=torch.float64) - 0.5) * 0.2
+    tgt = src @ R.T + t + noise * torch.randn(n, 3, generator=g, dtype=torch.float64)
+    n_out = int(n * outlier_frac)
+    out_idx = torch.randperm(n, generator=g)[:n_out]
+    tgt[out_idx] = (torch.rand(n_out, 3, generator=g, dtype=torch.float64) - 0.5) * extent * 1.5 + torch.tensor([0, 0, 1.0], dtype=torch.float64) + t
+    T = torch.eye(4, dtype=torch.float64)
+    T[:3, :3], T[:3, 3] = R, t
+    return dict(src=src.float(), tgt=tgt.float(), T=T.float(), outliers=out_idx)
+
+
+POINTDSC_DEFAULT_CFG = dict(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1,
+                            sigma_d=0.1, k=40, inlier_threshold=0.1)
+
+
+POINTDSC_CASES = {300: (500, 0.3), 301: (500, 0.6), 302: (137, 0.2), 303: (41, 0.1), 304: (500, 0.0)}  # seed -> (n, outlier frac)
+
+
+def pointdsc_state_dict(seed: int, cfg: Dict = POINTDSC_DEFAULT_CFG) -> Dict[str, Tensor]:
+    """Seeded random PointDSC ``state_dict`` with the reference's parameter names and shapes
+    (reference models/pointdsc/PointDSC.py:9-113): Xavier-normal conv weights, small random biases,
+    *non-trivial* BatchNorm running statistics so that eval-mode BN folding is exercised."""
+    g = _gen(seed)
+    C, L = cfg["num_channels"], cfg["num_layers"]
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, cout, cin):
+        std = math.sqrt(2.0 / (cin + cout))
+        sd[name + ".weight"] = torch.randn(cout, cin, 1, generator=g) * std
+        sd[name + ".bias"] = torch.randn(cout, generator=g) * 0.05
+
+    def bn(name, c):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        sd[name + ".bias"] = 0.05 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
+
+    sd["sigma"] = torch.tensor([1.0])
+    sd["sigma_spat"] = torch.tensor([float(cfg["sigma_d"])])
+    conv("encoder.layer0", C, cfg["in_dim"])
+    for i in range(L):
+        p = f"encoder.blocks.PointCN_layer_{i}"
+        conv(p + ".0", C, C)
+        bn(p + ".1", C)
+        p = f"encoder.blocks.NonLocal_layer_{i}"
+        conv(p + ".fc_message.0", C // 2, C)
+        bn(p + ".fc_message.1", C // 2)
+        conv(p + ".fc_message.3", C // 2, C // 2)
+        bn(p + ".fc_message.4", C // 2)
+        conv(p + ".fc_message.6", C, C // 2)
+        conv(p + ".projection_q", C, C)
+        conv(p + ".projection_k", C, C)
+        conv(p + ".projection_v", C, C)
+    conv("classification.0", 32, C)
+    conv("classification.2", 32, 32)
+    conv("classification.4", 1, 32)
+    return sd
+
+
+def synthetic_rgbd_pair(seed: int, raw_hw: Tuple[int, int] = (480, 640)) -> Dict[str, Tensor]:
+    """One synthetic NOCS-like RGB-D pair: a smooth depth surface (mm, int32)
+    for the anchor; the query depth is produced by moving the anchor cloud rigidly and re-rendering it
+    by nearest-pixel splatting (holes filled with the median), so a true relative pose exists."""
+    g = _gen(seed)
+    H, W = raw_hw
+    K = torch.tensor(NOCS_INTRINSICS, dtype=torch.float64).view(3, 3)
+    coarse = torch.rand(1, 1, 6, 8, generator=g) * 400.0 + 800.0
+    depth_a = F.interpolate(coarse, size=(H, W), mode="bicubic", align_corners=True)[0, 0].round().to(torch.int32)
+    rgb_a = torch.rand(3, 224, 224, generator=g)
+    rgb_q = torch.rand(3, 224, 224, generator=g)
+    R = random_rotation(g, 10.0)
+    t = (torch.rand(3, generator=g, dtype=torch.float64) - 0.5) * 0.05
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    z = depth_a.double() / 1000.0
+    pts = torch.stack(((xs - K[0, 2]) * z / K[0, 0], (ys - K[1, 2]) * z / K[1, 1], z), -1).view(-1, 3)
+    moved = pts @ R.T + t
+    u = (moved[:, 0] / moved[:, 2] * K[0, 0] + K[0, 2]).round().long()
+    v = (moved[:, 1] / moved[:, 2] * K[1, 1] + K[1, 2]).round().long()
+    ok = (u >= 0) & (u < W) & (v >= 0) & (v < H)
+    depth_q = torch.zeros(H * W, dtype=torch.float64)
+    depth_q[v[ok] * W + u[ok]] = moved[ok, 2] * 1000.0
+    med = depth_q[depth_q > 0].median()
+    depth_q[depth_q == 0] = med
+    T = torch.eye(4, dtype=torch.float64)
+    T[:3, :3], T[:3, 3] = R, t
+    return dict(rgb_a=rgb_a, rgb_q=rgb_q, depth_a=depth_a, depth_q=depth_q.view(H, W).round().to(torch.int32),
+                camera=K, T_rel=T)
+
+
+# name -> (seed, D, H, W, mask frac a, mask frac q, noise, threshold, max_corrs, subsample_source)
+MATCH_CASES = {
+    "m0_d32_48x48": (100, 32, 48, 48, 0.30, 0.35, 0.05, 0.25, 500, None),
+    "m1_d32_64x64_subsample": (101, 32, 64, 64, 0.40, 0.45, 0.05, 0.25, 500, 300),
+    "m2_d128_40x40_full": (102, 128, 40, 40, 2.0, 2.0, 0.05, 0.25, 500, 5000),
+    "m3_d32_none": (103, 32, 32, 32, 0.25, 0.25, 50.0, 0.02, 500, None),
+    "m4_d32_replacement": (104, 32, 32, 32, 0.05, 0.30, 0.05, 0.25, 500, None),
+    "m5_d17_24x40_ragged": (105, 17, 24, 40, 0.30, 0.50, 0.05, 0.25, 64, 100),
+    "m6_d32_96x96_refsize": (106, 32, 96, 96, 0.15, 0.20, 0.08, 0.25, 500, 5000),
+}
+
+
+def match_inputs(case):
+    seed, d, h, w, fa_frac, fq_frac, noise, th, max_corrs, sub = MATCH_CASES[case]
+    fa, fq = smooth_feature_pair(seed, d, h, w, noise=noise)
+    ma = ellipse_mask(h, w, fa_frac, 0.5, 0.5)
+    mq = ellipse_mask(h, w, fq_frac, 0.55, 0.45)
+    return fa, fq, ma, mq, th, max_corrs, sub, seed
+
+
+
+LIFT_CASES = {200: ((192, 192), (480, 640)), 201: ((192, 192), (200, 150)), 202: ((48, 64), (480, 640))}
+
+
+def lift_inputs(seed: int):
+    """Random featmap-space correspondences + integer depth maps (10 % zero-depth pixels, which the
+    reference does not filter: utils/pcd.py:52,72-74) for the scale/bounds/lift parity cases."""
+    (HO, WO), (H, W) = LIFT_CASES[seed]
+    g = _gen(seed)
+    corrs = torch.stack([torch.randint(0, HO, (500,), generator=g), torch.randint(0, WO, (500,), generator=g),
+                         torch.randint(0, HO, (500,), generator=g), torch.randint(0, WO, (500,), generator=g)], 1)
+    depth_a = torch.randint(0, 3000, (H, W), generator=g, dtype=torch.int32)
+    depth_q = torch.randint(0, 3000, (H, W), generator=g, dtype=torch.int32)
+    depth_a[torch.rand(H, W, generator=g) < 0.1] = 0
+    K = torch.tensor(NOCS_INTRINSICS, dtype=torch.float64)
+    return corrs, depth_a, depth_q, K, (HO, WO), (H, W)
+
+
+def tensor_checksum(t: Tensor) -> str:
+    """sha256 of the raw bytes: pins regenerated inputs to the ones the golden outputs came from."""
+    import hashlib
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()[:16]
