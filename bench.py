@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the Oryon matching hot path on B200 (BASELINE.json metric: image-pairs/sec; the workload
+is BASELINE config 2: batch of 32 synthetic 480x640 pairs, 128-d feature maps at stride 4 (120x160 ->
+19 200 positions per image), dense all-pairs matching).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the matcher (oryon_match_nn: normalise -> tcgen05 similarity + argmax ->
+fp32 re-score) over one batch of 32 pairs.  Prints ONE JSON line (rank 0).
+  value        pairs/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          pairs/s through the public Python API with pinned HOST buffers: H2D of both feature maps and
+               D2H of (index, distance) inside the timed region, every step
+  roofline     the tcgen05 similarity kernel against the measured bf16 tensor peak (MEASURED_PEAKS.json)
+  cpu_baseline the oracle (CPU port of the reference's nn_correspondences arithmetic) on a bounded sample
+`--impl reference` times that CPU port alone, with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(B=32, D=128, H=120, W=160)
+L2_BYTES = 126e6
+
+
+def algorithmic_work(B, D, na, nq, elt=4):
+    """SURVEY.md 8(d) / BASELINE.md section 4: per pair FLOPs = 2*Na*Nq*D, bytes = (Na+Nq)*D*s + (Na+Nq) + 8*Na."""
+    flops = 2.0 * na * nq * D * B
+    bytes_ = ((na + nq) * D * elt + (na + nq) + 8 * na) * B
+    return flops, bytes_
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons while the timed region runs (NVML, falling back to nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {}
+        if nv is not None:
+            for n in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap", "HwPowerBrakeSlowdown"):
+                v = getattr(nv, "nvmlClocksThrottleReason" + n, None) or getattr(nv, "nvmlClocksEventReason" + n, None)
+                if v:
+                    names[v] = n
+        while not self._stop.is_set():
+            try:
+                if nv is not None:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit, n in names.items():
+                        if mask & bit:
+                            self.reasons.add(n)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,"
+                                          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for n, v in zip(("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap"), f[2:]):
+                        if v == "Active":
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_port_sample(rows, threads, D=WORKLOAD["D"], n=WORKLOAD["H"] * WORKLOAD["W"], repeats=1, seed=0):
+    """Time the oracle's matcher (reference utils/pcd.py:202-204 restated) on `rows` anchor rows of one pair
+    against all `n` query positions.  Returns seconds per call (best of `repeats`)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oryon_oracle as oracle
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn(rows, D, generator=g)
+    f2 = torch.randn(n, D, generator=g)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.match_rows(f1, f2, row_chunk=64)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference matcher, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = WORKLOAD["H"] * WORKLOAD["W"]
+    rows = args.ref_rows
+    for _ in range(args.warmup):
+        cpu_port_sample(min(rows, 64), threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_port_sample(rows, threads, seed=s)
+    dt = (time.perf_counter() - t0) / args.steps
+    pairs_per_s = (rows / n) / dt
+    sample = f"{rows} of {n} anchor rows of one pair x all {n} query positions, D={WORKLOAD['D']}, scaled by {n / rows:.1f}"
+    line = {"impl": "reference", "metric": "image-pairs/sec", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (n / rows) * WORKLOAD["B"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: B=32 pairs, D=128, 120x160 (19200 positions), dense all-pairs NN matching",
+                       "note": "reference is Python/PyTorch and cannot travel to the GPU box: this is the oracle port of "
+                               "utils/pcd.py:202-204 (pinned to reference outputs by tests/golden)"},
+            "cpu_baseline": {"value": pairs_per_s, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": pairs_per_s, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-rows", type=int, default=1024, help="anchor rows per step of the CPU reference arm")
+    ap.add_argument("--cpu-rows", type=int, default=4096, help="anchor rows of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--B", type=int, default=WORKLOAD["B"])
+    ap.add_argument("--D", type=int, default=WORKLOAD["D"])
+    ap.add_argument("--H", type=int, default=WORKLOAD["H"])
+    ap.add_argument("--W", type=int, default=WORKLOAD["W"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from oryon_b200 import _lib, synth
+    from oryon_b200.utils import pcd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, D, H, W = args.B, args.D, args.H, args.W
+    n = H * W
+    # pairs are independent: every rank owns its own batch of B pairs (weak scaling), no data-path collective
+    fa, fq, perm = synth.permuted_feature_batch(1000 + rank, B, D, H, W, noise=0.1, device=f"cuda:{local}")
+    idx = torch.empty(B, n, dtype=torch.int32, device=dev)
+    dst = torch.empty(B, n, dtype=torch.float32, device=dev)
+
+    def step():
+        pcd.match_nn(fa, fq, out=(idx, dst))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches_per_step = pcd.match_last_stats(dev)["kernels_launched"]
+    _lib.profile_enable(local, True)
+    _lib.profile_read(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_read(local)
+    _lib.profile_enable(local, False)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ok = bool(torch.equal(idx.long(), perm))  # planted permutation recovered: the timed work is the real work
+    stats = pcd.match_last_stats(dev)
+
+    # ---- end to end through the public API with pinned host buffers --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ha, hq = fa.cpu().pin_memory(), fq.cpu().pin_memory()
+        h_idx = torch.empty(B, n, dtype=torch.int32).pin_memory()
+        h_dst = torch.empty(B, n, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            i, d = pcd.match_nn(ha, hq)          # H2D of both maps inside
+            h_idx.copy_(i, non_blocking=True)
+            h_dst.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * k / float(te.item()), "unit": "pairs/s",
+               "h2d_bytes_per_step": int(ha.numel() * 4 + hq.numel() * 4), "d2h_bytes_per_step": int(h_idx.numel() * 8),
+               "steps": k, "ok": bool(torch.equal(h_idx.long(), perm.cpu()))}
+        del ha, hq
+
+    # final (and only) collective of the path: gather one result row per rank
+    if world > 1:
+        row = torch.tensor([float(rank), float(ok), float(idx.sum().item())], device=dev, dtype=torch.float64)
+        rows = [torch.empty_like(row) for _ in range(world)]
+        dist.all_gather(rows, row)
+        ok = all(bool(r[1].item()) for r in rows)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+            "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        flops, bytes_ = algorithmic_work(B, D, n, n)
+        tc_ms, tc_n = prof.get("match_tc", (0.0, 0))
+        tc_avg = tc_ms / max(tc_n, 1)
+        achieved_tf = flops / (tc_avg * 1e-3) / 1e12 if tc_avg > 0 else None
+        hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        line = {
+            "metric": "image-pairs/sec", "value": world * B * args.steps / (ms_max * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands, f32 accumulate + f32 re-score", "data": "synthetic",
+            "config": {"workload": f"config2: B={B} pairs/GPU, D={D}, {H}x{W} ({n} positions/image), dense all-pairs NN matching "
+                                   "(480x640 frames at stride 4)",
+                       "l2": f"inputs are {2 * B * D * n * 4 / 1e6:.0f} MB per step, larger than the 126 MB L2 (no flush needed)",
+                       "parallelism": f"pairs sharded, {world} rank(s), no data-path collective"},
+            "results_ok": ok,
+            "clocks": clocks.summary(),
+            "e2e": e2e,
+            "gpu_launches": int(launches_per_step * args.steps),
+            "kernels_ms_per_step": {str(k): v[0] / args.steps for k, v in prof.items()},
+            "match_stats_last_step": stats,
+            "roofline": {"kernel": "match_tc_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (achieved_tf / peak_tf if achieved_tf else None), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_flops_per_launch": flops, "launch_ms": tc_avg,
+                         "hbm": {"algorithmic_bytes_per_step": bytes_, "achieved_gbs": bytes_ / (ms_max / args.steps * 1e-3) / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": bytes_ / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak}},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            cpu_port_sample(32, threads)
+            sec = cpu_port_sample(args.cpu_rows, threads)
+            line["cpu_baseline"] = {"value": (args.cpu_rows / n) / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_rows} of {n} anchor rows of one pair x all {n} query positions, D={D}; "
+                                              f"{sec:.1f} s measured, scaled by {n / args.cpu_rows:.1f}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

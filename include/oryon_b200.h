@@ -1,0 +1,134 @@
+/*
+ * oryon_b200.h -- C ABI of liboryon_b200.so: the B200 (sm_100a) implementation of the Oryon
+ * inference hot path.
+ *
+ * The reference (jcorsetti/oryon) has no FFI: its boundary for this path is a set of Python
+ * functions.  Each entry point below names the reference function (file:line under the reference
+ * tree) whose arithmetic it replaces; oryon_b200/*.py are the Python mirrors that keep the
+ * reference signatures and call these through ctypes (INTEGRATION.md shows the binding a reference
+ * maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - pointers marked DEVICE are CUDA device pointers on the handle's device, HOST are host pointers.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation
+ *     unless the function is documented as returning a host-visible count.
+ *   - the caller owns every input and output buffer; the library owns only its handle-scoped
+ *     workspace and packed weights.  Buffers are borrowed for the duration of the call's stream work.
+ *   - every function returns 0 on success or a negative oryon_status; oryon_last_error() returns a
+ *     thread-local human readable message for the last failure on this thread.
+ *   - a handle is bound to one (process, device) and is not thread-safe; use one per thread.
+ */
+#ifndef ORYON_B200_H_
+#define ORYON_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORYON_ABI_VERSION 1
+
+typedef struct oryon_handle oryon_handle;
+
+typedef enum {
+  ORYON_OK = 0,
+  ORYON_ERR_INVALID_ARGUMENT = -1,
+  ORYON_ERR_CUDA = -2,
+  ORYON_ERR_UNSUPPORTED_DEVICE = -3, /* not an sm_100 device: there is no fallback path */
+  ORYON_ERR_OUT_OF_MEMORY = -4,
+  ORYON_ERR_NOT_LOADED = -5          /* weights for the requested stage were not loaded */
+} oryon_status;
+
+/* Matching arithmetic (reference utils/pcd.py:195-200 picks fp32 on CPU or fp16 on CUDA). */
+typedef enum {
+  /* fp16-operand tcgen05 pass (fp32 accumulate) that keeps every candidate within the proven
+   * rounding bound of the row maximum, then exact fp32 re-scoring of the candidates: the result
+   * equals a full fp32 evaluation (corrs_device='cpu' semantics).  Default. */
+  ORYON_MATCH_TC_REFINED = 0,
+  /* straight fp32 CUDA-core evaluation of every (anchor,query) pair; slow, used as the device-side
+   * cross-check and as the fallback for rows whose candidate list overflowed. */
+  ORYON_MATCH_EXACT_FP32 = 1
+} oryon_match_mode;
+
+typedef enum { ORYON_DEPTH_I32 = 0, ORYON_DEPTH_F32 = 1, ORYON_DEPTH_I16 = 2, ORYON_DEPTH_U16 = 3 } oryon_depth_dtype;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+
+int oryon_abi_version(void);
+const char* oryon_last_error(void);
+
+/* Creates the per-device context (workspace, TMA descriptor entry point).  Fails with
+ * ORYON_ERR_UNSUPPORTED_DEVICE unless the device is compute capability 10.x. */
+int oryon_create(int device, oryon_handle** out);
+int oryon_destroy(oryon_handle* h);
+
+/* Bytes of device workspace currently held by the handle (diagnostics). */
+int64_t oryon_workspace_bytes(const oryon_handle* h);
+
+/* Per-kernel device timing for benchmarks.  When enabled, every kernel the library launches is bracketed
+ * by CUDA events recorded on the caller's stream.  oryon_profile_read waits for the recorded events,
+ * returns per kernel id the summed duration (ms) and launch count since the last read, and clears them.
+ * Kernel ids: 0 prep_rows, 1 match_tc (tcgen05 similarity + argmax epilogue), 2 refine_rows,
+ * 3 exact_rows, 4 mask_to_roi, 5 lift/corrs_to_pcd; further ids are listed in DESIGN.md. */
+int oryon_profile_enable(oryon_handle* h, int enable);
+int oryon_profile_read(oryon_handle* h, double* total_ms, int64_t* launches, int n_ids);
+
+/* ---- a8: masked nearest-neighbour feature matching ----------------------------------------
+ * Replaces, for B independent (anchor, query) pairs at once, the arithmetic of
+ *   utils/pcd.py:192-205   (ROI feature gather, pdist 'inv_norm_cosine' :28-29, amin/argmin)
+ * of the reference's nn_correspondences.  ROI selection order and the two random draws
+ * (utils/pcd.py:184-190, :211; utils/misc.py:242-254) stay with the caller so that torch's
+ * nonzero ordering and CPU generator are preserved bit-for-bit.
+ *
+ *   feat_a, feat_q   DEVICE  float32 planar feature maps [B][D][HW_a], [B][D][HW_q]
+ *   roi_a, roi_q     DEVICE  int32 flattened pixel ids (y*W+x) in match order, [B][cap_a] / [B][cap_q];
+ *                            NULL means the dense identity list 0..HW-1 (n_* must then be NULL too)
+ *   n_a, n_q         HOST    int32 [B] list lengths (<= cap); NULL with dense lists
+ *   out_idx          DEVICE  int32 [B][cap_a]: position in the pair's query list of the nearest
+ *                            neighbour of anchor row i (lowest position on exact ties, as
+ *                            torch.argmin); -1 for rows >= n_a[b] or when n_q[b] == 0
+ *   out_dist         DEVICE  float32 [B][cap_a]: 0.5*(1-cos) of that neighbour (fp32)
+ */
+int oryon_match_nn(oryon_handle* h, const float* feat_a, const float* feat_q, int B, int D, int HW_a, int HW_q,
+                   const int32_t* roi_a, const int32_t* roi_q, const int32_t* n_a, const int32_t* n_q,
+                   int cap_a, int cap_q, int mode, int32_t* out_idx, float* out_dist, void* stream);
+
+/* Statistics of the last oryon_match_nn call on this handle, valid after the stream work finished
+ * (reads a small device counter block: synchronises the stream).
+ *   stats[0] rows re-scored from the candidate list   stats[1] candidate chunks re-scored
+ *   stats[2] rows that overflowed to the exact fallback   stats[3] kernels launched by the call */
+int oryon_match_last_stats(oryon_handle* h, int64_t stats[4], void* stream);
+
+/* Row-major compaction of a [B][HW] mask into pixel-id lists: ids of elements equal to `value`
+ * in ascending order == torch.nonzero(mask == value) (reference utils/pcd.py:184-185).
+ *   mask    DEVICE int32 [B][HW]      roi_out DEVICE int32 [B][HW]      n_out DEVICE int32 [B] */
+int oryon_mask_to_roi(oryon_handle* h, const int32_t* mask, int B, int HW, int value, int32_t* roi_out,
+                      int32_t* n_out, void* stream);
+
+/* ---- a9 + a10: coordinate scaling, bounds test, truncation, 2D->3D lifting -----------------
+ * Replaces pipeline.py:447-460: utils/coordinates.py:5-13 scale_coords (float32 multiply by the
+ * Python-float ratio), :36-47 get_valid_coords, the .to(long) truncation, utils/pcd.py:35-81
+ * lift_pcd on the selected pixels and the division by 1000.
+ *
+ *   corrs            DEVICE  int64 [n][4] (y1,x1,y2,x2) in feature-map coordinates
+ *   depth_a/q        DEVICE  [Ha][Wa] / [Hq][Wq] of `depth_dtype` (millimetres)
+ *   cam_a, cam_q     HOST    float64 [9] row-major intrinsics
+ *   pcd_a, pcd_q     DEVICE  float32 [n][3] metres; only the first *n_valid rows are written, rows
+ *                            keep their order (stable compaction of the bounds mask)
+ *   n_valid          DEVICE  int32 [1]
+ */
+int oryon_corrs_to_pcd(oryon_handle* h, const int64_t* corrs, int n, int feat_h, int feat_w, const void* depth_a,
+                       const void* depth_q, int depth_dtype, int Ha, int Wa, int Hq, int Wq, const double* cam_a,
+                       const double* cam_q, float* pcd_a, float* pcd_q, int32_t* n_valid, void* stream);
+
+/* utils/pcd.py:35-81 lift_pcd with xy_idxs: out[i] = ((x-cx)*z/fx, (y-cy)*z/fy, z), z = depth[y][x].
+ *   xs, ys DEVICE int64 [n]; out DEVICE float32 [n][3] in depth units (the caller divides by 1000). */
+int oryon_lift_pcd(oryon_handle* h, const void* depth, int depth_dtype, int H, int W, const double* cam,
+                   const int64_t* xs, const int64_t* ys, int n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORYON_B200_H_ */

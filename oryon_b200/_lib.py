@@ -1,0 +1,120 @@
+"""ctypes binding of liboryon_b200.so (include/oryon_b200.h).
+
+There is no CPU or PyTorch fallback behind these calls: if the library is missing, cannot be loaded,
+or the device is not sm_100, the call raises.  PyTorch is used by the callers for device memory and
+streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from typing import Dict, Optional
+
+from . import build as _build
+
+ABI_VERSION = 1
+
+MATCH_TC_REFINED = 0
+MATCH_EXACT_FP32 = 1
+
+DEPTH_I32, DEPTH_F32, DEPTH_I16, DEPTH_U16 = 0, 1, 2, 3
+
+# name -> (restype, argtypes): every symbol include/oryon_b200.h declares
+SIGNATURES = {
+    "oryon_abi_version": (c_int, []),
+    "oryon_last_error": (c_char_p, []),
+    "oryon_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "oryon_destroy": (c_int, [c_void_p]),
+    "oryon_workspace_bytes": (c_int64, [c_void_p]),
+    "oryon_profile_enable": (c_int, [c_void_p, c_int]),
+    "oryon_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
+    "oryon_match_nn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "oryon_match_last_stats": (c_int, [c_void_p, POINTER(c_int64), c_void_p]),
+    "oryon_mask_to_roi": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "oryon_corrs_to_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "oryon_lift_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_void_p, c_void_p, c_int,
+                               c_void_p, c_void_p]),
+}
+
+_lock = threading.Lock()
+_cdll: Optional[ctypes.CDLL] = None
+_handles: Dict[int, c_void_p] = {}
+
+
+class OryonError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """dlopen the library (building it first if the .so is absent and nvcc exists) and bind every symbol."""
+    global _cdll
+    with _lock:
+        if _cdll is not None:
+            return _cdll
+        path = library_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise OryonError(f"{path} is missing: run `python -m oryon_b200.build` (no fallback path exists)")
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        got = lib.oryon_abi_version()
+        if got != ABI_VERSION:
+            raise OryonError(f"liboryon_b200.so ABI {got} != binding ABI {ABI_VERSION}; rebuild the library")
+        _cdll = lib
+        return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().oryon_last_error()
+        raise OryonError(f"liboryon_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def handle(device_index: int) -> c_void_p:
+    """One context per (process, device), created lazily; raises on non-sm_100 devices."""
+    lib = load()
+    with _lock:
+        h = _handles.get(device_index)
+        if h is None:
+            h = c_void_p()
+            rc = lib.oryon_create(int(device_index), ctypes.byref(h))
+            if rc != 0:
+                msg = lib.oryon_last_error()
+                raise OryonError(f"oryon_create({device_index}) failed ({rc}): {msg.decode() if msg else '?'}")
+            _handles[device_index] = h
+        return h
+
+
+def destroy_all() -> None:
+    lib = load()
+    with _lock:
+        for h in _handles.values():
+            lib.oryon_destroy(h)
+        _handles.clear()
+
+
+KERNEL_IDS = {"prep_rows": 0, "match_tc": 1, "refine_rows": 2, "exact_rows": 3, "mask_to_roi": 4, "lift": 5}
+
+
+def profile_enable(device_index: int, enable: bool) -> None:
+    check(load().oryon_profile_enable(handle(device_index), int(bool(enable))))
+
+
+def profile_read(device_index: int, n_ids: int = 16):
+    """{kernel name or id: (total_ms, launches)} since the last read (waits for the recorded events)."""
+    ms = (c_double * n_ids)()
+    cnt = (c_int64 * n_ids)()
+    check(load().oryon_profile_read(handle(device_index), ms, cnt, n_ids))
+    names = {v: k for k, v in KERNEL_IDS.items()}
+    return {names.get(i, i): (ms[i], cnt[i]) for i in range(n_ids) if cnt[i]}

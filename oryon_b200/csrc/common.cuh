@@ -1,0 +1,93 @@
+// Shared host-side plumbing for liboryon_b200: status/error reporting, the handle and its
+// grow-only device workspace.  No torch, no third-party headers.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/oryon_b200.h"
+
+namespace oryon {
+
+void set_error(const char* fmt, ...);
+
+#define ORYON_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      ::oryon::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ORYON_ERR_CUDA;                                                                     \
+    }                                                                                            \
+  } while (0)
+
+#define ORYON_REQUIRE(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ::oryon::set_error(__VA_ARGS__);                \
+      return ORYON_ERR_INVALID_ARGUMENT;              \
+    }                                                 \
+  } while (0)
+
+// One grow-only device buffer.  Growth happens on the caller's stream order: the old block is
+// released with cudaFreeAsync-like semantics by synchronising the stream first (growth is rare:
+// sizes are monotone per workload).
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t want, cudaStream_t stream);
+  void release();
+  template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace oryon
+
+namespace oryon {
+// Optional per-kernel timing (oryon_profile_enable): CUDA events recorded on the caller's stream around
+// each kernel launch, summed per kernel id when read.  Off by default (no events are recorded).
+enum KernelId { KID_PREP = 0, KID_MATCH_TC = 1, KID_REFINE = 2, KID_EXACT = 3, KID_MASK_ROI = 4, KID_LIFT = 5, KID_COUNT = 16 };
+struct ProfSpan {
+  int id;
+  cudaEvent_t a, b;
+};
+}  // namespace oryon
+
+// The opaque handle of the C ABI.
+struct oryon_handle {
+  bool profiling = false;
+  std::vector<oryon::ProfSpan> spans;       // recorded, not yet read
+  std::vector<cudaEvent_t> free_events;
+  cudaEvent_t take_event();
+  void span_begin(int id, cudaStream_t st);
+  void span_end(cudaStream_t st);
+
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  oryon::PFN_encodeTiled encode_tiled = nullptr;
+
+  // ---- matching workspace (see match.cu) ----
+  oryon::DeviceBuffer rows16_a, rows16_q;   // fp16 unit rows, K-major, padded   [B][Npad][Dpad]
+  oryon::DeviceBuffer rows32_a, rows32_q;   // fp32 unit rows                    [B][Npad][D]
+  oryon::DeviceBuffer cand;                 // per (pair,row,split) candidate lists
+  oryon::DeviceBuffer counters;             // small counter block (work queue, stats, overflow list size)
+  oryon::DeviceBuffer overflow_rows;        // rows that need the exact fallback
+  oryon::DeviceBuffer pair_meta;            // per-pair {n_a, n_q} on device
+  int64_t last_launches = 0;
+
+  // ---- lift workspace ----
+  oryon::DeviceBuffer lift_scratch;
+
+  int64_t workspace_bytes() const;
+};

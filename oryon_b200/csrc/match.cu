@@ -1,0 +1,772 @@
+// a8 -- masked nearest-neighbour feature matching (reference utils/pcd.py:192-205).
+//
+//   prep_rows_kernel      gather ROI pixels from the planar fp32 map, L2-normalise (fp32), write
+//                         fp32 unit rows [N][D4] and fp16 unit rows [Npad][Dpad] (K-major)     HBM-bound
+//   match_tc_kernel       S = A * Q^T on tcgen05 (fp16 operands, fp32 accumulate in TMEM), never
+//                         materialised: the epilogue keeps, per anchor row, the running maximum and
+//                         the list of 8-column chunks whose maximum is within the proven fp16
+//                         rounding bound of it                                                  tensor-bound
+//   refine_rows_kernel    exact fp32 re-scoring of the listed chunks -> (argmax, distance)
+//   exact_rows_kernel     fp32 CUDA-core evaluation of full rows: ORYON_MATCH_EXACT_FP32 mode and the
+//                         fallback for rows whose candidate list overflowed
+//
+// Layouts: rows16_x [B][Npad_x][Dpad] __half, rows32_x [B][Npad_x][D4] float (D4 = D rounded up to 4,
+// zero padded).  Candidate lists: cand_m / cand_cnt [B][S][Npad_a], cand_chunk [B][S][Npad_a][CAND_CAP].
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace oryon {
+namespace match {
+
+constexpr int kTileM = 128;        // rows per UMMA
+constexpr int kRowBlocks = 2;      // UMMA row blocks per CTA (A tile = 256 rows resident in smem)
+constexpr int kCtaRows = kTileM * kRowBlocks;
+constexpr int kTileN = 128;        // query columns per tile
+constexpr int kChunk = 8;          // columns per candidate chunk
+constexpr int kCandCap = 16;       // candidate chunks kept per (row, split)
+constexpr int kMaxSplits = 8;
+constexpr int kTcThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// |fp16-operand score - fp32 score| <= 2^-10 (two roundings of unit-norm operands, Cauchy-Schwarz)
+// + accumulation slack; a column can be the fp32 argmax only if its fp16 score is within twice that
+// of the fp16 row maximum.
+constexpr float kAmbiguity = 2.1e-3f;
+
+struct PairMeta {
+  int n_a, n_q;
+};
+
+// ------------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const float* feat[2];
+  const int32_t* roi[2];
+  int hw[2], cap[2], npad[2];
+  __half* rows16[2];
+  float* rows32[2];
+  const PairMeta* meta;
+  int D, D4, Dpad;
+};
+
+__global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
+  extern __shared__ float tile[];  // [D][33]
+  __shared__ float red[8][32];
+  __shared__ float inv_norm[32];
+  const int side = blockIdx.z, b = blockIdx.y, r0 = blockIdx.x * 32;
+  const int n = side == 0 ? a.meta[b].n_a : a.meta[b].n_q;
+  if (r0 >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = r0 + lane;
+  const int hw = a.hw[side];
+  int pix = 0;
+  if (r < n) pix = a.roi[side] ? a.roi[side][(size_t)b * a.cap[side] + r] : r;
+  const float* src = a.feat[side] + (size_t)b * a.D * hw + pix;
+  float ss = 0.f;
+  for (int d = warp; d < a.D; d += 8) {
+    const float v = (r < n) ? __ldg(src + (size_t)d * hw) : 0.f;
+    tile[d * 33 + lane] = v;
+    ss = fmaf(v, v, ss);
+  }
+  red[warp][lane] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][lane];
+    // reference: x / norm.clamp_min(eps), eps = 1e-8 (torch cosine_similarity default)
+    inv_norm[lane] = fmaxf(sqrtf(s), 1e-8f);
+  }
+  __syncthreads();
+  float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;
+  for (int i = threadIdx.x; i < 32 * a.D4; i += 256) {
+    const int row = i / a.D4, d = i - row * a.D4;
+    d32[i] = d < a.D ? __fdiv_rn(tile[d * 33 + row], inv_norm[row]) : 0.f;
+  }
+  __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
+  for (int i = threadIdx.x; i < 32 * a.Dpad; i += 256) {
+    const int row = i / a.Dpad, d = i - row * a.Dpad;
+    d16[i] = __float2half_rn(d < a.D ? __fdiv_rn(tile[d * 33 + row], inv_norm[row]) : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact fp32 rows (mode ORYON_MATCH_EXACT_FP32 and overflow fallback)
+// ------------------------------------------------------------------------------------------------
+struct ExactArgs {
+  const float* rows32_a;
+  const float* rows32_q;
+  const PairMeta* meta;
+  const int32_t* row_list;   // packed b * npad_a + r, or nullptr = all rows
+  const int32_t* n_items_dev;  // number of entries in row_list (device) or nullptr
+  int n_items_host;          // used when row_list == nullptr (B * npad_a)
+  int npad_a, npad_q, D4, cap_a;
+  int32_t* out_idx;
+  float* out_dist;
+};
+
+// 64 anchor rows per CTA, 256 threads as 16x16, each thread a 4x4 micro-tile, K chunks of 32.
+__global__ void __launch_bounds__(256) exact_rows_kernel(ExactArgs a) {
+  __shared__ float As[32][64 + 4];
+  __shared__ float Qs[32][64 + 4];
+  __shared__ int item_row[64];
+  __shared__ int item_pair[64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int n_items = a.row_list ? *a.n_items_dev : a.n_items_host;
+  for (int t0 = blockIdx.x * 64; t0 < n_items; t0 += gridDim.x * 64) {
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int it = t0 + threadIdx.x;
+      int packed = -1;
+      if (it < n_items) packed = a.row_list ? a.row_list[it] : it;
+      int b = -1, r = 0;
+      if (packed >= 0) {
+        b = packed / a.npad_a;
+        r = packed - b * a.npad_a;
+        if (r >= a.meta[b].n_a) b = -1;
+      }
+      item_pair[threadIdx.x] = b;
+      item_row[threadIdx.x] = r;
+    }
+    __syncthreads();
+    // all 64 items of a tile may belong to different pairs when row_list is used; the column loop
+    // is per pair, so process the distinct pairs present one after the other (usually one).
+    int done_pair = -1;
+    while (true) {
+      int b = 0x7fffffff;
+      for (int i = 0; i < 64; ++i) {
+        const int p = item_pair[i];
+        if (p > done_pair && p < b) b = p;
+      }
+      if (b == 0x7fffffff) break;
+      done_pair = b;
+      const int n_q = a.meta[b].n_q;
+      float best[4];
+      int best_j[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) best[i] = -INFINITY, best_j[i] = -1;
+      for (int c0 = 0; c0 < n_q; c0 += 64) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < a.D4; k0 += 32) {
+          __syncthreads();
+          for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+            const int row = i >> 5, k = i & 31;
+            float va = 0.f, vq = 0.f;
+            if (k0 + k < a.D4) {
+              if (item_pair[row] == b) va = a.rows32_a[((size_t)b * a.npad_a + item_row[row]) * a.D4 + k0 + k];
+              if (c0 + row < n_q) vq = a.rows32_q[((size_t)b * a.npad_q + c0 + row) * a.D4 + k0 + k];
+            }
+            As[k][row] = va;
+            Qs[k][row] = vq;
+          }
+          __syncthreads();
+#pragma unroll 8
+          for (int k = 0; k < 32; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 qv = *reinterpret_cast<const float4*>(&Qs[k][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w};
+            const float qr[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], qr[j], acc[i][j]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = c0 + tx * 4 + j;
+            if (col < n_q && acc[i][j] > best[i]) best[i] = acc[i][j], best_j[i] = col;
+          }
+      }
+      // reduce over the 16 threads (tx) that share rows ty*4..ty*4+3: max value, lowest column on ties
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = best[i];
+        int j = best_j[i];
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, v, off, 16);
+          const int oj = __shfl_xor_sync(0xffffffffu, j, off, 16);
+          if (ov > v || (ov == v && oj >= 0 && (j < 0 || oj < j))) v = ov, j = oj;
+        }
+        const int row = ty * 4 + i;
+        if (tx == 0 && item_pair[row] == b) {
+          const size_t o = (size_t)b * a.cap_a + item_row[row];
+          a.out_idx[o] = j;
+          a.out_dist[o] = j >= 0 ? 0.5f * (-1.f * v + 1.f) : INFINITY;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 similarity + running-max / candidate-chunk epilogue
+// ------------------------------------------------------------------------------------------------
+struct TcArgs {
+  const PairMeta* meta;
+  int B, npad_a, npad_q, splits;
+  float* cand_m;
+  int32_t* cand_cnt;
+  uint32_t* cand_chunk;
+  float ambiguity;
+};
+
+template <int KB_ELEMS, int NUM_KB, int STAGES>
+struct TcSmem {
+  static constexpr int kRowBytes = KB_ELEMS * 2;
+  static constexpr int kABlock = kTileM * kRowBytes;            // one (kb, row block) A tile
+  static constexpr int kABytes = kABlock * NUM_KB * kRowBlocks;
+  static constexpr int kQStage = kTileN * kRowBytes;            // one k-block of a query tile
+  static constexpr int kQBytes = kQStage * STAGES;
+  static constexpr int kBarBytes = 8 * (2 * STAGES + 2 + 4) + 16;
+  static constexpr int kTotal = 1024 /*align slack*/ + kABytes + kQBytes + kBarBytes;
+};
+
+__device__ __forceinline__ float max8(const uint32_t* v) {
+  float m = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+  m = fmaxf(fmaxf(m, __uint_as_float(v[3])), __uint_as_float(v[4]));
+  m = fmaxf(fmaxf(m, __uint_as_float(v[5])), __uint_as_float(v[6]));
+  return fmaxf(m, __uint_as_float(v[7]));
+}
+
+template <int KB_ELEMS, int NUM_KB, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_q, TcArgs args) {
+  using L = TcSmem<KB_ELEMS, NUM_KB, STAGES>;
+  constexpr int kRowBytes = L::kRowBytes;
+  constexpr int kKSteps = KB_ELEMS / 16;  // UMMA_K = 16 for 16-bit operands
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kTileM, kTileN, /*fp16*/ 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_q = smem + L::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_q + L::kQBytes);
+  uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* a_full = bars + 2 * STAGES;  // A tile landed
+  uint64_t* a_empty = a_full + 1;        // all MMAs of the task retired: A may be overwritten
+  uint64_t* t_full = a_empty + 1;        // [2] accumulator ready
+  uint64_t* t_empty = t_full + 2;        // [2] accumulator drained
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_q);
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_base_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int rb_per_pair = args.npad_a / kCtaRows;
+  const int total_tasks = args.B * rb_per_pair * args.splits;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, task_iter = 0;
+      for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
+        const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
+        const PairMeta pm = args.meta[b];
+        if (rb * kCtaRows >= pm.n_a || pm.n_q <= 0) continue;
+        const int tiles = (pm.n_q + kTileN - 1) / kTileN;
+        const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
+        if (j0 >= j1) continue;
+        ptx::mbar_wait(a_empty, (task_iter & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full, L::kABytes);
+#pragma unroll
+        for (int kb = 0; kb < NUM_KB; ++kb)
+#pragma unroll
+          for (int r = 0; r < kRowBlocks; ++r)
+            ptx::tma_load_2d(smem_a + (kb * kRowBlocks + r) * L::kABlock, &tm_a, a_full, kb * KB_ELEMS,
+                             b * args.npad_a + rb * kCtaRows + r * kTileM);
+        for (int j = j0; j < j1; ++j) {
+          for (int kb = 0; kb < NUM_KB; ++kb) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[stage], L::kQStage);
+            ptx::tma_load_2d(smem_q + stage * L::kQStage, &tm_q, &full[stage], kb * KB_ELEMS, b * args.npad_q + j * kTileN);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+        ++task_iter;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    uint32_t stage = 0, phase = 0, task_iter = 0, tile_iter = 0;
+    for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
+      const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
+      const PairMeta pm = args.meta[b];
+      if (rb * kCtaRows >= pm.n_a || pm.n_q <= 0) continue;
+      const int tiles = (pm.n_q + kTileN - 1) / kTileN;
+      const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
+      if (j0 >= j1) continue;
+      ptx::mbar_wait(a_full, task_iter & 1);
+      for (int j = j0; j < j1; ++j) {
+        const uint32_t buf = tile_iter & 1;
+        ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t q_addr = ptx::smem_u32(smem_q + stage * L::kQStage);
+#pragma unroll
+            for (int r = 0; r < kRowBlocks; ++r) {
+              const uint32_t a_addr = ptx::smem_u32(smem_a + (kb * kRowBlocks + r) * L::kABlock);
+              const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * kTileN) + r * kTileN;
+#pragma unroll
+              for (int k = 0; k < kKSteps; ++k) {
+                const uint64_t da = ptx::make_smem_desc_kmajor(a_addr + k * 32, kRowBytes);
+                const uint64_t dq = ptx::make_smem_desc_kmajor(q_addr + k * 32, kRowBytes);
+                ptx::umma_f16(d_tmem, da, dq, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit(&empty[stage]);                       // smem slot reusable when these MMAs retire
+            if (kb == NUM_KB - 1) ptx::umma_commit(&t_full[buf]);  // accumulator complete
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        ++tile_iter;
+      }
+      if (lane == 0) ptx::umma_commit(a_empty);
+      __syncwarp();
+      ++task_iter;
+    }
+  } else {
+    // ============================ epilogue (8 warps) ============================
+    const int ew = warp - 2;               // 0..7
+    const int rblk = ew >> 2;              // which 128-row block of the CTA tile
+    const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
+    const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
+      const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
+      const PairMeta pm = args.meta[b];
+      if (rb * kCtaRows >= pm.n_a || pm.n_q <= 0) continue;
+      const int tiles = (pm.n_q + kTileN - 1) / kTileN;
+      const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
+      const int row = rb * kCtaRows + row_in_cta;
+      const bool row_ok = row < pm.n_a;
+      const size_t slot = ((size_t)b * args.splits + s) * args.npad_a + row;
+      if (j0 >= j1) {
+        // this split owns no tile (more splits than tiles): publish an empty list
+        if (row_ok) args.cand_m[slot] = -INFINITY, args.cand_cnt[slot] = 0;
+        continue;
+      }
+      uint32_t* my_list = args.cand_chunk + slot * kCandCap;
+      float m_run = -INFINITY;
+      float thr = row_ok ? -INFINITY : INFINITY;  // rows beyond n_a never record anything
+      int cnt = 0;
+      for (int j = j0; j < j1; ++j) {
+        const uint32_t buf = tile_iter & 1;
+        ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * kTileN) + rblk * kTileN;
+        const int col_base = j * kTileN;
+        const bool ragged = col_base + kTileN > pm.n_q;
+#pragma unroll
+        for (int g = 0; g < kTileN / 32; ++g) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + g * 32, v);
+          ptx::tmem_ld_wait();
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col_base + g * 32 + i >= pm.n_q) v[i] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int c = 0; c < 32 / kChunk; ++c) {
+            const float cm = max8(v + c * kChunk);
+            if (cm >= thr) {
+              if (cm > m_run + args.ambiguity) cnt = 0;  // every earlier candidate is now out of range
+              if (cnt < kCandCap) my_list[cnt] = static_cast<uint32_t>((col_base + g * 32) / kChunk + c);
+              ++cnt;
+              m_run = fmaxf(m_run, cm);
+              thr = m_run - args.ambiguity;
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+        ++tile_iter;
+      }
+      if (row_ok) args.cand_m[slot] = m_run, args.cand_cnt[slot] = cnt;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// refine: exact fp32 score of every column of every listed chunk; one warp per anchor row
+// ------------------------------------------------------------------------------------------------
+struct RefineArgs {
+  const float* rows32_a;
+  const float* rows32_q;
+  const PairMeta* meta;
+  const float* cand_m;
+  const int32_t* cand_cnt;
+  const uint32_t* cand_chunk;
+  int B, npad_a, npad_q, D4, splits, cap_a;
+  float ambiguity;
+  int32_t* out_idx;
+  float* out_dist;
+  int32_t* overflow_rows;      // packed b * npad_a + r
+  int32_t* overflow_count;     // device counter
+  unsigned long long* stats;   // [0] rows refined, [1] chunks scored, [2] overflow rows
+};
+
+__global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int col_in_chunk = lane >> 2, part = lane & 3;
+  const int nvec = a.D4 >> 2;
+  unsigned long long n_rows = 0, n_chunks = 0, n_over = 0;
+  for (int item = wid; item < a.B * a.npad_a; item += nwarps) {
+    const int b = item / a.npad_a, r = item - b * a.npad_a;
+    const PairMeta pm = a.meta[b];
+    if (r >= pm.n_a) {
+      continue;
+    }
+    const size_t o = (size_t)b * a.cap_a + r;
+    if (pm.n_q <= 0) {
+      if (lane == 0) a.out_idx[o] = -1, a.out_dist[o] = INFINITY;
+      continue;
+    }
+    float m_all = -INFINITY;
+    bool overflow = false;
+    for (int s = 0; s < a.splits; ++s) {
+      const size_t slot = ((size_t)b * a.splits + s) * a.npad_a + r;
+      m_all = fmaxf(m_all, a.cand_m[slot]);
+      overflow |= a.cand_cnt[slot] > kCandCap;
+    }
+    if (overflow) {
+      if (lane == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = item;
+      ++n_over;
+      continue;
+    }
+    ++n_rows;
+    const float4* arow = reinterpret_cast<const float4*>(a.rows32_a + ((size_t)b * a.npad_a + r) * a.D4);
+    float best = -INFINITY;
+    int best_j = 0x7fffffff;
+    for (int s = 0; s < a.splits; ++s) {
+      const size_t slot = ((size_t)b * a.splits + s) * a.npad_a + r;
+      if (a.cand_m[slot] < m_all - a.ambiguity) continue;  // nothing in this split can win
+      const int cnt = a.cand_cnt[slot];
+      for (int e = 0; e < cnt; ++e) {
+        const int col = (int)a.cand_chunk[slot * kCandCap + e] * kChunk + col_in_chunk;
+        float acc = 0.f;
+        if (col < pm.n_q) {
+          const float4* qrow = reinterpret_cast<const float4*>(a.rows32_q + ((size_t)b * a.npad_q + col) * a.D4);
+          for (int i = part; i < nvec; i += 4) {
+            const float4 x = __ldg(arow + i), y = __ldg(qrow + i);
+            acc = fmaf(x.x, y.x, acc);
+            acc = fmaf(x.y, y.y, acc);
+            acc = fmaf(x.z, y.z, acc);
+            acc = fmaf(x.w, y.w, acc);
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (col < pm.n_q && (acc > best || (acc == best && col < best_j))) best = acc, best_j = col;
+        ++n_chunks;
+      }
+    }
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+      if (ov > best || (ov == best && oj < best_j)) best = ov, best_j = oj;
+    }
+    if (lane == 0) {
+      a.out_idx[o] = best_j;
+      a.out_dist[o] = 0.5f * (-1.f * best + 1.f);
+    }
+  }
+  if (lane == 0 && a.stats) {
+    if (n_rows) atomicAdd(a.stats + 0, n_rows);
+    if (n_chunks) atomicAdd(a.stats + 1, n_chunks);
+    if (n_over) atomicAdd(a.stats + 2, n_over);
+  }
+}
+
+__global__ void fill_invalid_kernel(int32_t* out_idx, float* out_dist, const PairMeta* meta, int B, int cap_a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cap_a) return;
+  const int b = i / cap_a, r = i - b * cap_a;
+  if (r >= meta[b].n_a) out_idx[i] = -1, out_dist[i] = INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask -> ordered pixel-id list (torch.nonzero order)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) mask_to_roi_kernel(const int32_t* mask, int HW, int value, int32_t* roi, int32_t* n_out) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t* m = mask + (size_t)b * HW;
+  int32_t* out = roi + (size_t)b * HW;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < HW; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool hit = i < HW && m[i] == value;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (hit) out[off + __popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_tot[w];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_out[b] = base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+static int make_rows_tensor_map(oryon_handle* h, CUtensorMap* tm, const void* base, int rows, int dpad, int kb_elems, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)dpad, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dpad * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kb_elems, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = kb_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d dpad=%d)", (int)r, rows, dpad);
+    return ORYON_ERR_CUDA;
+  }
+  return ORYON_OK;
+}
+
+template <int KB_ELEMS, int NUM_KB, int STAGES>
+static int launch_tc(oryon_handle* h, const CUtensorMap& tma, const CUtensorMap& tmq, const TcArgs& args, int grid, cudaStream_t st) {
+  using L = TcSmem<KB_ELEMS, NUM_KB, STAGES>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  auto kern = match_tc_kernel<KB_ELEMS, NUM_KB, STAGES>;
+  ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  h->span_begin(KID_MATCH_TC, st);
+  kern<<<grid, kTcThreads, L::kTotal, st>>>(tma, tmq, args);
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, int D, int HW_a, int HW_q, const int32_t* roi_a,
+              const int32_t* roi_q, const int32_t* n_a, const int32_t* n_q, int cap_a, int cap_q, int mode, int32_t* out_idx,
+              float* out_dist, cudaStream_t st) {
+  ORYON_REQUIRE(h && feat_a && feat_q && out_idx && out_dist, "oryon_match_nn: null argument");
+  ORYON_REQUIRE(B > 0 && D > 0 && HW_a > 0 && HW_q > 0, "oryon_match_nn: B, D, HW must be positive");
+  ORYON_REQUIRE(D <= 256, "oryon_match_nn: D=%d not supported (max 256)", D);
+  ORYON_REQUIRE((roi_a == nullptr) == (n_a == nullptr) && (roi_q == nullptr) == (n_q == nullptr),
+                "oryon_match_nn: roi_x and n_x must both be given or both be NULL");
+  ORYON_REQUIRE(mode == ORYON_MATCH_TC_REFINED || mode == ORYON_MATCH_EXACT_FP32, "oryon_match_nn: unknown mode %d", mode);
+  if (!roi_a) ORYON_REQUIRE(cap_a >= HW_a, "oryon_match_nn: dense anchor list needs cap_a >= HW_a");
+  if (!roi_q) cap_q = HW_q;
+
+  std::vector<PairMeta> meta(B);
+  int max_a = 0, max_q = 0;
+  for (int b = 0; b < B; ++b) {
+    meta[b].n_a = n_a ? n_a[b] : HW_a;
+    meta[b].n_q = n_q ? n_q[b] : HW_q;
+    ORYON_REQUIRE(meta[b].n_a >= 0 && meta[b].n_a <= cap_a && meta[b].n_q >= 0 && meta[b].n_q <= cap_q,
+                  "oryon_match_nn: pair %d list lengths (%d, %d) outside [0, cap]", b, meta[b].n_a, meta[b].n_q);
+    max_a = std::max(max_a, meta[b].n_a);
+    max_q = std::max(max_q, meta[b].n_q);
+  }
+  h->last_launches = 0;
+  ORYON_CUDA_CHECK(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = h->pair_meta.reserve(sizeof(PairMeta) * B, st))) return rc;
+  if ((rc = h->counters.reserve(256, st))) return rc;
+  ORYON_CUDA_CHECK(cudaMemcpyAsync(h->pair_meta.ptr, meta.data(), sizeof(PairMeta) * B, cudaMemcpyHostToDevice, st));
+  ORYON_CUDA_CHECK(cudaMemsetAsync(h->counters.ptr, 0, 256, st));
+  const PairMeta* d_meta = h->pair_meta.as<PairMeta>();
+  // counters: [0] overflow count (int32), bytes 64.. : stats (3 x u64)
+  int32_t* d_overflow_count = h->counters.as<int32_t>();
+  unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(h->counters.as<char>() + 64);
+
+  {
+    const int blocks = (B * cap_a + 255) / 256;
+    fill_invalid_kernel<<<blocks, 256, 0, st>>>(out_idx, out_dist, d_meta, B, cap_a);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    ++h->last_launches;
+  }
+  if (max_a == 0) return ORYON_OK;
+
+  const int D4 = round_up(D, 4);
+  const bool sw64 = D <= 32;
+  const int kb_elems = sw64 ? 32 : 64;
+  const int Dpad = round_up(D, kb_elems);
+  const int num_kb = Dpad / kb_elems;
+  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), kTileN);
+
+  if ((rc = h->rows16_a.reserve((size_t)B * npad_a * Dpad * 2, st))) return rc;
+  if ((rc = h->rows16_q.reserve((size_t)B * npad_q * Dpad * 2, st))) return rc;
+  if ((rc = h->rows32_a.reserve((size_t)B * npad_a * D4 * 4, st))) return rc;
+  if ((rc = h->rows32_q.reserve((size_t)B * npad_q * D4 * 4, st))) return rc;
+
+  {
+    PrepArgs pa;
+    pa.feat[0] = feat_a, pa.feat[1] = feat_q;
+    pa.roi[0] = roi_a, pa.roi[1] = roi_q;
+    pa.hw[0] = HW_a, pa.hw[1] = HW_q;
+    pa.cap[0] = cap_a, pa.cap[1] = cap_q;
+    pa.npad[0] = npad_a, pa.npad[1] = npad_q;
+    pa.rows16[0] = h->rows16_a.as<__half>(), pa.rows16[1] = h->rows16_q.as<__half>();
+    pa.rows32[0] = h->rows32_a.as<float>(), pa.rows32[1] = h->rows32_q.as<float>();
+    pa.meta = d_meta;
+    pa.D = D, pa.D4 = D4, pa.Dpad = Dpad;
+    const dim3 grid((std::max(max_a, max_q) + 31) / 32, B, 2);
+    const size_t smem = (size_t)D * 33 * sizeof(float);
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->span_begin(KID_PREP, st);
+    prep_rows_kernel<<<grid, 256, smem, st>>>(pa);
+    h->span_end(st);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    ++h->last_launches;
+  }
+
+  ExactArgs ea;
+  ea.rows32_a = h->rows32_a.as<float>(), ea.rows32_q = h->rows32_q.as<float>();
+  ea.meta = d_meta;
+  ea.npad_a = npad_a, ea.npad_q = npad_q, ea.D4 = D4, ea.cap_a = cap_a;
+  ea.out_idx = out_idx, ea.out_dist = out_dist;
+
+  if (mode == ORYON_MATCH_EXACT_FP32 || max_q == 0) {
+    ea.row_list = nullptr, ea.n_items_dev = nullptr, ea.n_items_host = B * npad_a;
+    const int blocks = std::min((B * npad_a + 63) / 64, h->sm_count * 8);
+    h->span_begin(KID_EXACT, st);
+    exact_rows_kernel<<<blocks, 256, 0, st>>>(ea);
+    h->span_end(st);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    ++h->last_launches;
+    return ORYON_OK;
+  }
+
+  // ---- tensor-core pass ----
+  const int rb_per_pair = npad_a / kCtaRows;
+  const int tiles_max = npad_q / kTileN;
+  int splits = 1;
+  if (B * rb_per_pair < h->sm_count) splits = std::min({kMaxSplits, tiles_max, (h->sm_count + B * rb_per_pair - 1) / (B * rb_per_pair)});
+  splits = std::max(splits, 1);
+  const size_t slots = (size_t)B * splits * npad_a;
+  if ((rc = h->cand.reserve(slots * (4 + 4 + 4 * kCandCap), st))) return rc;
+  if ((rc = h->overflow_rows.reserve((size_t)B * npad_a * 4, st))) return rc;
+  TcArgs ta;
+  ta.meta = d_meta;
+  ta.B = B, ta.npad_a = npad_a, ta.npad_q = npad_q, ta.splits = splits;
+  ta.cand_m = h->cand.as<float>();
+  ta.cand_cnt = reinterpret_cast<int32_t*>(ta.cand_m + slots);
+  ta.cand_chunk = reinterpret_cast<uint32_t*>(ta.cand_cnt + slots);
+  ta.ambiguity = kAmbiguity;
+
+  CUtensorMap tma, tmq;
+  if ((rc = make_rows_tensor_map(h, &tma, h->rows16_a.ptr, B * npad_a, Dpad, kb_elems, kTileM))) return rc;
+  if ((rc = make_rows_tensor_map(h, &tmq, h->rows16_q.ptr, B * npad_q, Dpad, kb_elems, kTileN))) return rc;
+  const int grid = std::min(h->sm_count, B * rb_per_pair * splits);
+  if (sw64) {
+    rc = launch_tc<32, 1, 8>(h, tma, tmq, ta, grid, st);
+  } else {
+    switch (num_kb) {
+      case 1: rc = launch_tc<64, 1, 8>(h, tma, tmq, ta, grid, st); break;
+      case 2: rc = launch_tc<64, 2, 8>(h, tma, tmq, ta, grid, st); break;
+      case 3: rc = launch_tc<64, 3, 6>(h, tma, tmq, ta, grid, st); break;
+      default: rc = launch_tc<64, 4, 5>(h, tma, tmq, ta, grid, st); break;
+    }
+  }
+  if (rc) return rc;
+  ++h->last_launches;
+
+  RefineArgs ra;
+  ra.rows32_a = ea.rows32_a, ra.rows32_q = ea.rows32_q;
+  ra.meta = d_meta;
+  ra.cand_m = ta.cand_m, ra.cand_cnt = ta.cand_cnt, ra.cand_chunk = ta.cand_chunk;
+  ra.B = B, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = splits, ra.cap_a = cap_a;
+  ra.ambiguity = kAmbiguity;
+  ra.out_idx = out_idx, ra.out_dist = out_dist;
+  ra.overflow_rows = h->overflow_rows.as<int32_t>();
+  ra.overflow_count = d_overflow_count;
+  ra.stats = d_stats;
+  {
+    const int warps_needed = B * npad_a;
+    const int blocks = std::min((warps_needed + 7) / 8, h->sm_count * 16);
+    h->span_begin(KID_REFINE, st);
+    refine_rows_kernel<<<blocks, 256, 0, st>>>(ra);
+    h->span_end(st);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    ++h->last_launches;
+  }
+  {
+    ea.row_list = ra.overflow_rows, ea.n_items_dev = d_overflow_count, ea.n_items_host = 0;
+    h->span_begin(KID_EXACT, st);
+    exact_rows_kernel<<<h->sm_count * 2, 256, 0, st>>>(ea);
+    h->span_end(st);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    ++h->last_launches;
+  }
+  return ORYON_OK;
+}
+
+int run_mask_to_roi(oryon_handle* h, const int32_t* mask, int B, int HW, int value, int32_t* roi_out, int32_t* n_out, cudaStream_t st) {
+  ORYON_REQUIRE(h && mask && roi_out && n_out && B > 0 && HW > 0, "oryon_mask_to_roi: bad argument");
+  ORYON_CUDA_CHECK(cudaSetDevice(h->device));
+  h->span_begin(KID_MASK_ROI, st);
+  mask_to_roi_kernel<<<B, 1024, 0, st>>>(mask, HW, value, roi_out, n_out);
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+int read_stats(oryon_handle* h, int64_t stats[4], cudaStream_t st) {
+  ORYON_REQUIRE(h && stats, "oryon_match_last_stats: null argument");
+  unsigned long long s[3] = {0, 0, 0};
+  if (h->counters.ptr) {
+    ORYON_CUDA_CHECK(cudaMemcpyAsync(s, h->counters.as<char>() + 64, sizeof(s), cudaMemcpyDeviceToHost, st));
+    ORYON_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  stats[0] = (int64_t)s[0], stats[1] = (int64_t)s[1], stats[2] = (int64_t)s[2], stats[3] = h->last_launches;
+  return ORYON_OK;
+}
+
+}  // namespace match
+}  // namespace oryon

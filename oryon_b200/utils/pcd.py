@@ -1,0 +1,199 @@
+"""Mirror of the reference ``utils/pcd.py`` for the hot path: ``nn_correspondences`` (:177-216) and
+``lift_pcd`` (:35-81), same names, argument meaning and error behaviour, computed by
+liboryon_b200.so on the GPU.
+
+What stays in torch is what the reference itself leaves to the *caller's* generator and ordering:
+the two ``torch.multinomial`` draws (utils/misc.py:242-254) and row selection by the drawn indices.
+ROI enumeration (``torch.nonzero(mask == 1)`` order), the all-pairs inverted-cosine distance, the
+row argmin and the threshold are computed by the library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .._torch_glue import as_device, device_of, ptr, stream_ptr
+
+_DEPTH_DTYPES = {torch.int32: _lib.DEPTH_I32, torch.float32: _lib.DEPTH_F32, torch.int16: _lib.DEPTH_I16,
+                 torch.uint16: _lib.DEPTH_U16}
+
+
+def torch_sample_select(t: Tensor, n: int) -> Tensor:
+    """Exactly ``n`` row indices of ``t``; replacement only if ``n > N`` (reference utils/misc.py:242-254).
+    The draw uses the default generator of ``t.device`` exactly as the reference's call does."""
+    N = t.shape[0]
+    uniform_dist = torch.ones(N, dtype=float).to(t.device)
+    return torch.multinomial(uniform_dist, n, replacement=bool(n > N)).to(t.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# library calls
+# ------------------------------------------------------------------------------------------------
+
+
+def mask_to_roi(mask: Tensor, value: int = 1) -> Tuple[Tensor, Tensor]:
+    """``[B,H,W]`` (or ``[H,W]``) integer masks on the GPU -> ``(pixel_ids int32 [B,HW], counts int32 [B])``;
+    ``pixel_ids[b,:counts[b]]`` are the flattened ``y*W+x`` of ``mask[b] == value`` in ``torch.nonzero`` order."""
+    dev = device_of(mask)
+    m = as_device(mask, dev, torch.int32)
+    if m.dim() == 2:
+        m = m[None]
+    B, HW = m.shape[0], m.shape[1] * m.shape[2]
+    roi = torch.empty(B, HW, dtype=torch.int32, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.oryon_mask_to_roi(_lib.handle(dev.index), ptr(m), B, HW, int(value), ptr(roi), ptr(cnt), stream_ptr(dev)))
+    return roi, cnt
+
+
+def match_nn(feat_a: Tensor, feat_q: Tensor, roi_a: Optional[Tensor] = None, roi_q: Optional[Tensor] = None,
+             n_a: Optional[Sequence[int]] = None, n_q: Optional[Sequence[int]] = None, *,
+             mode: int = _lib.MATCH_TC_REFINED, out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """Row-wise nearest neighbour under ``0.5*(1-cos)`` for B pairs at once (``oryon_match_nn``).
+
+    ``feat_a/q``: float32 ``[B,D,H,W]`` (or ``[B,D,HW]``) on the GPU.  ``roi_x``: int32 ``[B,cap]`` pixel-id
+    lists with host lengths ``n_x`` or ``None`` for every pixel.  Returns ``(idx int32 [B,cap_a],
+    dist float32 [B,cap_a])``: position in the pair's query list of the nearest neighbour (lowest on
+    ties) and its distance; ``-1`` / ``inf`` beyond ``n_a[b]``."""
+    dev = device_of(feat_a, feat_q)
+    fa, fq = as_device(feat_a, dev, torch.float32), as_device(feat_q, dev, torch.float32)
+    if fa.dim() < 3 or fq.dim() < 3 or fa.shape[:2] != fq.shape[:2]:
+        raise ValueError(f"match_nn: feature maps must be [B,D,...] with equal B and D, got {tuple(fa.shape)} / {tuple(fq.shape)}")
+    B, D = fa.shape[0], fa.shape[1]
+    hw_a, hw_q = fa[0, 0].numel(), fq[0, 0].numel()
+    if (roi_a is None) != (n_a is None) or (roi_q is None) != (n_q is None):
+        raise ValueError("match_nn: roi_x and n_x go together")
+    cap_a = hw_a if roi_a is None else roi_a.shape[1]
+    cap_q = hw_q if roi_q is None else roi_q.shape[1]
+    if roi_a is not None:
+        roi_a = as_device(roi_a, dev, torch.int32)
+    if roi_q is not None:
+        roi_q = as_device(roi_q, dev, torch.int32)
+    na = None if n_a is None else (ctypes.c_int32 * B)(*[int(v) for v in n_a])
+    nq = None if n_q is None else (ctypes.c_int32 * B)(*[int(v) for v in n_q])
+    if out is None:
+        idx = torch.empty(B, cap_a, dtype=torch.int32, device=dev)
+        dist = torch.empty(B, cap_a, dtype=torch.float32, device=dev)
+    else:
+        idx, dist = out
+        if idx.shape != (B, cap_a) or dist.shape != (B, cap_a) or idx.dtype != torch.int32 or dist.dtype != torch.float32 \
+                or idx.device != dev or dist.device != dev or not idx.is_contiguous() or not dist.is_contiguous():
+            raise ValueError("match_nn: bad `out` buffers")
+    lib = _lib.load()
+    _lib.check(lib.oryon_match_nn(_lib.handle(dev.index), ptr(fa), ptr(fq), B, D, hw_a, hw_q, ptr(roi_a), ptr(roi_q), na, nq,
+                                  cap_a, cap_q, int(mode), ptr(idx), ptr(dist), stream_ptr(dev)))
+    return idx, dist
+
+
+def match_last_stats(device: Optional[torch.device] = None) -> dict:
+    dev = device or device_of()
+    s = (ctypes.c_int64 * 4)()
+    _lib.check(_lib.load().oryon_match_last_stats(_lib.handle(dev.index), s, stream_ptr(dev)))
+    return dict(rows_refined=s[0], chunks_rescored=s[1], rows_overflowed=s[2], kernels_launched=s[3])
+
+
+# ------------------------------------------------------------------------------------------------
+# reference interface
+# ------------------------------------------------------------------------------------------------
+
+
+def nn_correspondences(feats1: Tensor, feats2: Tensor, mask1: Tensor, mask2: Tensor, threshold: float, max_corrs: int,
+                       subsample_source: Optional[int], corrs_device: str = "cpu", *, return_debug: bool = False):
+    """Finds matches between two ``[D,H,W]`` feature maps; returns ``int64 [max_corrs,4]`` rows
+    ``(y1,x1,y2,x2)`` on ``feats1.device`` or ``None`` when at most one row passes ``threshold``
+    (reference utils/pcd.py:177-216).
+
+    ``corrs_device`` keeps its one observable meaning, the device whose default generator serves the two
+    ``multinomial`` draws ('cpu' in the reference configuration, configs/config.yaml:7); the distance
+    arithmetic always runs on the GPU and equals a float32 evaluation (ORYON_MATCH_TC_REFINED), which is
+    what the reference computes for 'cpu' and is more precise than its float16 'cuda' branch."""
+    orig_device = feats1.device
+    dev = device_of(feats1, feats2, mask1, mask2)
+    if feats1.dim() != 3 or feats2.dim() != 3 or feats1.shape[0] != feats2.shape[0]:
+        raise ValueError("nn_correspondences: feature maps must be [D,H,W] with equal D")
+    H1, W1 = feats1.shape[1:]
+    H2, W2 = feats2.shape[1:]
+    pix1, c1 = mask_to_roi(as_device(mask1, dev).reshape(1, H1, W1))
+    pix2, c2 = mask_to_roi(as_device(mask2, dev).reshape(1, H2, W2))
+    n1, n2 = (int(v) for v in torch.stack((c1[0], c2[0])).tolist())  # the reference syncs here too (nonzero)
+    pix1, pix2 = pix1[0, :n1], pix2[0, :n2]
+
+    if subsample_source is not None and n1 > subsample_source:
+        probe = torch.empty(n1, 0, device=corrs_device)
+        idxs = torch_sample_select(probe, subsample_source)
+        pix1 = pix1[idxs.to(dev)]
+        n1 = int(subsample_source)
+    if n1 == 0 or n2 == 0:
+        # torch.amin over an empty dimension raises in the reference (callers gate on is_detection_valid)
+        raise RuntimeError("nn_correspondences: empty mask (amin over an empty dimension)")
+
+    idx, dist = match_nn(feats1[None], feats2[None], pix1[None].contiguous(), pix2[None].contiguous(), [n1], [n2])
+    idx, dist = idx[0, :n1], dist[0, :n1]
+    valid = torch.nonzero(dist < threshold).squeeze(1)
+    final_corrs = None
+    if valid.shape[0] > 1:
+        p1 = pix1[valid].long()
+        p2 = pix2[idx[valid].long()].long()
+        final = torch.stack((p1 // W1, p1 % W1, p2 // W2, p2 % W2), dim=1)
+        probe = torch.empty(final.shape[0], 0, device=corrs_device)
+        sel = torch_sample_select(probe, max_corrs)
+        final_corrs = final[sel.to(dev)].to(orig_device)
+    if return_debug:
+        return final_corrs, dict(pix1=pix1, pix2=pix2, nn_idx=idx, min_dist=dist, valid=valid)
+    return final_corrs
+
+
+def lift_pcd(depth: Tensor, camera: Tensor, xy_idxs: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
+    """Pin-hole lifting of a depth image ``[H,W,C]`` to a point cloud ``[n,3]`` in depth units (reference
+    utils/pcd.py:35-81).  With ``xy_idxs = (x, y)`` only those pixels are lifted; without, every pixel in
+    row-major order.  Extra channels (RGB point clouds, C > 1) are not part of the hot path."""
+    if depth.dim() != 3:
+        raise ValueError("lift_pcd: depth must be [H,W,C]")
+    H, W, C = depth.shape
+    if C != 1:
+        raise NotImplementedError("lift_pcd: only single-channel depth is on the inference path")
+    dev = device_of(depth)
+    d = depth[:, :, 0]
+    if d.dtype not in _DEPTH_DTYPES:
+        d = d.to(torch.float32)
+    d = as_device(d, dev)
+    if xy_idxs is None:
+        xs = torch.arange(W, device=dev, dtype=torch.int64).repeat(H)
+        ys = torch.arange(H, device=dev, dtype=torch.int64).repeat_interleave(W)
+    else:
+        xs, ys = as_device(xy_idxs[0], dev, torch.int64), as_device(xy_idxs[1], dev, torch.int64)
+    n = xs.numel()
+    cam = (ctypes.c_double * 9)(*[float(v) for v in camera.reshape(9).tolist()])
+    out = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.oryon_lift_pcd(_lib.handle(dev.index), ptr(d), _DEPTH_DTYPES[d.dtype], H, W, cam, ptr(xs), ptr(ys), n, ptr(out),
+                                  stream_ptr(dev)))
+    return out
+
+
+def corrs_to_pcd(corrs: Tensor, depth_a: Tensor, depth_q: Tensor, camera_a: Tensor, camera_q: Tensor,
+                 featmap_size: Sequence[int], size_a: Sequence[int], size_q: Sequence[int]) -> Tuple[Tensor, Tensor]:
+    """Fused form of reference pipeline.py:447-460: scale featmap-space correspondences to raw-frame pixels,
+    drop out-of-bounds rows, truncate, lift both views and convert to metres -> ``(pcd_a, pcd_q) [m,3]``."""
+    dev = device_of(depth_a, depth_q, corrs)
+    c = as_device(corrs, dev, torch.int64)
+    da, dq = depth_a.squeeze(), depth_q.squeeze()
+    if da.dtype != dq.dtype or da.dtype not in _DEPTH_DTYPES:
+        da, dq = da.to(torch.float32), dq.to(torch.float32)
+    da, dq = as_device(da, dev), as_device(dq, dev)
+    n = c.shape[0]
+    ka = (ctypes.c_double * 9)(*[float(v) for v in camera_a.reshape(9).tolist()])
+    kq = (ctypes.c_double * 9)(*[float(v) for v in camera_q.reshape(9).tolist()])
+    pa = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    pq = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    nv = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.oryon_corrs_to_pcd(_lib.handle(dev.index), ptr(c), n, int(featmap_size[0]), int(featmap_size[1]), ptr(da), ptr(dq),
+                                      _DEPTH_DTYPES[da.dtype], int(size_a[0]), int(size_a[1]), int(size_q[0]), int(size_q[1]), ka, kq,
+                                      ptr(pa), ptr(pq), ptr(nv), stream_ptr(dev)))
+    m = int(nv.item())
+    return pa[:m], pq[:m]
