@@ -71,7 +71,8 @@ int64_t oryon_workspace_bytes(const oryon_handle* h);
  * by CUDA events recorded on the caller's stream.  oryon_profile_read waits for the recorded events,
  * returns per kernel id the summed duration (ms) and launch count since the last read, and clears them.
  * Kernel ids: 0 prep_rows, 1 match_tc (tcgen05 similarity + argmax epilogue), 2 refine_rows,
- * 3 exact_rows, 4 mask_to_roi, 5 lift/corrs_to_pcd; further ids are listed in DESIGN.md. */
+ * 3 exact_rows, 4 mask_to_roi, 5 lift/corrs_to_pcd, 6 pointdsc SC matrix, 7 pointdsc NonLocalNet,
+ * 8 pointdsc seeds/kNN/power/Kabsch/fitness, 9 pointdsc refinement; further ids are listed in DESIGN.md. */
 int oryon_profile_enable(oryon_handle* h, int enable);
 int oryon_profile_read(oryon_handle* h, double* total_ms, int64_t* launches, int n_ids);
 
@@ -127,6 +128,63 @@ int oryon_corrs_to_pcd(oryon_handle* h, const int64_t* corrs, int n, int feat_h,
  *   xs, ys DEVICE int64 [n]; out DEVICE float32 [n][3] in depth units (the caller divides by 1000). */
 int oryon_lift_pcd(oryon_handle* h, const void* depth, int depth_dtype, int H, int W, const double* cam,
                    const int64_t* xs, const int64_t* ys, int n, float* out, void* stream);
+
+/* ---- a11: PointDSC registration ------------------------------------------------------------
+ * Replaces utils/pointdsc/init.py:10-29 get_pointdsc_pose + models/pointdsc/PointDSC.py:128-197
+ * PointDSC.forward in test mode (spatial-consistency matrix :150-153, NonLocalNet :48-77, confidence MLP
+ * :171, pick_seeds :199-217, cal_seed_trans :234-336 with knn common.py:48-69, power iteration :338-358,
+ * weighted Kabsch common.py:7-45 -- the 3x3 SVD runs on the device, not through H.cpu() --, hypothesis
+ * scoring, post_refinement :403-438), for P independent correspondence sets in one call.
+ *
+ * oryon_pointdsc_config mirrors the constructor arguments the reference reads from the snapshot's
+ * config.json (utils/pointdsc/init.py:37-50).  `nms_radius` is what init.py:49 feeds from
+ * config.inlier_threshold; `inlier_threshold` is the model attribute, which init.py leaves at the
+ * constructor default 0.10 (PointDSC.py:87); sigma is the learnt nn.Parameter `sigma` (state_dict),
+ * sigma_d the buffer `sigma_spat`. */
+typedef struct {
+  int32_t in_dim;          /* 6 */
+  int32_t num_layers;      /* 12 in the 3DMatch release */
+  int32_t num_channels;    /* 128 (the kernels are specialised for it) */
+  int32_t num_iterations;  /* power iterations, 10 */
+  int32_t k;               /* neighbourhood size, 40 (<= 64) */
+  int32_t reserved;
+  double ratio;            /* seeds = int(n * ratio) */
+  double sigma_d;          /* sigma_spat */
+  double sigma;            /* state_dict['sigma'] */
+  double nms_radius;
+  double inlier_threshold;
+} oryon_pointdsc_config;
+
+/* Loads (replaces) the PointDSC weights of this handle.
+ *   weights  HOST float32, the state_dict tensors flattened and concatenated in this order
+ *            (C = num_channels, H = C/2; BN = weight, bias, running_mean, running_var):
+ *              encoder.layer0.{weight [C][in_dim], bias [C]}
+ *              for i in 0..num_layers-1:
+ *                encoder.blocks.PointCN_layer_i.0.{weight [C][C], bias}, .1 BN [C]
+ *                encoder.blocks.NonLocal_layer_i.fc_message.0.{weight [H][C], bias}, .1 BN [H],
+ *                  .3.{weight [H][H], bias}, .4 BN [H], .6.{weight [C][H], bias}
+ *                encoder.blocks.NonLocal_layer_i.projection_q/.projection_k/.projection_v {weight [C][C], bias}
+ *              classification.0.{weight [32][C], bias}, .2.{weight [32][32], bias}, .4.{weight [1][32], bias}
+ *            Eval-mode BatchNorm is folded into the preceding convolution at load time. */
+int oryon_pointdsc_load(oryon_handle* h, const oryon_pointdsc_config* cfg, const float* weights, int64_t n_floats, void* stream);
+
+/* Optional intermediate outputs for parity tests; every pointer may be NULL.  All DEVICE. */
+typedef struct {
+  float* conf;            /* [P][cap]          confidence logits (PointDSC.py:171) */
+  float* features;        /* [P][cap][C]       L2-normalised correspondence features (:156) */
+  int32_t* seeds;         /* [P][seeds_cap]    seed indices in rank order (:174) */
+  int32_t* fitness;       /* [P][seeds_cap]    inlier count of each seed hypothesis (:331) */
+  int32_t seeds_cap;
+  int32_t reserved;
+  float* initial_trans;   /* [P][16]           best hypothesis before post-refinement (:335) */
+  int32_t* best_seed;     /* [P]               argmax position among the seeds */
+} oryon_pointdsc_debug;
+
+/*   src, tgt   DEVICE float32 [P][cap][3] corresponding 3-D points in metres (pcd1, pcd2 of init.py:10)
+ *   n          HOST   int32 [P] correspondences per pair, 2 <= n[p] <= cap <= 2048, int(n*ratio) >= 1
+ *   out_T      DEVICE float32 [P][16] row-major 4x4 final_trans (PointDSC.py:186) */
+int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t* n, int P, int cap, float* out_T,
+                        const oryon_pointdsc_debug* debug, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,21 @@ MATCH_EXACT_FP32 = 1
 
 DEPTH_I32, DEPTH_F32, DEPTH_I16, DEPTH_U16 = 0, 1, 2, 3
 
+
+
+class PointDSCConfig(ctypes.Structure):
+    """oryon_pointdsc_config"""
+    _fields_ = [("in_dim", c_int32), ("num_layers", c_int32), ("num_channels", c_int32), ("num_iterations", c_int32),
+                ("k", c_int32), ("reserved", c_int32), ("ratio", c_double), ("sigma_d", c_double), ("sigma", c_double),
+                ("nms_radius", c_double), ("inlier_threshold", c_double)]
+
+
+class PointDSCDebug(ctypes.Structure):
+    """oryon_pointdsc_debug"""
+    _fields_ = [("conf", c_void_p), ("features", c_void_p), ("seeds", c_void_p), ("fitness", c_void_p), ("seeds_cap", c_int32),
+                ("reserved", c_int32), ("initial_trans", c_void_p), ("best_seed", c_void_p)]
+
+
 # name -> (restype, argtypes): every symbol include/oryon_b200.h declares
 SIGNATURES = {
     "oryon_abi_version": (c_int, []),
@@ -38,6 +53,9 @@ SIGNATURES = {
                                    c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),
     "oryon_lift_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),
+    "oryon_pointdsc_load": (c_int, [c_void_p, POINTER(PointDSCConfig), c_void_p, c_int64, c_void_p]),
+    "oryon_pointdsc_pose": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p,
+                                    POINTER(PointDSCDebug), c_void_p]),
 }
 
 _lock = threading.Lock()
@@ -104,14 +122,15 @@ def destroy_all() -> None:
         _handles.clear()
 
 
-KERNEL_IDS = {"prep_rows": 0, "match_tc": 1, "refine_rows": 2, "exact_rows": 3, "mask_to_roi": 4, "lift": 5}
+KERNEL_IDS = {"prep_rows": 0, "match_tc": 1, "refine_rows": 2, "exact_rows": 3, "mask_to_roi": 4, "lift": 5,
+              "pointdsc_sc": 6, "pointdsc_net": 7, "pointdsc_seeds": 8, "pointdsc_refine": 9}
 
 
 def profile_enable(device_index: int, enable: bool) -> None:
     check(load().oryon_profile_enable(handle(device_index), int(bool(enable))))
 
 
-def profile_read(device_index: int, n_ids: int = 16):
+def profile_read(device_index: int, n_ids: int = 32):
     """{kernel name or id: (total_ms, launches)} since the last read (waits for the recorded events)."""
     ms = (c_double * n_ids)()
     cnt = (c_int64 * n_ids)()

@@ -58,6 +58,11 @@ int run_lift(oryon_handle*, const void*, int, int, int, const double*, const int
 int run_corrs_to_pcd(oryon_handle*, const int64_t*, int, int, int, const void*, const void*, int, int, int, int, int, const double*,
                      const double*, float*, float*, int32_t*, cudaStream_t);
 }  // namespace lift
+namespace pdsc {
+int load_weights(oryon_handle*, const oryon_pointdsc_config*, const float*, int64_t, cudaStream_t);
+int run_pose(oryon_handle*, const float*, const float*, const int32_t*, int, int, float*, const oryon_pointdsc_debug*, cudaStream_t);
+void destroy_model(oryon_handle*);
+}  // namespace pdsc
 
 }  // namespace oryon
 
@@ -84,7 +89,7 @@ void oryon_handle::span_end(cudaStream_t st) {
 
 int64_t oryon_handle::workspace_bytes() const {
   return (int64_t)(rows16_a.bytes + rows16_q.bytes + rows32_a.bytes + rows32_q.bytes + cand.bytes + counters.bytes +
-                   overflow_rows.bytes + pair_meta.bytes + lift_scratch.bytes);
+                   overflow_rows.bytes + pair_meta.bytes + lift_scratch.bytes + pdsc_ws.bytes);
 }
 
 extern "C" {
@@ -131,6 +136,8 @@ int oryon_destroy(oryon_handle* h) {
   for (auto& s : h->spans) cudaEventDestroy(s.a), cudaEventDestroy(s.b);
   for (auto e : h->free_events) cudaEventDestroy(e);
   h->cand.release(), h->counters.release(), h->overflow_rows.release(), h->pair_meta.release(), h->lift_scratch.release();
+  oryon::pdsc::destroy_model(h);
+  h->pdsc_ws.release();
   delete h;
   return ORYON_OK;
 }
@@ -182,6 +189,15 @@ int oryon_corrs_to_pcd(oryon_handle* h, const int64_t* corrs, int n, int feat_h,
 int oryon_lift_pcd(oryon_handle* h, const void* depth, int depth_dtype, int H, int W, const double* cam, const int64_t* xs,
                    const int64_t* ys, int n, float* out, void* stream) {
   return oryon::lift::run_lift(h, depth, depth_dtype, H, W, cam, xs, ys, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_pointdsc_load(oryon_handle* h, const oryon_pointdsc_config* cfg, const float* weights, int64_t n_floats, void* stream) {
+  return oryon::pdsc::load_weights(h, cfg, weights, n_floats, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t* n, int P, int cap, float* out_T,
+                        const oryon_pointdsc_debug* debug, void* stream) {
+  return oryon::pdsc::run_pose(h, src, tgt, n, P, cap, out_T, debug, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
