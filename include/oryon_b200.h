@@ -186,6 +186,19 @@ typedef struct {
 int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t* n, int P, int cap, float* out_T,
                         const oryon_pointdsc_debug* debug, void* stream);
 
+/* ---- a1-a6 building block: the tensor-core GEMM every linear / convolution / attention-score op of the
+ * backbone runs on (oryon_b200/csrc/gemm.cu), exposed for parity tests and kernel benchmarks.
+ *   out[b][m][n] = residual[b][m][n] + act(alpha * sum_k A[b][m][k] * W[b][n][k] + bias[n])
+ * i.e. torch.nn.functional.linear(A, W, bias) per batch matrix (the form of nn.Linear / nn.Conv1d(k=1) /
+ * nn.MultiheadAttention projections used by models/vlm.py:46-56, models/fusion.py:83-85, ...).
+ *   A DEVICE float32 [batch][M][K], W DEVICE float32 [batch][N][K], bias DEVICE float32 [N] or NULL,
+ *   residual DEVICE float32 [batch][M][N] or NULL, out DEVICE float32 [batch][M][N]
+ *   act: 0 none, 1 QuickGELU x*sigmoid(1.702x) (CLIP), 2 GELU(erf) (timm Mlp), 3 ReLU
+ *   precision: 3 = fp16 split pairs, three tcgen05 products, float32-equivalent (default of the backbone);
+ *              1 = single fp16 product (run_test.py:14 'medium' precision class) */
+int oryon_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
+                   int K, int batch, int act, float alpha, int precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

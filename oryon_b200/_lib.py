@@ -53,6 +53,8 @@ SIGNATURES = {
                                    c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),
     "oryon_lift_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),
+    "oryon_gemm_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_float, c_int, c_void_p]),
     "oryon_pointdsc_load": (c_int, [c_void_p, POINTER(PointDSCConfig), c_void_p, c_int64, c_void_p]),
     "oryon_pointdsc_pose": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p,
                                     POINTER(PointDSCDebug), c_void_p]),

@@ -58,6 +58,10 @@ int run_lift(oryon_handle*, const void*, int, int, int, const double*, const int
 int run_corrs_to_pcd(oryon_handle*, const int64_t*, int, int, int, const void*, const void*, int, int, int, int, int, const double*,
                      const double*, float*, float*, int32_t*, cudaStream_t);
 }  // namespace lift
+namespace gemm {
+int run_gemm_f32(oryon_handle*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, int,
+                 cudaStream_t);
+}  // namespace gemm
 namespace pdsc {
 int load_weights(oryon_handle*, const oryon_pointdsc_config*, const float*, int64_t, cudaStream_t);
 int run_pose(oryon_handle*, const float*, const float*, const int32_t*, int, int, float*, const oryon_pointdsc_debug*, cudaStream_t);
@@ -89,7 +93,7 @@ void oryon_handle::span_end(cudaStream_t st) {
 
 int64_t oryon_handle::workspace_bytes() const {
   return (int64_t)(rows16_a.bytes + rows16_q.bytes + rows32_a.bytes + rows32_q.bytes + cand.bytes + counters.bytes +
-                   overflow_rows.bytes + pair_meta.bytes + lift_scratch.bytes + pdsc_ws.bytes);
+                   overflow_rows.bytes + pair_meta.bytes + lift_scratch.bytes + pdsc_ws.bytes + gemm_scratch.bytes);
 }
 
 extern "C" {
@@ -138,6 +142,7 @@ int oryon_destroy(oryon_handle* h) {
   h->cand.release(), h->counters.release(), h->overflow_rows.release(), h->pair_meta.release(), h->lift_scratch.release();
   oryon::pdsc::destroy_model(h);
   h->pdsc_ws.release();
+  h->gemm_scratch.release();
   delete h;
   return ORYON_OK;
 }
@@ -198,6 +203,11 @@ int oryon_pointdsc_load(oryon_handle* h, const oryon_pointdsc_config* cfg, const
 int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t* n, int P, int cap, float* out_T,
                         const oryon_pointdsc_debug* debug, void* stream) {
   return oryon::pdsc::run_pose(h, src, tgt, n, P, cap, out_T, debug, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
+                   int K, int batch, int act, float alpha, int precision, void* stream) {
+  return oryon::gemm::run_gemm_f32(h, A, W, bias, residual, out, M, N, K, batch, act, alpha, precision, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

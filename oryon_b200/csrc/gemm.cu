@@ -1,0 +1,415 @@
+// gemm_tc_kernel<TN, NPASS>: persistent, warp-specialised tcgen05 GEMM (see gemm.cuh for the contract).
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor.4d (128B swizzle) into a ring of stages; a stage holds one
+//                              64-deep K block of the 256-row A tile and of the TN-row W tile -- for NPASS == 3
+//                              both halves (hi, lo) of each, so the three products hi*hi, lo*hi, hi*lo reuse
+//                              what was fetched once
+//   warp 1      MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16 M=128 N=TN K=16, fp32
+//                              accumulators in TMEM, two 128-row blocks per CTA tile, double-buffered so the
+//                              epilogue of tile t overlaps the MMAs of tile t+1
+//   warps 2..9  epilogue       tcgen05.ld 32x32b -> registers, alpha / bias / activation / residual, fp32 and/or
+//                              split-fp16 stores (thread <-> output row, 128 contiguous bytes per 32 columns)
+//
+// Grid = min(#SM, tasks); a task is one 256 x TN output tile of one batch matrix, N fastest so that CTAs that run
+// together share the A rows (read once from HBM) and hit L2 for W.
+#include "gemm.cuh"
+#include "ptx_sm100.cuh"
+
+namespace oryon {
+namespace gemm {
+
+constexpr int kTileM = 128;
+constexpr int kRowBlocks = 2;
+constexpr int kCtaRows = kTileM * kRowBlocks;
+constexpr int kKB = 64;                 // K elements per stage (128 bytes of fp16)
+constexpr int kThreads = 320;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int TN, int NPASS>
+struct Cfg {
+  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kABlock = kTileM * kKB * 2;                    // 16 KB
+  static constexpr int kABytes = kABlock * kRowBlocks * kHalves;
+  static constexpr int kWBlock = TN * kKB * 2;
+  static constexpr int kWBytes = kWBlock * kHalves;
+  static constexpr int kStage = kABytes + kWBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStage;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kBarBytes = 8 * (2 * kStages + 4) + 16;
+  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes;
+  static constexpr int kTmemCols = 2 * kRowBlocks * TN;               // 512 / 256 / 128
+  static_assert(kStages >= 2, "pipeline depth");
+};
+
+struct KArgs {
+  int M, N, KB;          // KB = number of 64-deep K blocks
+  int nb0, nb1, tiles_m, tiles_n;
+  Epilogue ep;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_QUICKGELU: return x / (1.f + expf(-1.702f * x));
+    case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case ACT_RELU: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+template <int TN, int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, KArgs args) {
+  using L = Cfg<TN, NPASS>;
+  constexpr int STAGES = L::kStages;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kTileM, TN, /*fp16*/ 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kStage * STAGES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* t_full = empty + STAGES;   // [2]
+  uint64_t* t_empty = t_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a_hi);
+    ptx::prefetch_tensormap(&tm_w_hi);
+    if (NPASS == 3) ptx::prefetch_tensormap(&tm_a_lo), ptx::prefetch_tensormap(&tm_w_lo);
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, L::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tasks_per_mat = args.tiles_m * args.tiles_n;
+  const int total_tasks = tasks_per_mat * args.nb0 * args.nb1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
+        const int nt = t % args.tiles_n, mt = (t / args.tiles_n) % args.tiles_m;
+        const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
+        for (int kb = 0; kb < args.KB; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], L::kStage);
+          uint8_t* sa = smem + stage * L::kStage;
+          uint8_t* sw = sa + L::kABytes;
+#pragma unroll
+          for (int r = 0; r < kRowBlocks; ++r) {
+            tma_load_4d(sa + r * L::kABlock, &tm_a_hi, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
+            if (NPASS == 3)
+              tma_load_4d(sa + (kRowBlocks + r) * L::kABlock, &tm_a_lo, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
+          }
+          tma_load_4d(sw, &tm_w_hi, &full[stage], kb * kKB, nt * TN, b0, b1);
+          if (NPASS == 3) tma_load_4d(sw + L::kWBlock, &tm_w_lo, &full[stage], kb * kKB, nt * TN, b0, b1);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, tile_iter = 0;
+    for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
+      const uint32_t buf = tile_iter & 1;
+      ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      for (int kb = 0; kb < args.KB; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
+          const uint32_t sw = sa + L::kABytes;
+#pragma unroll
+          for (int r = 0; r < kRowBlocks; ++r) {
+            const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * TN) + r * TN;
+#pragma unroll
+            for (int pass = 0; pass < NPASS; ++pass) {
+              // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
+              const uint32_t a_addr = sa + ((pass == 1 ? kRowBlocks : 0) + r) * L::kABlock;
+              const uint32_t w_addr = sw + (pass == 2 ? L::kWBlock : 0);
+#pragma unroll
+              for (int k = 0; k < kKB / 16; ++k) {
+                const uint64_t da = ptx::make_smem_desc_kmajor(a_addr + k * 32, 128);
+                const uint64_t dw = ptx::make_smem_desc_kmajor(w_addr + k * 32, 128);
+                ptx::umma_f16(d_tmem, da, dw, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (kb == args.KB - 1) ptx::umma_commit(&t_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+      ++tile_iter;
+    }
+  } else {
+    const int ew = warp - 2, rblk = ew >> 2, quarter = warp & 3;
+    const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
+    const Epilogue& ep = args.ep;
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
+      const int nt = t % args.tiles_n, mt = (t / args.tiles_n) % args.tiles_m;
+      const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
+      const uint32_t buf = tile_iter & 1;
+      const int row = mt * kCtaRows + row_in_cta;
+      int drow = row;
+      bool row_ok = row < args.M;
+      if (row_ok && ep.row_map) {
+        drow = ep.row_map[row];
+        row_ok = drow >= 0;
+      }
+      const int64_t off32 = (int64_t)b1 * ep.out_b1 + (int64_t)b0 * ep.out_b0 + (int64_t)drow * ep.ld32;
+      const int64_t offh = (int64_t)b1 * ep.outh_b1 + (int64_t)b0 * ep.outh_b0;
+      ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * TN) + rblk * TN;
+#pragma unroll 1
+      for (int g = 0; g < TN / 32; ++g) {
+        const int col0 = nt * TN + g * 32;
+        if (col0 >= args.N) break;   // warp-uniform
+        __syncwarp();                // lanes of dropped rows skip the stores below: reconverge before the aligned load
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + g * 32, v);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool full_chunk = col0 + 32 <= args.N;
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float y = __uint_as_float(v[i]) * ep.alpha;
+          if (ep.bias && (full_chunk || col0 + i < args.N)) y += __ldg(ep.bias + col0 + i);
+          x[i] = apply_act(y, ep.act);
+        }
+        if (ep.residual) {
+          const float* r = ep.residual + off32 + col0;
+          if (full_chunk && (ep.ld32 & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(r) + i);
+              x[4 * i] += q.x, x[4 * i + 1] += q.y, x[4 * i + 2] += q.z, x[4 * i + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < args.N) x[i] += r[i];
+          }
+        }
+        if (ep.out32) {
+          float* o = ep.out32 + off32 + col0;
+          if (full_chunk && (ep.ld32 & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < args.N) o[i] = x[i];
+          }
+        }
+        if (ep.out_hi) {
+          __half hi[32], lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) split_half(x[i], hi[i], lo[i]);
+          if (ep.transpose_h) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < args.N) {
+                const int64_t o = offh + (int64_t)(col0 + i) * ep.ldh + drow;
+                ep.out_hi[o] = hi[i];
+                if (ep.out_lo) ep.out_lo[o] = lo[i];
+              }
+          } else {
+            const int64_t o = offh + (int64_t)drow * ep.ldh + col0;
+            if (full_chunk && (ep.ldh & 7) == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                reinterpret_cast<uint4*>(ep.out_hi + o)[i] = reinterpret_cast<const uint4*>(hi)[i];
+                if (ep.out_lo) reinterpret_cast<uint4*>(ep.out_lo + o)[i] = reinterpret_cast<const uint4*>(lo)[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < args.N) {
+                  ep.out_hi[o + i] = hi[i];
+                  if (ep.out_lo) ep.out_lo[o + i] = lo[i];
+                }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+      ++tile_iter;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, L::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int make_map(oryon_handle* h, CUtensorMap* tm, const __half* base, int kpad, int rows, int nb0, int nb1, int64_t ld,
+                    int64_t sb0, int64_t sb1, int box_rows) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
+  // a stride of 0 is not encodable: singleton batch dims get any valid multiple of 16 bytes
+  const cuuint64_t s1 = (cuuint64_t)ld * 2;
+  const cuuint64_t s2 = nb0 > 1 ? (cuuint64_t)sb0 * 2 : s1 * (cuuint64_t)rows;
+  const cuuint64_t s3 = nb1 > 1 ? (cuuint64_t)sb1 * 2 : s2 * (cuuint64_t)nb0;
+  const cuuint64_t gstride[3] = {s1, s2, s3};
+  const cuuint32_t box[4] = {(cuuint32_t)kKB, (cuuint32_t)box_rows, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm: cuTensorMapEncodeTiled failed with CUresult %d (kpad=%d rows=%d nb=%dx%d ld=%lld sb0=%lld sb1=%lld base=%p)", (int)r,
+              kpad, rows, nb0, nb1, (long long)ld, (long long)sb0, (long long)sb1, (const void*)base);
+    return ORYON_ERR_CUDA;
+  }
+  return ORYON_OK;
+}
+
+template <int TN, int NPASS>
+static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
+  using L = Cfg<TN, NPASS>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  const int kpad = round_up(p.K, kKB);
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  int rc;
+  if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+  if ((rc = make_map(h, &tw_hi, p.W.hi, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
+  if (NPASS == 3) {
+    if ((rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+    if ((rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
+  } else {
+    ta_lo = ta_hi, tw_lo = tw_hi;
+  }
+  KArgs ka;
+  ka.M = p.M, ka.N = p.N, ka.KB = kpad / kKB;
+  ka.nb0 = p.nb0, ka.nb1 = p.nb1;
+  ka.tiles_m = (p.M + kCtaRows - 1) / kCtaRows;
+  ka.tiles_n = (p.N + TN - 1) / TN;
+  ka.ep = p.ep;
+  const long long tasks = (long long)ka.tiles_m * ka.tiles_n * p.nb0 * p.nb1;
+  const int grid = (int)std::min<long long>(h->sm_count, tasks);
+  auto kern = gemm_tc_kernel<TN, NPASS>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  h->span_begin(KID_GEMM, st);
+  kern<<<grid, kThreads, L::kTotal, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, ka);
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  ++h->gemm_launches;
+  h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  return ORYON_OK;
+}
+
+int launch(oryon_handle* h, const Problem& p, cudaStream_t st) {
+  ORYON_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.nb0 > 0 && p.nb1 > 0, "gemm: empty problem (M=%d N=%d K=%d)", p.M, p.N, p.K);
+  ORYON_REQUIRE(p.precision == 1 || p.precision == 3, "gemm: precision must be 1 or 3");
+  ORYON_REQUIRE(p.A.hi && p.W.hi && (p.precision == 1 || (p.A.lo && p.W.lo)), "gemm: missing operand");
+  ORYON_REQUIRE((p.A.ld % 8) == 0 && (p.W.ld % 8) == 0 && (p.A.stride_b0 % 8) == 0 && (p.A.stride_b1 % 8) == 0 &&
+                    (p.W.stride_b0 % 8) == 0 && (p.W.stride_b1 % 8) == 0,
+                "gemm: operand strides must be multiples of 8 elements (16 bytes)");
+  ORYON_REQUIRE(p.A.ld >= round_up(p.K, kKB) || p.A.ld >= p.K, "gemm: A row stride shorter than K");
+  ORYON_REQUIRE(!p.ep.row_map || (p.nb0 == 1 && p.nb1 == 1), "gemm: row_map needs an unbatched problem");
+  const int tn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+  if (p.precision == 3) {
+    switch (tn) {
+      case 32: return launch_t<32, 3>(h, p, st);
+      case 64: return launch_t<64, 3>(h, p, st);
+      default: return launch_t<128, 3>(h, p, st);
+    }
+  }
+  switch (tn) {
+    case 32: return launch_t<32, 1>(h, p, st);
+    case 64: return launch_t<64, 1>(h, p, st);
+    default: return launch_t<128, 1>(h, p, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols, __half* hi,
+                                                         __half* lo, int64_t ld_out) {
+  const int64_t total = (int64_t)rows * ld_out;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / ld_out;
+    const int c = (int)(i - r * ld_out);
+    const float x = c < cols ? in[r * ld_in + c] : 0.f;
+    __half a, b;
+    split_half(x, a, b);
+    hi[i] = a;
+    if (lo) lo[i] = b;
+  }
+}
+
+int split_rows(oryon_handle* h, const float* in, int64_t ld_in, int rows, int cols, __half* hi, __half* lo, int64_t ld_out,
+               cudaStream_t st) {
+  const int64_t total = (int64_t)rows * ld_out;
+  if (total == 0) return ORYON_OK;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+  split_rows_kernel<<<blocks, 256, 0, st>>>(in, ld_in, rows, cols, hi, lo, ld_out);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+// C-ABI test entry (include/oryon_b200.h: oryon_gemm_f32): fp32 operands are split on the device, then the
+// tensor-core kernel runs exactly as it does inside the backbone.
+int run_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N, int K,
+                 int batch, int act, float alpha, int precision, cudaStream_t st) {
+  ORYON_REQUIRE(h && A && W && out, "oryon_gemm_f32: null argument");
+  ORYON_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "oryon_gemm_f32: empty problem");
+  ORYON_CUDA_CHECK(cudaSetDevice(h->device));
+  const int kpad = round_up(K, kKB);
+  const size_t a_el = (size_t)batch * M * kpad, w_el = (size_t)batch * N * kpad;
+  int rc;
+  if ((rc = h->gemm_scratch.reserve((a_el + w_el) * 2 * sizeof(__half), st))) return rc;
+  __half* a_hi = h->gemm_scratch.as<__half>();
+  __half* a_lo = a_hi + a_el;
+  __half* w_hi = a_lo + a_el;
+  __half* w_lo = w_hi + w_el;
+  if ((rc = split_rows(h, A, K, batch * M, K, a_hi, a_lo, kpad, st))) return rc;
+  if ((rc = split_rows(h, W, K, batch * N, K, w_hi, w_lo, kpad, st))) return rc;
+  Problem p;
+  p.M = M, p.N = N, p.K = K, p.nb0 = batch, p.nb1 = 1, p.precision = precision;
+  p.A.hi = a_hi, p.A.lo = a_lo, p.A.ld = kpad, p.A.stride_b0 = (int64_t)M * kpad;
+  p.W.hi = w_hi, p.W.lo = w_lo, p.W.ld = kpad, p.W.stride_b0 = (int64_t)N * kpad;
+  p.ep.alpha = alpha, p.ep.bias = bias, p.ep.act = act, p.ep.residual = residual;
+  p.ep.out32 = out, p.ep.ld32 = N, p.ep.out_b0 = (int64_t)M * N;
+  return launch(h, p, st);
+}
+
+}  // namespace gemm
+}  // namespace oryon

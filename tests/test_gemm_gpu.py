@@ -1,0 +1,76 @@
+"""GPU parity of the backbone's tensor-core GEMM (oryon_gemm_f32) against a float64 torch evaluation of
+``residual + act(alpha * A W^T + bias)``.
+
+Tolerances, relative to the magnitude scale ``sqrt(K) * rms(A) * rms(W)`` of one output:
+  precision 3 (fp16 split pairs, three tcgen05 products)  1e-4   operand error is ~2^-21; what remains is the tensor
+                                                                  core's truncating fp32 accumulation, ~(K/16) * 2^-24 per
+                                                                  output (measured 2e-5 at K = 1024)
+  precision 1 (single fp16 product)                        2e-3
+"""
+import pytest
+import torch
+
+from gpu_util import need_gpu
+from oryon_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, W, bias, res, act, alpha):
+    y = alpha * (A.double() @ W.double().transpose(-1, -2))
+    if bias is not None:
+        y = y + bias.double()
+    if act == "quickgelu":
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act == "relu":
+        y = torch.relu(y)
+    if res is not None:
+        y = y + res.double()
+    return y
+
+
+CASES = [
+    # M, N, K, batch, act, bias, residual
+    (256, 128, 64, 1, "none", False, False),
+    (577, 1024, 1024, 1, "none", True, True),
+    (1154, 3072, 1024, 1, "none", True, False),
+    (300, 4096, 1024, 1, "quickgelu", True, False),
+    (300, 1000, 4096, 1, "none", True, True),
+    (576, 80, 768, 3, "none", False, False),      # cost volume: per-image text matrix, N < tile
+    (2304, 64, 1152, 1, "relu", True, False),     # decoder conv as GEMM, TN = 64
+    (9216, 16, 1152, 1, "relu", True, False),     # TN = 32, N = 16
+    (100, 33, 48, 2, "gelu", True, True),         # everything ragged
+    (1, 7, 5, 1, "none", True, False),
+]
+
+
+@pytest.mark.parametrize("M,N,K,batch,act,use_bias,use_res", CASES)
+@pytest.mark.parametrize("precision", [3, 1])
+def test_gemm_matches_float64(M, N, K, batch, act, use_bias, use_res, precision):
+    need_gpu()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + batch)
+    shape_a = (batch, M, K) if batch > 1 else (M, K)
+    shape_w = (batch, N, K) if batch > 1 else (N, K)
+    A = torch.randn(shape_a, generator=g)
+    W = torch.randn(shape_w, generator=g) * 0.05
+    bias = torch.randn(N, generator=g) if use_bias else None
+    res = torch.randn(*shape_a[:-1], N, generator=g) if use_res else None
+    alpha = 0.125 if act == "none" and not use_bias else 1.0
+    out = ops.linear(A.cuda(), W.cuda(), None if bias is None else bias.cuda(), None if res is None else res.cuda(), act=act,
+                     alpha=alpha, precision=precision).cpu()
+    ref = _ref(A, W, bias, res, act, alpha)
+    scale = alpha * (K ** 0.5) * 1.0 * 0.05 + 1e-3
+    err = (out.double() - ref).abs().max().item() / scale
+    tol = 1e-4 if precision == 3 else 2e-3
+    print(f'scaled err {err:.3e}')
+    assert err < tol, f"max scaled error {err:.3e} (tol {tol})"
+
+
+def test_gemm_large_values_saturate_not_nan():
+    need_gpu()
+    A = torch.full((128, 64), 300.0)
+    W = torch.full((128, 64), 300.0)
+    out = ops.linear(A.cuda(), W.cuda()).cpu()
+    assert torch.isfinite(out).all() and torch.allclose(out, torch.full_like(out, 300.0 * 300.0 * 64), rtol=1e-6)
