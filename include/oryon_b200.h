@@ -72,7 +72,8 @@ int64_t oryon_workspace_bytes(const oryon_handle* h);
  * returns per kernel id the summed duration (ms) and launch count since the last read, and clears them.
  * Kernel ids: 0 prep_rows, 1 match_tc (tcgen05 similarity + argmax epilogue), 2 refine_rows,
  * 3 exact_rows, 4 mask_to_roi, 5 lift/corrs_to_pcd, 6 pointdsc SC matrix, 7 pointdsc NonLocalNet,
- * 8 pointdsc seeds/kNN/power/Kabsch/fitness, 9 pointdsc refinement; further ids are listed in DESIGN.md. */
+ * 8 pointdsc seeds/kNN/power/Kabsch/fitness, 9 pointdsc refinement, 10 backbone GEMM (tcgen05), 11 attention,
+ * 12 normalisations, 13 element-wise / small fused heads, 14 im2col. */
 int oryon_profile_enable(oryon_handle* h, int enable);
 int oryon_profile_read(oryon_handle* h, double* total_ms, int64_t* launches, int n_ids);
 
@@ -198,6 +199,50 @@ int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, con
  *              1 = single fp16 product (run_test.py:14 'medium' precision class) */
 int oryon_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
                    int K, int batch, int act, float alpha, int precision, void* stream);
+
+/* ---- a1-a6: the network, Oryon.forward (net.py:142-167) ------------------------------------------
+ * Weights are handed over by their reference state_dict names (the keys of FPM_Pipeline's checkpoint with the
+ * leading "model." stripped, i.e. Oryon's own: vlm.clip_model.*, guidance_backbone.features.*, fusion.*,
+ * decoder.*; net.py:99-139 shows how the reference fills them), float32, in the reference's shapes.  Integer
+ * buffers (relative_position_index, attn_mask) are derived by the library and need not be passed.
+ * oryon_backbone_finalize packs them (fp16 split pairs, K-major, conv weights permuted to the im2col order)
+ * and frees the host copies. */
+typedef struct {
+  int32_t vis_layers;          /* CLIP vision transformer depth: 24 for ViT-L/14@336 (vlm.py:19) */
+  int32_t txt_layers;          /* CLIP text transformer depth: 12; 0 = text tower not loaded */
+  int32_t precision;           /* GEMM precision, see oryon_gemm_f32: 3 (float32-equivalent, default) or 1 */
+  int32_t max_pairs_per_pass;  /* pairs processed per pass over the network (bounds activation memory); 0 = 16 */
+} oryon_backbone_config;
+
+int oryon_backbone_set_weight(oryon_handle* h, const char* name, const float* data /*HOST*/, int64_t numel);
+int oryon_backbone_finalize(oryon_handle* h, const oryon_backbone_config* cfg, void* stream);
+
+/* CLIPEncoder.encode_prompt after tokenisation (models/vlm.py:74-83):
+ *   tokens DEVICE int32 [n][77] (SimpleTokenizer ids; EOT is the arg-max id) -> out DEVICE float32 [n][768].
+ * A pure function of the prompt strings: the caller caches it per object. */
+int oryon_text_forward(oryon_handle* h, const int32_t* tokens, int n, float* out, void* stream);
+
+/* Optional intermediate outputs (all DEVICE float32, NCHW, 2B images: anchors [0,B), queries [B,2B)). */
+typedef struct {
+  int32_t B;
+  int32_t reserved;
+  float* clip_tokens;   /* [2B][1024][24][24]  encode_image output (vlm.py:58-61) */
+  float* guid1;         /* [2B][512][24][24]   get_guidance_embeds (net.py:60-75) */
+  float* guid2;         /* [2B][256][48][48] */
+  float* guid3;         /* [2B][128][96][96] */
+  float* fusion;        /* [2B][128][24][24]   ImageTextFusion.forward output (T = 1 squeezed) */
+} oryon_backbone_debug;
+
+/* Oryon.forward for B pairs:
+ *   rgb_a, rgb_q   DEVICE float32 [B][3][224][224] in [0,1]        (xs['anchor'|'query']['rgb'])
+ *   text_emb       DEVICE float32 [B][80][768]                      (encode_prompt output, oryon_text_forward)
+ *   featmap_a/q    DEVICE float32 [B][32][192][192]                 ('featmap_a', 'featmap_q')
+ *   mask_a/q       DEVICE float32 [B][1][192][192] logits           ('mask_a', 'mask_q') */
+int oryon_backbone_forward(oryon_handle* h, const float* rgb_a, const float* rgb_q, int B, const float* text_emb, float* featmap_a,
+                           float* featmap_q, float* mask_a, float* mask_q, const oryon_backbone_debug* debug, void* stream);
+
+/* GEMM accounting since the last call (launches, algorithmic FLOPs 2*M*N*K); resets the counters. */
+int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops);
 
 #ifdef __cplusplus
 }

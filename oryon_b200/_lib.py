@@ -36,6 +36,17 @@ class PointDSCDebug(ctypes.Structure):
                 ("reserved", c_int32), ("initial_trans", c_void_p), ("best_seed", c_void_p)]
 
 
+class BackboneConfig(ctypes.Structure):
+    """oryon_backbone_config"""
+    _fields_ = [("vis_layers", c_int32), ("txt_layers", c_int32), ("precision", c_int32), ("max_pairs_per_pass", c_int32)]
+
+
+class BackboneDebug(ctypes.Structure):
+    """oryon_backbone_debug"""
+    _fields_ = [("B", c_int32), ("reserved", c_int32), ("clip_tokens", c_void_p), ("guid1", c_void_p), ("guid2", c_void_p),
+                ("guid3", c_void_p), ("fusion", c_void_p)]
+
+
 # name -> (restype, argtypes): every symbol include/oryon_b200.h declares
 SIGNATURES = {
     "oryon_abi_version": (c_int, []),
@@ -55,6 +66,12 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "oryon_gemm_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_float, c_int, c_void_p]),
+    "oryon_backbone_set_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "oryon_backbone_finalize": (c_int, [c_void_p, POINTER(BackboneConfig), c_void_p]),
+    "oryon_text_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "oryon_backbone_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       POINTER(BackboneDebug), c_void_p]),
+    "oryon_gemm_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double)]),
     "oryon_pointdsc_load": (c_int, [c_void_p, POINTER(PointDSCConfig), c_void_p, c_int64, c_void_p]),
     "oryon_pointdsc_pose": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p,
                                     POINTER(PointDSCDebug), c_void_p]),
@@ -125,7 +142,8 @@ def destroy_all() -> None:
 
 
 KERNEL_IDS = {"prep_rows": 0, "match_tc": 1, "refine_rows": 2, "exact_rows": 3, "mask_to_roi": 4, "lift": 5,
-              "pointdsc_sc": 6, "pointdsc_net": 7, "pointdsc_seeds": 8, "pointdsc_refine": 9}
+              "pointdsc_sc": 6, "pointdsc_net": 7, "pointdsc_seeds": 8, "pointdsc_refine": 9,
+              "gemm_tc": 10, "attention": 11, "norm": 12, "eltwise": 13, "im2col": 14}
 
 
 def profile_enable(device_index: int, enable: bool) -> None:

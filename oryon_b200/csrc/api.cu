@@ -62,6 +62,14 @@ namespace gemm {
 int run_gemm_f32(oryon_handle*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, int,
                  cudaStream_t);
 }  // namespace gemm
+namespace net {
+int set_weight(oryon_handle*, const char*, const float*, int64_t);
+int finalize(oryon_handle*, const oryon_backbone_config*, cudaStream_t);
+int text_forward(oryon_handle*, const int32_t*, int, float*, cudaStream_t);
+int backbone_forward(oryon_handle*, const float*, const float*, int, const float*, float*, float*, float*, float*,
+                     const oryon_backbone_debug*, cudaStream_t);
+void destroy_backbone(oryon_handle*);
+}  // namespace net
 namespace pdsc {
 int load_weights(oryon_handle*, const oryon_pointdsc_config*, const float*, int64_t, cudaStream_t);
 int run_pose(oryon_handle*, const float*, const float*, const int32_t*, int, int, float*, const oryon_pointdsc_debug*, cudaStream_t);
@@ -141,6 +149,7 @@ int oryon_destroy(oryon_handle* h) {
   for (auto e : h->free_events) cudaEventDestroy(e);
   h->cand.release(), h->counters.release(), h->overflow_rows.release(), h->pair_meta.release(), h->lift_scratch.release();
   oryon::pdsc::destroy_model(h);
+  oryon::net::destroy_backbone(h);
   h->pdsc_ws.release();
   h->gemm_scratch.release();
   delete h;
@@ -208,6 +217,27 @@ int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, con
 int oryon_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
                    int K, int batch, int act, float alpha, int precision, void* stream) {
   return oryon::gemm::run_gemm_f32(h, A, W, bias, residual, out, M, N, K, batch, act, alpha, precision, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_backbone_set_weight(oryon_handle* h, const char* name, const float* data, int64_t numel) {
+  return oryon::net::set_weight(h, name, data, numel);
+}
+int oryon_backbone_finalize(oryon_handle* h, const oryon_backbone_config* cfg, void* stream) {
+  return oryon::net::finalize(h, cfg, static_cast<cudaStream_t>(stream));
+}
+int oryon_text_forward(oryon_handle* h, const int32_t* tokens, int n, float* out, void* stream) {
+  return oryon::net::text_forward(h, tokens, n, out, static_cast<cudaStream_t>(stream));
+}
+int oryon_backbone_forward(oryon_handle* h, const float* rgb_a, const float* rgb_q, int B, const float* text_emb, float* featmap_a,
+                           float* featmap_q, float* mask_a, float* mask_q, const oryon_backbone_debug* debug, void* stream) {
+  return oryon::net::backbone_forward(h, rgb_a, rgb_q, B, text_emb, featmap_a, featmap_q, mask_a, mask_q, debug,
+                                      static_cast<cudaStream_t>(stream));
+}
+int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops) {
+  ORYON_REQUIRE(h && launches && flops, "oryon_gemm_counters: null argument");
+  *launches = h->gemm_launches, *flops = h->gemm_flops;
+  h->gemm_launches = 0, h->gemm_flops = 0.0;
+  return ORYON_OK;
 }
 
 }  // extern "C"
