@@ -244,6 +244,20 @@ int oryon_backbone_forward(oryon_handle* h, const float* rgb_a, const float* rgb
 /* GEMM accounting since the last call (launches, algorithmic FLOPs 2*M*N*K); resets the counters. */
 int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops);
 
+/* ---- a7: mask post-processing ----------------------------------------------------------------------
+ * Replaces the no-grad part of FeatureLoss.mask_loss (losses.py:56-60: torch.where(sigmoid(logits) > mask_th, 1, 0)
+ * and mask_iou, utils/metrics.py:18-40, against the nearest-resized ground truth, losses.py:52-53) and the
+ * counting / external-mask resize of is_detection_valid and get_featmap_corrs (pipeline.py:372-395, :409-412).
+ *   logits      DEVICE float32 [B][H][W] or NULL (external mask only)
+ *   gt          DEVICE uint8   [B][Hg][Wg] or NULL (no IoU)
+ *   pred_mask   DEVICE int32   [B][H][W]  (with logits)
+ *   gt_resized  DEVICE int32   [B][H][W]  or NULL  nearest resize of gt (F.interpolate mode='nearest')
+ *   n_pred      DEVICE int32   [B] or NULL  pixels with pred_mask == 1
+ *   n_gt        DEVICE int32   [B] or NULL  pixels with gt_resized == 1
+ *   iou         DEVICE float32 [B] or NULL  |pred & gt| / |pred | gt|  (NaN for 0/0, as the reference) */
+int oryon_mask_postproc(oryon_handle* h, const float* logits, int B, int H, int W, float mask_th, const uint8_t* gt, int Hg, int Wg,
+                        int32_t* pred_mask, int32_t* gt_resized, int32_t* n_pred, int32_t* n_gt, float* iou, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

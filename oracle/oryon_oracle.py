@@ -369,3 +369,49 @@ def pointdsc_pose(w: Dict[str, Tensor], cfg: Dict, pcd1: Tensor, pcd2: Tensor, r
         return final, dict(sc=sc, feat=feat, conf=conf, seeds=seeds, seed_trans=seed_trans,
                            fitness=fitness, initial=best)
     return final
+
+
+# --------------------------------------------------------------------------------------------
+# a12  the per-pair loop of test_step  (reference pipeline.py:313-355) on given network outputs
+# --------------------------------------------------------------------------------------------
+
+
+def post_network_step(outputs: Dict[str, Tensor], batch: Dict, pointdsc_w: Dict[str, Tensor], pointdsc_cfg: Dict, *,
+                      mask_mode: str = "predicted", mask_th: float = 0.5, dist_th: float = 0.25, n_corrs: int = 500,
+                      src_sampling: Optional[int] = 5000, featmap_size: Tuple[int, int] = (192, 192)):
+    """Everything ``test_step`` does after ``model.forward`` (reference pipeline.py:311-355), pair by pair and in
+    the reference's order (so the CPU generator is consumed exactly as the reference consumes it): mask
+    post-processing and IoU (losses.py:52-60), validity (:372-395), ``nn_correspondences`` (:397-427),
+    scale / lift (:438-460), ``get_pointdsc_pose`` (:468), ``pred_q = pred_pose @ anchor_pose`` (:320), identity
+    pose on failure (:335-350).  ``outputs`` holds CPU tensors."""
+    B = outputs["featmap_a"].shape[0]
+    res = {}
+    for v, key in (("a", "anchor"), ("q", "query")):
+        gt = batch[key]["mask"]
+        gt_c = F.interpolate(gt.unsqueeze(1).float(), tuple(featmap_size), mode="nearest").squeeze(1)
+        res["mask_" + v] = predicted_mask(outputs["mask_" + v], mask_th)
+        res["iou_" + v] = mask_iou(gt_c, res["mask_" + v])
+    rows = []
+    for b in range(B):
+        if mask_mode != "predicted":
+            ma = resize_mask_nearest(batch["anchor"]["mask"][b], featmap_size)
+            mq = resize_mask_nearest(batch["query"]["mask"][b], featmap_size)
+        else:
+            ma, mq = res["mask_a"][b], res["mask_q"][b]
+        valid = int(torch.count_nonzero(ma == 1)) > 0 and int(torch.count_nonzero(mq == 1)) > 0
+        pose, status, corrs = torch.eye(4), "invalid_mask", None
+        if valid:
+            corrs = nn_correspondences(outputs["featmap_a"][b].clone(), outputs["featmap_q"][b].clone(), ma, mq, dist_th, n_corrs,
+                                       src_sampling)
+            status = "no_corrs"
+            if corrs is not None:
+                HA, WA = (int(x) for x in batch["anchor"]["sizes"][b])
+                HQ, WQ = (int(x) for x in batch["query"]["sizes"][b])
+                pa, pq = corrs_to_pcds(corrs, batch["anchor"]["orig_depth"][b].squeeze(), batch["query"]["orig_depth"][b].squeeze(),
+                                       batch["anchor"]["camera"][b].reshape(9), batch["query"]["camera"][b].reshape(9), featmap_size,
+                                       (HA, WA), (HQ, WQ))
+                pose, status = pointdsc_pose(pointdsc_w, pointdsc_cfg, pa, pq).to(torch.float32), "ok"
+        pred_q = pose @ batch["anchor"]["pose"][b].to(torch.float32) if status == "ok" else None
+        rows.append(dict(pred_pose_rel=pose, pred_pose=pred_q, iou_a=float(res["iou_a"][b]), iou_q=float(res["iou_q"][b]),
+                         status=status, corrs=corrs))
+    return rows

@@ -72,6 +72,8 @@ SIGNATURES = {
     "oryon_backbone_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        POINTER(BackboneDebug), c_void_p]),
     "oryon_gemm_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double)]),
+    "oryon_mask_postproc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "oryon_pointdsc_load": (c_int, [c_void_p, POINTER(PointDSCConfig), c_void_p, c_int64, c_void_p]),
     "oryon_pointdsc_pose": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p,
                                     POINTER(PointDSCDebug), c_void_p]),

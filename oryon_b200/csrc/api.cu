@@ -70,6 +70,10 @@ int backbone_forward(oryon_handle*, const float*, const float*, int, const float
                      const oryon_backbone_debug*, cudaStream_t);
 void destroy_backbone(oryon_handle*);
 }  // namespace net
+namespace maskpost {
+int run(oryon_handle*, const float*, int, int, int, float, const uint8_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, float*,
+        cudaStream_t);
+}  // namespace maskpost
 namespace pdsc {
 int load_weights(oryon_handle*, const oryon_pointdsc_config*, const float*, int64_t, cudaStream_t);
 int run_pose(oryon_handle*, const float*, const float*, const int32_t*, int, int, float*, const oryon_pointdsc_debug*, cudaStream_t);
@@ -238,6 +242,12 @@ int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops) {
   *launches = h->gemm_launches, *flops = h->gemm_flops;
   h->gemm_launches = 0, h->gemm_flops = 0.0;
   return ORYON_OK;
+}
+
+int oryon_mask_postproc(oryon_handle* h, const float* logits, int B, int H, int W, float mask_th, const uint8_t* gt, int Hg, int Wg,
+                        int32_t* pred_mask, int32_t* gt_resized, int32_t* n_pred, int32_t* n_gt, float* iou, void* stream) {
+  return oryon::maskpost::run(h, logits, B, H, W, mask_th, gt, Hg, Wg, pred_mask, gt_resized, n_pred, n_gt, iou,
+                              static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,248 @@
+"""Mirror of the inference part of the reference ``pipeline.py``: ``FPM_Pipeline`` with ``forward`` (:593),
+``test_step`` (:306-355), ``is_detection_valid`` (:372-395), ``get_featmap_corrs`` (:397-427), ``get_pose``
+(:429-472) and ``add_pred_pose`` (:490-497).  Same names, argument meaning, failure rows and CSV wire format.
+
+Every arithmetic step runs in liboryon_b200.so: the network (``oryon_backbone_forward``), mask post-processing
+(``oryon_mask_postproc``), matching (``oryon_match_nn``), scaling / lifting (``oryon_corrs_to_pcd``) and
+registration (``oryon_pointdsc_pose``).  What stays in torch is what the reference leaves to torch's generator: the
+two ``multinomial`` draws per pair, in the reference's order.
+
+``test_step`` is batched the B200 way -- one network pass, one matching call and one registration call for the
+whole batch -- yet produces exactly what the reference's per-pair loop produces: the nearest neighbour of an anchor
+pixel does not depend on which other anchor pixels were sub-sampled, so all ROI pixels of all pairs are matched in
+one launch and the (cheap, ordered) random selections are applied afterwards, pair by pair, in the reference's
+draw order.
+
+Lightning / hydra are not dependencies: the class is a plain object with the LightningModule hook names; ``args`` is
+any attribute-style mapping with the keys of configs/config.yaml that the inference path reads.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._torch_glue import as_device, ptr, stream_ptr
+from .net import Oryon
+from .utils import pcd as _pcd
+from .utils.pcd import corrs_to_pcd, mask_to_roi, match_nn, nn_correspondences, torch_sample_select
+from .utils.pointdsc.init import get_pointdsc_pose, get_pointdsc_solver, pointdsc_poses
+
+
+def _get(obj, path: str, default=None):
+    cur = obj
+    for key in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(key) if isinstance(cur, dict) else getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+def mask_postproc(logits: Optional[Tensor], gt: Optional[Tensor], size: Tuple[int, int], mask_th: float = 0.5) -> Dict[str, Tensor]:
+    """``oryon_mask_postproc``: predicted mask, nearest-resized ground truth, counts and IoU for a batch.
+    ``logits [B,1,H,W]`` or ``[B,H,W]`` (or ``None``), ``gt [B,Hg,Wg]`` (or ``None``)."""
+    src = logits if logits is not None else gt
+    dev = src.device if src.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    H, W = int(size[0]), int(size[1])
+    lg = None
+    if logits is not None:
+        lg = as_device(logits, dev, torch.float32).reshape(-1, H, W)
+    g = None
+    if gt is not None:
+        g = as_device(gt, dev).to(torch.uint8).contiguous()
+    B = lg.shape[0] if lg is not None else g.shape[0]
+    out = dict(n_pred=torch.zeros(B, dtype=torch.int32, device=dev), n_gt=torch.zeros(B, dtype=torch.int32, device=dev))
+    out["pred"] = torch.empty(B, H, W, dtype=torch.int32, device=dev) if lg is not None else None
+    out["gt_resized"] = torch.empty(B, H, W, dtype=torch.int32, device=dev) if g is not None else None
+    out["iou"] = torch.empty(B, dtype=torch.float32, device=dev) if (lg is not None and g is not None) else None
+    _lib.check(_lib.load().oryon_mask_postproc(
+        _lib.handle(dev.index), ptr(lg), B, H, W, float(mask_th), ptr(g), 0 if g is None else g.shape[1], 0 if g is None else g.shape[2],
+        ptr(out["pred"]), ptr(out["gt_resized"]), ptr(out["n_pred"]), ptr(out["n_gt"]), ptr(out["iou"]), stream_ptr(dev)))
+    return out
+
+
+class FPM_Pipeline:
+    def __init__(self, args, test_model: bool = False, *, model: Optional[Oryon] = None, pointdsc_solver=None):
+        self.args = args
+        self.test_model = test_model
+        self.device = torch.device(_get(args, "device", "cuda"))
+        if self.device.type != "cuda":
+            raise _lib.OryonError("oryon_b200.pipeline.FPM_Pipeline runs on a CUDA (sm_100) device only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.model = model if model is not None else Oryon(args, self.device)
+        self.corrs_device = _get(args, "corrs_device", "cpu")
+        self.solver = _get(args, "test.solver", "pointdsc")
+        self.pointdsc_solver = pointdsc_solver
+        if self.solver == "pointdsc" and self.pointdsc_solver is None:
+            self.pointdsc_solver = get_pointdsc_solver(_get(args, "pretrained.pointdsc"), self.device)
+        self.mask_mode = _get(args, "test.mask", "predicted")
+        self.mask_th = float(_get(args, "test.mask_threshold", 0.5))
+        self.dist_th = float(_get(args, "test.dist_th", 0.25))
+        self.n_corrs = int(_get(args, "test.n_corrs", _get(args, "dataset.max_corrs", 500)))
+        self.src_sampling = _get(args, "test.src_sampling", 5000)
+        self.featmap_size = tuple(_get(args, "model.image_encoder.img_size", (192, 192)))
+        self.pred_file = None
+        self.rows: List[dict] = []
+
+    # ---- LightningModule surface -----------------------------------------------------------------------
+    def forward(self, x: dict) -> Dict[str, Tensor]:
+        return self.model.forward(x)
+
+    def on_test_start(self, pred_path: Optional[str] = None, seed: Optional[int] = None):
+        """Opens the prediction CSV and seeds numpy / torch as ``set_deterministic_seed`` (utils/misc.py:186-196,
+        pipeline.py:296-299: ``args.seed`` if ``use_seed`` else 1)."""
+        if pred_path is not None:
+            self.pred_file = open(pred_path, "w")
+        if seed is None:
+            seed = int(_get(self.args, "seed", 1)) if _get(self.args, "use_seed", False) else 1
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed(seed)
+        self.rows = []
+
+    def on_test_end(self):
+        if self.pred_file is not None:
+            self.pred_file.close()
+            self.pred_file = None
+
+    # ---- a7 -----------------------------------------------------------------------------------------------
+    def mask_results(self, batch: dict, outputs: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """The entries of ``FeatureLoss.forward``'s ``results`` that inference consumes (losses.py:56-60 via :64-141):
+        ``mask_a/q`` int ``[B,H,W]``, ``iou_a/q [B]``, ``logits_a/q [B,H,W]``, plus the pixel counts."""
+        res = {}
+        for v, key in (("a", "anchor"), ("q", "query")):
+            gt = batch[key].get("mask") if isinstance(batch.get(key), dict) else None
+            mp = mask_postproc(outputs["mask_" + v], gt, self.featmap_size, self.mask_th)
+            res["mask_" + v], res["iou_" + v] = mp["pred"], mp["iou"]
+            res["logits_" + v] = outputs["mask_" + v].squeeze(1)
+            res["n_pred_" + v], res["n_gt_" + v], res["gt_" + v] = mp["n_pred"], mp["n_gt"], mp["gt_resized"]
+        return res
+
+    def _masks_and_counts(self, results: dict) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        if self.mask_mode != "predicted":  # external mask, nearest-resized to the feature map (pipeline.py:378-386, :407-412)
+            return results["gt_a"], results["gt_q"], results["n_gt_a"], results["n_gt_q"]
+        return results["mask_a"], results["mask_q"], results["n_pred_a"], results["n_pred_q"]
+
+    def is_detection_valid(self, results: dict, batch: dict, idx: int) -> bool:
+        """True when both views have at least one mask pixel equal to 1 (pipeline.py:372-395)."""
+        _, _, na, nq = self._masks_and_counts(results)
+        return bool(na[idx].item() > 0) and bool(nq[idx].item() > 0)
+
+    # ---- a8 -----------------------------------------------------------------------------------------------
+    def get_featmap_corrs(self, batch: dict, net_output: dict, results: dict, idx: int):
+        """Correspondences of pair ``idx`` between the two feature maps (pipeline.py:397-427)."""
+        ma, mq, _, _ = self._masks_and_counts(results)
+        fa, fq = net_output["featmap_a"][idx], net_output["featmap_q"][idx]
+        pred_corrs = nn_correspondences(fa, fq, ma[idx], mq[idx], self.dist_th, self.n_corrs, self.src_sampling, self.corrs_device)
+        if pred_corrs is not None:
+            ca, cq = pred_corrs[:, :2], pred_corrs[:, 2:]
+            pos_a = fa[:, ca[:, 0], ca[:, 1]].transpose(1, 0)
+            pos_q = fq[:, cq[:, 0], cq[:, 1]].transpose(1, 0)
+        else:
+            pos_a, pos_q = None, None
+        return pred_corrs, pos_a, pos_q
+
+    # ---- a9-a11 -------------------------------------------------------------------------------------------
+    def _lift(self, batch: dict, corrs: Tensor, idx: int) -> Tuple[Tensor, Tensor]:
+        depth_a, depth_q = batch["anchor"]["orig_depth"][idx].squeeze(), batch["query"]["orig_depth"][idx].squeeze()
+        cam_a, cam_q = batch["anchor"]["camera"][idx].reshape(9), batch["query"]["camera"][idx].reshape(9)
+        HA, WA = (int(v) for v in batch["anchor"]["sizes"][idx])
+        HQ, WQ = (int(v) for v in batch["query"]["sizes"][idx])
+        return corrs_to_pcd(corrs, as_device(depth_a, self.device), as_device(depth_q, self.device), cam_a, cam_q, self.featmap_size,
+                            (HA, WA), (HQ, WQ))
+
+    def get_pose(self, batch: dict, corrs: Tensor, idx: int) -> Tensor:
+        """3D-3D correspondences of pair ``idx`` and their registration -> ``[4,4]`` float32 CPU (pipeline.py:429-472)."""
+        pcd_a, pcd_q = self._lift(batch, corrs, idx)
+        if self.solver == "pointdsc":
+            pose4 = get_pointdsc_pose(self.pointdsc_solver, pcd_a, pcd_q, self.device)
+        else:
+            raise RuntimeError(f"Solver {self.solver} not implemented")
+        return pose4.to(torch.float32)
+
+    # ---- a12 ----------------------------------------------------------------------------------------------
+    def add_pred_pose(self, id_a: str, id_q: str, mask_a_iou, mask_q_iou, pred_pose: np.ndarray):
+        """One CSV line ``id_a,id_q,<12 floats>,iou_a,iou_q`` (pipeline.py:490-497; read back by
+        scripts/evaluation/compute_metrics.py:14-49)."""
+        pose = " ".join([str(n) for n in pred_pose[:3, :].flatten()])
+        line = ",".join([id_a, id_q, pose, str(mask_a_iou), str(mask_q_iou)]) + "\n"
+        if self.pred_file is not None:
+            self.pred_file.write(line)
+        return line
+
+    def select_correspondences(self, results: dict, net_output: dict, valid: List[bool]) -> List[Optional[Tensor]]:
+        """Batched ``nn_correspondences`` for every valid pair: one ROI compaction and one matching launch over ALL
+        ROI pixels, then per pair, in order, the reference's two draws (utils/pcd.py:187-190, :211) and selections."""
+        ma, mq, na, nq = self._masks_and_counts(results)
+        fa, fq = net_output["featmap_a"], net_output["featmap_q"]
+        B, D, H, W = fa.shape
+        roi_a, cnt_a = mask_to_roi(ma)
+        roi_q, cnt_q = mask_to_roi(mq)
+        n_a, n_q = cnt_a.tolist(), cnt_q.tolist()
+        n_a = [n if v else 0 for n, v in zip(n_a, valid)]
+        n_q = [n if v else 0 for n, v in zip(n_q, valid)]
+        out: List[Optional[Tensor]] = [None] * B
+        if not any(valid):
+            return out
+        idx, dist = match_nn(fa, fq, roi_a, roi_q, n_a, n_q)
+        for b in range(B):
+            if not valid[b]:
+                continue
+            n1 = n_a[b]
+            pix1, pix2 = roi_a[b, :n1], roi_q[b, :n_q[b]]
+            ib, db = idx[b, :n1], dist[b, :n1]
+            if self.src_sampling is not None and n1 > self.src_sampling:
+                sel = torch_sample_select(torch.empty(n1, 0, device=self.corrs_device), int(self.src_sampling)).to(self.device)
+                pix1, ib, db = pix1[sel], ib[sel], db[sel]
+            ok = torch.nonzero(db < self.dist_th).squeeze(1)
+            if ok.shape[0] > 1:
+                p1 = pix1[ok].long()
+                p2 = pix2[ib[ok].long()].long()
+                final = torch.stack((p1 // W, p1 % W, p2 // W, p2 % W), dim=1)
+                sel2 = torch_sample_select(torch.empty(final.shape[0], 0, device=self.corrs_device), self.n_corrs).to(self.device)
+                out[b] = final[sel2]
+        return out
+
+    def test_step(self, batch: dict, batch_idx: int = 0) -> List[dict]:
+        """The reference's hot loop (pipeline.py:306-355) for one batch; returns (and accumulates in ``self.rows``)
+        one record per pair: ids, ``pred_pose_rel`` (identity on failure, :335-350), ``pred_pose`` =
+        ``pred_pose_rel @ anchor pose`` (:320), IoUs, status, and writes the CSV line when a file is open."""
+        outputs = self.forward(batch)
+        results = self.mask_results(batch, outputs)
+        B = outputs["featmap_a"].shape[0]
+        _, _, na, nq = self._masks_and_counts(results)
+        valid = [(a > 0 and q > 0) for a, q in zip(na.tolist(), nq.tolist())]
+        corrs = self.select_correspondences(results, outputs, valid)
+        # lifting per pair, registration for all pairs with correspondences at once
+        todo, pa, pq = [], [], []
+        for b in range(B):
+            if corrs[b] is not None:
+                a, q = self._lift(batch, corrs[b], b)
+                todo.append(b), pa.append(a), pq.append(q)
+        poses = {}
+        if todo:
+            if self.solver != "pointdsc":
+                raise RuntimeError(f"Solver {self.solver} not implemented")
+            T = pointdsc_poses(self.pointdsc_solver.to(self.device), pa, pq).cpu().to(torch.float32)
+            poses = {b: T[i] for i, b in enumerate(todo)}
+        iou_a = results["iou_a"].cpu().numpy() if results["iou_a"] is not None else np.full(B, np.nan, np.float32)
+        iou_q = results["iou_q"].cpu().numpy() if results["iou_q"] is not None else np.full(B, np.nan, np.float32)
+        rows = []
+        for b in range(B):
+            id_a, id_q = batch["anchor"]["instance_id"][b], batch["query"]["instance_id"][b]
+            if b in poses:
+                pred_pose, status = poses[b], "ok"
+                pred_q = pred_pose @ batch["anchor"]["pose"][b].cpu().detach().to(torch.float32)
+            else:
+                pred_pose, status = torch.eye(4), ("no_corrs" if valid[b] else "invalid_mask")
+                pred_q = None
+            self.add_pred_pose(id_a, id_q, iou_a[b], iou_q[b], pred_pose.cpu().numpy())
+            rows.append(dict(instance_id_a=id_a, instance_id_q=id_q, pred_pose_rel=pred_pose, pred_pose=pred_q, iou_a=float(iou_a[b]),
+                             iou_q=float(iou_q[b]), status=status, corrs=corrs[b]))
+        self.rows.extend(rows)
+        return rows

@@ -217,3 +217,56 @@ def tensor_checksum(t: Tensor) -> str:
     """sha256 of the raw bytes: pins regenerated inputs to the ones the golden outputs came from."""
     import hashlib
     return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def synthetic_batch(seed: int, B: int, *, empty_mask_pairs=(), mask_frac: float = 0.12) -> Dict:
+    """A batch dict with the schema of the reference's ``CollateWrapper.__call__`` (datasets.py:202-245), filled
+    with synthetic RGB-D pairs (``synthetic_rgbd_pair``): the input contract of ``FPM_Pipeline.test_step``.
+    ``prompt_tokens [B,80,77]`` stands in for ``prompt`` (no BPE vocabulary offline)."""
+    from . import synth_backbone
+    pairs = [synthetic_rgbd_pair(seed * 1000 + i) for i in range(B)]
+    masks_a = torch.stack([ellipse_mask(224, 224, mask_frac, 0.5, 0.5, torch.uint8) for _ in range(B)])
+    masks_q = torch.stack([ellipse_mask(224, 224, mask_frac * 1.2, 0.52, 0.47, torch.uint8) for _ in range(B)])
+    for i in empty_mask_pairs:
+        masks_q[i] = 0
+    K = torch.stack([p["camera"] for p in pairs])
+    g = _gen(seed)
+    pose_a = torch.eye(4, dtype=torch.float64).repeat(B, 1, 1)
+    for i in range(B):
+        pose_a[i, :3, :3] = random_rotation(g, 30.0)
+        pose_a[i, :3, 3] = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64) + 0.1 * torch.randn(3, generator=g, dtype=torch.float64)
+    pose_q = torch.stack([p["T_rel"] for p in pairs]) @ pose_a
+    sizes = torch.tensor([[480, 640]] * B)
+
+    def view(key_rgb, key_depth, masks, poses, tag):
+        return dict(rgb=torch.stack([p[key_rgb] for p in pairs]), mask=masks, orig_depth=[p[key_depth] for p in pairs],
+                    camera=K.clone(), pose=poses, sizes=sizes.clone(), instance_id=[f"{tag}_{seed}_{i}" for i in range(B)])
+
+    return dict(anchor=view("rgb_a", "depth_a", masks_a, pose_a, "a"), query=view("rgb_q", "depth_q", masks_q, pose_q, "q"),
+                prompt_tokens=synth_backbone.synthetic_tokens(seed, 1).expand(B, -1, -1).contiguous(),
+                instance_id=[f"pair_{seed}_{i}" for i in range(B)], cls_id=[1] * B)
+
+
+def planted_network_outputs(seed: int, B: int, shift=(2, 3), noise: float = 0.02):
+    """Network outputs + batch for which the post-network path has a well-posed answer: the query feature map is
+    the anchor's rolled by ``shift`` feature-map pixels (+ noise), the depth maps are near-planar and rolled by the
+    same shift in raw pixels ((480/192, 640/192) per feature-map pixel), so true matches lift to 3-D points related
+    by a (near) pure translation that PointDSC recovers.  Returns ``(outputs, batch)`` with CPU tensors."""
+    g = _gen(seed)
+    feats_a, feats_q, logit_a, logit_q = [], [], [], []
+    batch = synthetic_batch(seed, B)
+    for i in range(B):
+        fa, _ = smooth_feature_pair(seed * 100 + i, 32, 192, 192, coarse=6, noise=noise)
+        fq = torch.roll(fa, shifts=shift, dims=(1, 2)) + noise * torch.randn(32, 192, 192, generator=g)
+        ma = ellipse_mask(192, 192, 0.10 + 0.03 * i, 0.5, 0.5, torch.float32)
+        mq = torch.roll(ma, shifts=shift, dims=(0, 1))
+        feats_a.append(fa), feats_q.append(fq)
+        logit_a.append((ma * 2 - 1) * (0.5 + torch.rand(192, 192, generator=g)))
+        logit_q.append((mq * 2 - 1) * (0.5 + torch.rand(192, 192, generator=g)))
+        coarse = torch.rand(1, 1, 4, 5, generator=g) * 60.0 + 970.0
+        da = F.interpolate(coarse, size=(480, 640), mode="bicubic", align_corners=True)[0, 0].round().to(torch.int32)
+        dq = torch.roll(da, shifts=(int(shift[0] * 480 / 192), int(shift[1] * 640 / 192)), dims=(0, 1))
+        batch["anchor"]["orig_depth"][i], batch["query"]["orig_depth"][i] = da, dq
+    outputs = dict(featmap_a=torch.stack(feats_a), featmap_q=torch.stack(feats_q),
+                   mask_a=torch.stack(logit_a).unsqueeze(1), mask_q=torch.stack(logit_q).unsqueeze(1))
+    return outputs, batch

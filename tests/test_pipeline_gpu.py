@@ -1,0 +1,167 @@
+"""GPU parity of the whole inference step, FPM_Pipeline.test_step (pipeline.py:306-355): network -> masks / IoU ->
+matching -> lifting -> PointDSC -> pose rows and CSV lines, on a synthetic batch with the CollateWrapper schema.
+
+The network itself is checked against the oracle in test_backbone_gpu.py (1e-3).  Here the oracle's post-network
+loop (oracle.post_network_step, pair by pair in the reference's order, CPU generator seeded as on_test_start does)
+is run on the SAME feature maps / mask logits the GPU produced, so every discrete quantity must agree exactly:
+masks, IoU, validity, the [500,4] correspondences (both multinomial draws included).
+
+Poses are compared (1e-4) on the planted case, where the correspondences describe a real rigid motion.  With seeded
+random network weights the matches are geometrically meaningless, registration has no consensus to find, and its
+answer hinges on which zero-score points ATen's unstable argsort happens to put in the seed list (see
+test_pointdsc_gpu.py): there only the rigid-transform property of the result is checked.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oryon_oracle as oracle
+from gpu_util import need_gpu
+from oryon_b200 import synth, synth_backbone as sb
+from oryon_b200.net import Oryon
+from oryon_b200.pipeline import FPM_Pipeline, mask_postproc
+from oryon_b200.utils.pointdsc.init import PointDSCSolver
+
+pytestmark = pytest.mark.gpu
+
+CFG = synth.POINTDSC_DEFAULT_CFG
+ARGS = dict(device="cuda:0", corrs_device="cpu", use_seed=False, seed=1,
+            dataset=dict(img_size=[224, 224], max_corrs=500),
+            model=dict(image_encoder=dict(img_size=[192, 192])),
+            test=dict(mask="predicted", src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
+
+
+@pytest.fixture(scope="module")
+def system():
+    need_gpu()
+    from oryon_b200 import _lib
+    _lib.destroy_all()
+    model = Oryon(None, "cuda:0", state_dict=sb.oryon_state_dict(11))
+    psd = synth.pointdsc_state_dict(300)
+    solver = PointDSCSolver(psd, in_dim=CFG["in_dim"], num_layers=CFG["num_layers"], num_channels=CFG["num_channels"],
+                            num_iterations=CFG["num_iterations"], ratio=CFG["ratio"], sigma_d=CFG["sigma_d"], k=CFG["k"],
+                            nms_radius=CFG["inlier_threshold"], device="cuda:0")
+    return model, solver, psd
+
+
+def _cuda_batch(batch):
+    out = dict(batch)
+    for key in ("anchor", "query"):
+        v = dict(batch[key])
+        v["rgb"], v["mask"] = v["rgb"].cuda(), v["mask"].cuda()
+        v["orig_depth"] = [d.cuda() for d in v["orig_depth"]]
+        out[key] = v
+    out["prompt_tokens"] = batch["prompt_tokens"].cuda()
+    return out
+
+
+@pytest.mark.parametrize("mask_mode", ["predicted", "oracle"])
+def test_test_step_equals_reference_loop(system, mask_mode, tmp_path):
+    model, solver, psd = system
+    args = dict(ARGS, test=dict(ARGS["test"], mask=mask_mode))
+    pipe = FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver)
+    batch = synth.synthetic_batch(7, 3, empty_mask_pairs=(1,) if mask_mode == "oracle" else ())
+    gb = _cuda_batch(batch)
+    csv = tmp_path / "pred.csv"
+    pipe.on_test_start(str(csv))                  # seeds torch CPU generator with 1 (pipeline.py:296-299)
+    outputs = pipe.forward(gb)
+    torch.manual_seed(1)
+    rows = pipe.test_step(gb, 0)
+    pipe.on_test_end()
+    cpu_out = {k: v.cpu() for k, v in outputs.items()}
+    torch.manual_seed(1)
+    torch.set_num_threads(8)
+    ref = oracle.post_network_step(cpu_out, batch, psd, CFG, mask_mode=mask_mode)
+    assert [r["status"] for r in rows] == [r["status"] for r in ref]
+    for i, (r, o) in enumerate(zip(rows, ref)):
+        assert (np.isnan(r["iou_a"]) and np.isnan(o["iou_a"])) or r["iou_a"] == o["iou_a"], i
+        assert (np.isnan(r["iou_q"]) and np.isnan(o["iou_q"])) or r["iou_q"] == o["iou_q"], i
+        if o["corrs"] is None:
+            assert r["corrs"] is None and torch.equal(r["pred_pose_rel"], torch.eye(4))
+            continue
+        assert torch.equal(r["corrs"].cpu(), o["corrs"]), f"pair {i}: correspondences differ"
+        R = r["pred_pose_rel"][:3, :3].double()
+        assert torch.allclose(R @ R.T, torch.eye(3, dtype=torch.float64), atol=1e-5) and abs(torch.det(R).item() - 1) < 1e-5
+        np.testing.assert_allclose(r["pred_pose"].numpy(), (r["pred_pose_rel"] @ batch["anchor"]["pose"][i].float()).numpy(), atol=1e-6)
+    if mask_mode == "oracle":
+        assert rows[1]["status"] == "invalid_mask"
+    lines = csv.read_text().strip().split("\n")
+    assert len(lines) == 3
+    f = lines[0].split(",")
+    assert f[0] == "a_7_0" and f[1] == "q_7_0" and len(f[2].split(" ")) == 12 and len(f) == 5   # id_a,id_q,<12 floats>,iou_a,iou_q
+
+
+class _PlantedModel:
+    """Stands in for the network: returns fixed (planted) outputs, so the post-network path has a well-posed answer."""
+
+    def __init__(self, outputs):
+        self.outputs = outputs
+
+    def forward(self, xs):
+        return self.outputs
+
+
+def test_post_network_path_recovers_and_matches_planted_pose(system):
+    _, solver, psd = system
+    outputs, batch = synth.planted_network_outputs(21, 4)
+    pipe = FPM_Pipeline(ARGS, test_model=True, model=_PlantedModel({k: v.cuda() for k, v in outputs.items()}), pointdsc_solver=solver)
+    gb = _cuda_batch(batch)
+    pipe.on_test_start()
+    rows = pipe.test_step(gb, 0)
+    torch.manual_seed(1)
+    torch.set_num_threads(8)
+    ref = oracle.post_network_step(outputs, batch, psd, CFG)
+    K = synth.NOCS_INTRINSICS
+    for i, (r, o) in enumerate(zip(rows, ref)):
+        assert r["status"] == o["status"] == "ok"
+        assert r["iou_a"] == o["iou_a"] and r["iou_q"] == o["iou_q"]
+        assert torch.equal(r["corrs"].cpu(), o["corrs"]), f"pair {i}: correspondences differ"
+        np.testing.assert_allclose(r["pred_pose_rel"].numpy(), o["pred_pose_rel"].numpy(), atol=1e-4)
+        np.testing.assert_allclose(r["pred_pose"].numpy(), o["pred_pose"].numpy(), atol=2e-4)
+        # the planted motion: a translation of (10 px * z / fx, 5 px * z / fy, 0) at z ~ 1 m
+        t = r["pred_pose_rel"][:3, 3].numpy()
+        np.testing.assert_allclose(t, [10.0 / K[0], 5.0 / K[4], 0.0], atol=5e-3)
+        np.testing.assert_allclose(r["pred_pose_rel"][:3, :3].numpy(), np.eye(3), atol=2e-2)
+
+
+def test_per_pair_interface_matches_batched(system):
+    """is_detection_valid / get_featmap_corrs / get_pose (reference signatures) give what test_step gives."""
+    model, solver, _ = system
+    pipe = FPM_Pipeline(ARGS, test_model=True, model=model, pointdsc_solver=solver)
+    gb = _cuda_batch(synth.synthetic_batch(8, 2))
+    torch.manual_seed(1)
+    rows = pipe.test_step(gb, 0)
+    outputs = pipe.forward(gb)
+    results = pipe.mask_results(gb, outputs)
+    torch.manual_seed(1)
+    for i in range(2):
+        assert pipe.is_detection_valid(results, gb, i) == (rows[i]["status"] != "invalid_mask")
+        corrs, pos_a, pos_q = pipe.get_featmap_corrs(gb, outputs, results, i)
+        if corrs is None:
+            assert rows[i]["corrs"] is None
+            continue
+        assert torch.equal(corrs, rows[i]["corrs"]) and pos_a.shape == (500, 32)
+        pose = pipe.get_pose(gb, corrs, i)
+        assert pose.dtype == torch.float32 and pose.device.type == "cpu"
+        np.testing.assert_allclose(pose.numpy(), rows[i]["pred_pose_rel"].numpy(), atol=1e-6)
+
+
+def test_mask_postproc_bit_exact():
+    need_gpu()
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(4, 1, 192, 192, generator=g)
+    logits[0, 0, :5, :5] = 0.0
+    logits[3] = -5.0                                   # empty prediction -> IoU of an empty union is NaN / 0
+    gt = (torch.rand(4, 224, 224, generator=g) > 0.6).to(torch.uint8)
+    gt[3] = 0
+    mp = mask_postproc(logits.cuda(), gt.cuda(), (192, 192), 0.5)
+    ref_mask = oracle.predicted_mask(logits, 0.5)
+    gt_c = torch.nn.functional.interpolate(gt.unsqueeze(1).float(), (192, 192), mode="nearest").squeeze(1)
+    assert torch.equal(mp["pred"].cpu().long(), ref_mask)
+    assert torch.equal(mp["gt_resized"].cpu().float(), gt_c)
+    iou = oracle.mask_iou(gt_c, ref_mask)
+    got = mp["iou"].cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(iou)) and torch.equal(got[~torch.isnan(got)], iou[~torch.isnan(iou)])
+    assert mp["n_pred"].cpu().tolist() == [int((ref_mask[i] == 1).sum()) for i in range(4)]
+    for i in range(4):
+        assert torch.equal(oracle.resize_mask_nearest(gt[i], (192, 192)), mp["gt_resized"][i].cpu())
