@@ -23,7 +23,9 @@ constexpr int kRowBlocks = 2;
 constexpr int kCtaRows = kTileM * kRowBlocks;
 constexpr int kKB = 64;                 // K elements per stage (128 bytes of fp16)
 constexpr int kThreads = 320;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 196 * 1024;
+constexpr int kEpiLd = 20;                                  // padded row stride of the per-warp staging tile (floats)
+constexpr int kEpiWarpFloats = 32 * kEpiLd + 128;           // staging tile + bias slice
 
 template <int TN, int NPASS>
 struct Cfg {
@@ -35,8 +37,9 @@ struct Cfg {
   static constexpr int kStage = kABytes + kWBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kBarBytes = 8 * (2 * kStages + 4) + 16;
-  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes;
+  static constexpr int kBarBytes = (8 * (2 * kStages + 4) + 16 + 15) / 16 * 16;
+  static constexpr int kEpiBytes = 8 * kEpiWarpFloats * 4;
+  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes + kEpiBytes;
   static constexpr int kTmemCols = 2 * kRowBlocks * TN;               // 512 / 256 / 128
   static_assert(kStages >= 2, "pipeline depth");
 };
@@ -168,94 +171,121 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ++tile_iter;
     }
   } else {
+    // ============================ epilogue (8 warps) ============================
+    // A warp owns 32 rows of one 128-row block (TMEM lane quarter = warp % 4).  Per 16-column chunk: tcgen05.ld
+    // (thread <-> row), alpha / bias / activation in registers, transpose through a private 32 x 16 staging tile so
+    // that the residual loads and every store are issued with 4 lanes per row: each instruction touches 8 rows x
+    // 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
     const int ew = warp - 2, rblk = ew >> 2, quarter = warp & 3;
     const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
     const Epilogue& ep = args.ep;
+    float* stage_f = reinterpret_cast<float*>(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats;  // [32][kEpiLd]
+    float* bias_s = stage_f + 32 * kEpiLd;                                                                       // [TN]
+    const int sub_row = lane >> 2, cg = lane & 3;
     uint32_t tile_iter = 0;
     for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
       const int nt = t % args.tiles_n, mt = (t / args.tiles_n) % args.tiles_m;
       const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
       const uint32_t buf = tile_iter & 1;
       const int row = mt * kCtaRows + row_in_cta;
-      int drow = row;
-      bool row_ok = row < args.M;
-      if (row_ok && ep.row_map) {
-        drow = ep.row_map[row];
-        row_ok = drow >= 0;
+      int drow = row < args.M ? row : -1;
+      if (drow >= 0 && ep.row_map) drow = ep.row_map[row];
+      const int64_t base32 = (int64_t)b1 * ep.out_b1 + (int64_t)b0 * ep.out_b0;
+      const int64_t baseh = (int64_t)b1 * ep.outh_b1 + (int64_t)b0 * ep.outh_b0;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < TN / 32; ++j) {
+        const int col = nt * TN + j * 32 + lane;
+        bias_s[j * 32 + lane] = (ep.bias && col < args.N) ? __ldg(ep.bias + col) : 0.f;
       }
-      const int64_t off32 = (int64_t)b1 * ep.out_b1 + (int64_t)b0 * ep.out_b0 + (int64_t)drow * ep.ld32;
-      const int64_t offh = (int64_t)b1 * ep.outh_b1 + (int64_t)b0 * ep.outh_b0;
+      __syncwarp();
       ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * TN) + rblk * TN;
 #pragma unroll 1
-      for (int g = 0; g < TN / 32; ++g) {
-        const int col0 = nt * TN + g * 32;
+      for (int g = 0; g < TN / 16; ++g) {
+        const int col0 = nt * TN + g * 16;
         if (col0 >= args.N) break;   // warp-uniform
-        __syncwarp();                // lanes of dropped rows skip the stores below: reconverge before the aligned load
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr + g * 32, v);
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(taddr + g * 16, v);
         ptx::tmem_ld_wait();
-        if (!row_ok) continue;
-        const bool full_chunk = col0 + 32 <= args.N;
-        float x[32];
+        float x[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float y = __uint_as_float(v[i]) * ep.alpha;
-          if (ep.bias && (full_chunk || col0 + i < args.N)) y += __ldg(ep.bias + col0 + i);
-          x[i] = apply_act(y, ep.act);
+        for (int i = 0; i < 4; ++i) {
+          const float4 bq = *reinterpret_cast<const float4*>(bias_s + g * 16 + 4 * i);
+          x[4 * i] = fmaf(__uint_as_float(v[4 * i]), ep.alpha, bq.x), x[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), ep.alpha, bq.y);
+          x[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), ep.alpha, bq.z), x[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), ep.alpha, bq.w);
         }
-        if (ep.residual) {
-          const float* r = ep.residual + off32 + col0;
-          if (full_chunk && (ep.ld32 & 3) == 0) {
+        switch (ep.act) {  // hoisted: one branch per chunk, straight-line math inside
+          case ACT_QUICKGELU:
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(r) + i);
-              x[4 * i] += q.x, x[4 * i + 1] += q.y, x[4 * i + 2] += q.z, x[4 * i + 3] += q.w;
-            }
-          } else {
+            for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.f + expf(-1.702f * x[i]));
+            break;
+          case ACT_GELU:
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < args.N) x[i] += r[i];
-          }
+            for (int i = 0; i < 16; ++i) x[i] = 0.5f * x[i] * (1.f + erff(x[i] * 0.70710678118654752440f));
+            break;
+          case ACT_RELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+            break;
+          default: break;
         }
-        if (ep.out32) {
-          float* o = ep.out32 + off32 + col0;
-          if (full_chunk && (ep.ld32 & 3) == 0) {
+        if (ep.transpose_h) {
+          // out_h element (m, n) lives at n * ldh + m: lanes are consecutive m, already coalesced
+          if (drow >= 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < args.N) o[i] = x[i];
-          }
-        }
-        if (ep.out_hi) {
-          __half hi[32], lo[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) split_half(x[i], hi[i], lo[i]);
-          if (ep.transpose_h) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < 16; ++i)
               if (col0 + i < args.N) {
-                const int64_t o = offh + (int64_t)(col0 + i) * ep.ldh + drow;
-                ep.out_hi[o] = hi[i];
-                if (ep.out_lo) ep.out_lo[o] = lo[i];
+                __half hh, ll;
+                split_half(x[i], hh, ll);
+                const int64_t o = baseh + (int64_t)(col0 + i) * ep.ldh + drow;
+                ep.out_hi[o] = hh;
+                if (ep.out_lo) ep.out_lo[o] = ll;
               }
+          }
+          if (!ep.out32) continue;
+        }
+        __syncwarp();  // previous chunk's readers are done with the staging tile
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(stage_f + lane * kEpiLd + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        __syncwarp();
+        const int col = col0 + cg * 4;
+        const bool vec_ok = col + 3 < args.N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = k * 8 + sub_row;
+          const int dr = __shfl_sync(0xffffffffu, drow, r);
+          if (dr < 0 || col >= args.N) continue;
+          float4 y = *reinterpret_cast<const float4*>(stage_f + r * kEpiLd + cg * 4);
+          const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
+          if (vec_ok && (ep.ld32 & 3) == 0) {
+            if (ep.residual) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(ep.residual + o32));
+              y.x += q.x, y.y += q.y, y.z += q.z, y.w += q.w;
+            }
+            if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o32) = y;
           } else {
-            const int64_t o = offh + (int64_t)drow * ep.ldh + col0;
-            if (full_chunk && (ep.ldh & 7) == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                reinterpret_cast<uint4*>(ep.out_hi + o)[i] = reinterpret_cast<const uint4*>(hi)[i];
-                if (ep.out_lo) reinterpret_cast<uint4*>(ep.out_lo + o)[i] = reinterpret_cast<const uint4*>(lo)[i];
+            float* yy = reinterpret_cast<float*>(&y);
+            for (int i = 0; i < 4; ++i)
+              if (col + i < args.N) {
+                if (ep.residual) yy[i] += ep.residual[o32 + i];
+                if (ep.out32) ep.out32[o32 + i] = yy[i];
               }
+          }
+          if (ep.out_hi && !ep.transpose_h) {
+            const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
+            __half hh[4], ll[4];
+            split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
+            if (vec_ok && (ep.ldh & 3) == 0) {
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
             } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < args.N) {
-                  ep.out_hi[o + i] = hi[i];
-                  if (ep.out_lo) ep.out_lo[o + i] = lo[i];
+              for (int i = 0; i < 4; ++i)
+                if (col + i < args.N) {
+                  ep.out_hi[oh + i] = hh[i];
+                  if (ep.out_lo) ep.out_lo[oh + i] = ll[i];
                 }
             }
           }
