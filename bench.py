@@ -118,6 +118,70 @@ def cpu_port_sample(rows, threads, D=WORKLOAD["D"], n=WORKLOAD["H"] * WORKLOAD["
     return best
 
 
+NCU_TRAFFIC_BYTES = 330.933504e6 + 24.936704e6   # profiles/r01_match_tc_ncu_full.md (config 2, one launch)
+
+
+def full_path_measure(pairs, local, peaks):
+    """Extra (non-contract) measurement: the WHOLE inference step -- FPM_Pipeline.test_step = network (CLIP ViT-L/14@336
+    + swin_b guidance + fusion + decoder) -> masks -> matching -> lifting -> PointDSC -- on `pairs` synthetic 224x224
+    RGB-D pairs (the reference's real sizes), seeded random weights, prompt embeddings cached as
+    the reference's 34-object benchmark allows.  Host batch in, pose rows out (H2D / D2H inside the timed region)."""
+    from oryon_b200 import _lib, synth, synth_backbone as sb
+    from oryon_b200.net import Oryon, gemm_counters
+    from oryon_b200.pipeline import FPM_Pipeline
+    from oryon_b200.utils.pointdsc.init import PointDSCSolver
+    cfg = synth.POINTDSC_DEFAULT_CFG
+    dev = f"cuda:{local}"
+    model = Oryon(None, dev, state_dict=sb.oryon_state_dict(11))
+    solver = PointDSCSolver(synth.pointdsc_state_dict(300), in_dim=cfg["in_dim"], num_layers=cfg["num_layers"],
+                            num_channels=cfg["num_channels"], num_iterations=cfg["num_iterations"], ratio=cfg["ratio"],
+                            sigma_d=cfg["sigma_d"], k=cfg["k"], nms_radius=cfg["inlier_threshold"], device=dev)
+    args = dict(device=dev, corrs_device="cpu", dataset=dict(img_size=[224, 224], max_corrs=500),
+                model=dict(image_encoder=dict(img_size=[192, 192])),
+                test=dict(mask="oracle", src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
+    pipe = FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver)
+    batch = synth.synthetic_batch(5, pairs)
+    emb = model.encode_tokens(batch["prompt_tokens"][0].cuda())[None].expand(pairs, -1, -1).contiguous()   # cached prompt set
+    for key in ("anchor", "query"):
+        batch[key]["rgb"] = batch[key]["rgb"].pin_memory()
+    batch["prompt_emb"] = emb
+    del batch["prompt_tokens"]
+    pipe.on_test_start()
+    for _ in range(2):
+        pipe.test_step(batch, 0)
+    torch.cuda.synchronize()
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rows = pipe.test_step(batch, 0)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    _lib.profile_enable(local, True)
+    _lib.profile_read(local)
+    gemm_counters(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = pipe.forward(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read(local)
+    _lib.profile_enable(local, False)
+    n_gemm, flops = gemm_counters(local)
+    gemm_ms = prof.get("gemm_tc", (0.0, 0))[0]
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
+    return {"workload": f"{pairs} synthetic pairs: 224x224 RGB -> CLIP ViT-L/14@336 + swin_b + fusion + decoder -> 32x192x192 maps -> "
+                        "matching (5000-row subsample) -> lift -> PointDSC (500 corrs)",
+            "pairs_per_s": pairs / dt, "ms_per_step": dt * 1e3, "network_ms": e0.elapsed_time(e1),
+            "status": {s: sum(r["status"] == s for r in rows) for s in ("ok", "no_corrs", "invalid_mask")},
+            "network_kernels_ms": {str(k): round(v[0], 3) for k, v in prof.items()},
+            "network_kernel_launches": int(sum(v[1] for v in prof.values())),
+            "gemm": {"launches": n_gemm, "algorithmic_tflop": flops / 1e12, "tflops": tf, "precision": "fp16 split pairs, 3 tcgen05 products "
+                     "per algorithmic product (float32-equivalent)", "tensor_pipe_tflops": (3 * tf if tf else None),
+                     "peak_tflops": peak_tf, "frac_algorithmic": (tf / peak_tf if tf else None),
+                     "frac_tensor_pipe": (3 * tf / peak_tf if tf else None)}}
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference matcher, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -156,6 +220,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=4096, help="anchor rows of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-path", action="store_true", help="skip the extra full-pipeline measurement (network + post-network)")
+    ap.add_argument("--full-pairs", type=int, default=16)
     ap.add_argument("--B", type=int, default=WORKLOAD["B"])
     ap.add_argument("--D", type=int, default=WORKLOAD["D"])
     ap.add_argument("--H", type=int, default=WORKLOAD["H"])
@@ -226,7 +292,7 @@ def main():
         h_dst = torch.empty(B, n, dtype=torch.float32).pin_memory()
 
         def e2e_step():
-            i, d = pcd.match_nn(ha, hq)          # H2D of both maps inside
+            i, d = pcd.match_nn_streamed(ha, hq, chunk_pairs=4)   # H2D of both maps inside, overlapped with the kernels
             h_idx.copy_(i, non_blocking=True)
             h_dst.copy_(d, non_blocking=True)
             torch.cuda.synchronize()
@@ -284,11 +350,18 @@ def main():
             "kernels_ms_per_step": {str(k): v[0] / args.steps for k, v in prof.items()},
             "match_stats_last_step": stats,
             "roofline": {"kernel": "match_tc_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved_tf / peak_tf if achieved_tf else None), "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved_tf / peak_tf if achieved_tf else None), "traffic": NCU_TRAFFIC_BYTES if (B, D, n) == (32, 128, 19200) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch "
+                                           "(profiles/r01_match_tc_ncu_full.md)", "peak_source": peak_src,
                          "algorithmic_flops_per_launch": flops, "launch_ms": tc_avg,
                          "hbm": {"algorithmic_bytes_per_step": bytes_, "achieved_gbs": bytes_ / (ms_max / args.steps * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": bytes_ / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak}},
         }
+        if not args.no_full_path and world == 1:
+            try:
+                line["full_path"] = full_path_measure(args.full_pairs, local, peaks)
+            except Exception as e:  # the contract line must still be printed
+                line["full_path"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             cpu_port_sample(32, threads)

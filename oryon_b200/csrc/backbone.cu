@@ -473,23 +473,62 @@ gemm::Epilogue ep_split(const SplitA& o, const float* bias, int act) {
   return e;
 }
 
-// CLIP residual attention blocks (clip/model.py ResidualAttentionBlock), x [n_seq*S][width] fp32 in place
+// CLIP residual attention blocks (clip/model.py ResidualAttentionBlock), x [n_seq*S][width] fp32 in place.
+// Long sequences (the vision tower, S = 577) run attention on the tensor cores: the QKV projection writes split
+// pairs, scores = alpha * Q K^T is a GEMM batched over (head, sequence) with strided operand views, a row softmax
+// writes split probabilities, and P V is a second batched GEMM against V^T that writes straight into the
+// concatenated-heads layout.  Short sequences (text tower, S = 77) use the shared-memory attention kernel.
 void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool causal, const std::vector<ClipBlock>& blocks) {
-  const int M = n_seq * S;
+  const int M = n_seq * S, d = width / heads;
+  const bool tc_attn = S >= 256 && !causal && d == 64;
   const size_t mark = c.ar.off;
   SplitA hsp = c.split(M, width);
-  float* qkv = c.ar.take<float>((size_t)M * 3 * width);
   SplitA att = c.split(M, width);
   SplitA hid = c.split(M, 4 * width);
+  float* qkv = nullptr;
+  SplitA qkvh{}, P{}, vt{};
+  float* scores = nullptr;
+  const int ldS = round_up(S, 4), ldP = round_up(S, 64);
+  if (tc_attn) {
+    qkvh = c.split(M, 3 * width);
+    scores = c.ar.take<float>((size_t)n_seq * heads * S * ldS);
+    P = c.split((size_t)n_seq * heads * S, ldP);
+    vt = c.split((size_t)n_seq * heads * d, ldP);
+  } else {
+    qkv = c.ar.take<float>((size_t)M * 3 * width);
+  }
+  const float scale = 1.f / sqrtf((float)d);
   for (const ClipBlock& b : blocks) {
     LnArgs l;
     l.x = x, l.ldx = width, l.C = width, l.gamma = b.ln1_g, l.beta = b.ln1_b, l.rows = M, l.out_hi = hsp.hi, l.out_lo = hsp.lo, l.ldh = width;
     c.ln(l);
-    c.gemm(hsp, M, b.qkv, ep_f32(qkv, 3 * width, b.qkv_b));
-    AttnArgs a;
-    a.qkv = qkv, a.ld = 3 * width, a.off_k = width, a.off_v = 2 * width, a.n_seq = n_seq, a.S = S, a.heads = heads, a.d = width / heads;
-    a.scale = 1.f / sqrtf((float)(width / heads)), a.causal = causal ? 1 : 0, a.out_hi = att.hi, a.out_lo = att.lo, a.ldh = width;
-    c.attn(a);
+    if (tc_attn) {
+      c.gemm(hsp, M, b.qkv, ep_split(qkvh, b.qkv_b, gemm::ACT_NONE));
+      if (!c.dry && !c.rc) c.rc = transpose_v(c.h, qkvh.hi, qkvh.lo, 3 * width, 2 * width, n_seq, S, heads, d, vt.hi, vt.lo, ldP, c.st);
+      if (!c.dry && !c.rc) {  // scores[seq][head] = scale * Q K^T
+        gemm::Problem p;
+        p.M = S, p.N = S, p.K = d, p.nb0 = heads, p.nb1 = n_seq, p.precision = c.prec;
+        p.A.hi = qkvh.hi, p.A.lo = qkvh.lo, p.A.ld = 3 * width, p.A.stride_b0 = d, p.A.stride_b1 = (int64_t)S * 3 * width;
+        p.W.hi = qkvh.hi + width, p.W.lo = qkvh.lo + width, p.W.ld = 3 * width, p.W.stride_b0 = d, p.W.stride_b1 = (int64_t)S * 3 * width;
+        p.ep.alpha = scale, p.ep.out32 = scores, p.ep.ld32 = ldS, p.ep.out_b0 = (int64_t)S * ldS, p.ep.out_b1 = (int64_t)heads * S * ldS;
+        c.rc = gemm::launch(c.h, p, c.st);
+      }
+      if (!c.dry && !c.rc) c.rc = softmax_split(c.h, scores, (int64_t)n_seq * heads * S, S, ldS, P.hi, P.lo, ldP, c.st);
+      if (!c.dry && !c.rc) {  // out[seq][s][head*d + :] = P V
+        gemm::Problem p;
+        p.M = S, p.N = d, p.K = S, p.nb0 = heads, p.nb1 = n_seq, p.precision = c.prec;
+        p.A.hi = P.hi, p.A.lo = P.lo, p.A.ld = ldP, p.A.stride_b0 = (int64_t)S * ldP, p.A.stride_b1 = (int64_t)heads * S * ldP;
+        p.W.hi = vt.hi, p.W.lo = vt.lo, p.W.ld = ldP, p.W.stride_b0 = (int64_t)d * ldP, p.W.stride_b1 = (int64_t)heads * d * ldP;
+        p.ep.out_hi = att.hi, p.ep.out_lo = att.lo, p.ep.ldh = width, p.ep.outh_b0 = d, p.ep.outh_b1 = (int64_t)S * width;
+        c.rc = gemm::launch(c.h, p, c.st);
+      }
+    } else {
+      c.gemm(hsp, M, b.qkv, ep_f32(qkv, 3 * width, b.qkv_b));
+      AttnArgs a;
+      a.qkv = qkv, a.ld = 3 * width, a.off_k = width, a.off_v = 2 * width, a.n_seq = n_seq, a.S = S, a.heads = heads, a.d = d;
+      a.scale = scale, a.causal = causal ? 1 : 0, a.out_hi = att.hi, a.out_lo = att.lo, a.ldh = width;
+      c.attn(a);
+    }
     c.gemm(att, M, b.out, ep_f32(x, width, b.out_b, gemm::ACT_NONE, x));
     l.gamma = b.ln2_g, l.beta = b.ln2_b;
     c.ln(l);

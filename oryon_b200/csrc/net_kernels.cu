@@ -310,6 +310,87 @@ int attention(oryon_handle* h, const AttnArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// softmax over materialised scores / V transpose (tensor-core attention path)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_split_kernel(const float* scores, int64_t rows, int S, int ld_in, __half* hi, __half* lo, int ld_out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+    const float* x = scores + r * ld_in;
+    float v[32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < S ? x[c] : -INFINITY;
+      m = fmaxf(m, v[i]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = (lane + 32 * i < S) ? expf(v[i] - m) : 0.f;
+      s += v[i];
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < ld_out) {
+        __half hh, ll;
+        split_half(c < S ? __fdiv_rn(v[i], s) : 0.f, hh, ll);
+        hi[r * ld_out + c] = hh;
+        if (lo) lo[r * ld_out + c] = ll;
+      }
+    }
+  }
+}
+
+int softmax_split(oryon_handle* h, const float* scores, int64_t rows, int S, int ld_in, __half* hi, __half* lo, int ld_out, cudaStream_t st) {
+  ORYON_REQUIRE(S <= 1024 && ld_out <= 1024, "softmax_split: S=%d unsupported", S);
+  h->span_begin(KID_ATTN, st);
+  softmax_split_kernel<<<blocks_for(rows, 8, h->sm_count * 32), 256, 0, st>>>(scores, rows, S, ld_in, hi, lo, ld_out);
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+__global__ void __launch_bounds__(256) transpose_v_kernel(const __half* qkv_hi, const __half* qkv_lo, int64_t ld, int off_v, int S, int heads, int d,
+                                                         __half* vt_hi, __half* vt_lo, int ld_out) {
+  __shared__ __half th[32][34], tl[32][34];
+  const int s0 = blockIdx.x * 32, d0 = blockIdx.y * 32, sh = blockIdx.z, seq = sh / heads, hd = sh % heads;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int s = s0 + i;
+    __half a = __float2half(0.f), b = a;
+    if (s < S && d0 + tx < d) {
+      const int64_t o = ((int64_t)seq * S + s) * ld + off_v + hd * d + d0 + tx;
+      a = qkv_hi[o];
+      if (qkv_lo) b = qkv_lo[o];
+    }
+    th[i][tx] = a, tl[i][tx] = b;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int dd = d0 + i, s = s0 + tx;
+    if (dd < d && s < ld_out) {
+      const int64_t o = ((int64_t)sh * d + dd) * ld_out + s;
+      vt_hi[o] = th[tx][i];
+      if (vt_lo) vt_lo[o] = tl[tx][i];
+    }
+  }
+}
+
+int transpose_v(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, int64_t ld, int off_v, int n_seq, int S, int heads, int d,
+                __half* vt_hi, __half* vt_lo, int ld_out, cudaStream_t st) {
+  h->span_begin(KID_ATTN, st);
+  transpose_v_kernel<<<dim3((ld_out + 31) / 32, (d + 31) / 32, n_seq * heads), 256, 0, st>>>(qkv_hi, qkv_lo, ld, off_v, S, heads, d, vt_hi, vt_lo,
+                                                                                         ld_out);
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // embeddings
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) clip_embed_ln_kernel(const float* patch, const float* cls, const float* pos, const float* gamma,
@@ -385,42 +466,51 @@ int eot_rows(oryon_handle* h, const int32_t* tokens, int n_seq, int L, int32_t* 
 // ------------------------------------------------------------------------------------------------
 // im2col
 // ------------------------------------------------------------------------------------------------
+// One warp per output row (pixel): taps in the outer loop (bounds test and source address once per tap), lanes
+// over the contiguous channel run of the tap -> coalesced 128-byte reads and 64-byte writes, no per-element division.
 __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
   const int Ct = a.C0 + a.C1, kk = a.k * a.k, half = a.k / 2;
-  const int64_t total = (int64_t)a.n * a.H * a.W * a.ld;
-  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
-    const int col = (int)(e % a.ld);
-    const int64_t row = e / a.ld;
-    float val = 0.f;
-    if (col < kk * Ct) {
-      const int tap = col / Ct, c = col % Ct;
-      const int x = (int)(row % a.W), y = (int)((row / a.W) % a.H), n = (int)(row / ((int64_t)a.W * a.H));
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)a.n * a.H * a.W;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 8) {
+    const int x = (int)(row % a.W), y = (int)((row / a.W) % a.H), n = (int)(row / ((int64_t)a.W * a.H));
+    __half* hi = a.hi + row * a.ld;
+    __half* lo = a.lo ? a.lo + row * a.ld : nullptr;
+    for (int tap = 0; tap < kk; ++tap) {
       const int yy = y + tap / a.k - half, xx = x + tap % a.k - half;
-      if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-        if (c < a.C0) {
-          if (a.shuffle0) {
-            const int64_t p = ((int64_t)n * (a.H / 2) + yy / 2) * (a.W / 2) + xx / 2;
-            val = __ldg(a.src0 + p * 4 * a.C0 + ((yy & 1) * 2 + (xx & 1)) * a.C0 + c);
-          } else {
-            val = __ldg(a.src0 + (((int64_t)n * a.H + yy) * a.W + xx) * a.C0 + c);
-          }
+      const bool inb = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+      const float* s0 = nullptr;
+      const float* s1 = nullptr;
+      if (inb) {
+        if (a.shuffle0) {
+          const int64_t p = ((int64_t)n * (a.H / 2) + yy / 2) * (a.W / 2) + xx / 2;
+          s0 = a.src0 + p * 4 * a.C0 + ((yy & 1) * 2 + (xx & 1)) * a.C0;
         } else {
-          val = __ldg(a.src1 + (((int64_t)n * a.H + yy) * a.W + xx) * a.C1 + (c - a.C0));
+          s0 = a.src0 + (((int64_t)n * a.H + yy) * a.W + xx) * a.C0;
         }
+        if (a.C1) s1 = a.src1 + (((int64_t)n * a.H + yy) * a.W + xx) * a.C1;
+      }
+      for (int c = lane; c < Ct; c += 32) {
+        float val = 0.f;
+        if (inb) val = c < a.C0 ? __ldg(s0 + c) : __ldg(s1 + (c - a.C0));
+        __half hh, ll;
+        split_half(val, hh, ll);
+        hi[tap * Ct + c] = hh;
+        if (lo) lo[tap * Ct + c] = ll;
       }
     }
-    __half hh, ll;
-    split_half(val, hh, ll);
-    a.hi[e] = hh;
-    if (a.lo) a.lo[e] = ll;
+    for (int c = kk * Ct + lane; c < a.ld; c += 32) {
+      hi[c] = __float2half(0.f);
+      if (lo) lo[c] = __float2half(0.f);
+    }
   }
 }
 
 int im2col(oryon_handle* h, const Im2colArgs& a, cudaStream_t st) {
   ORYON_REQUIRE(a.ld >= a.k * a.k * (a.C0 + a.C1), "im2col: ld too small");
-  const int64_t total = (int64_t)a.n * a.H * a.W * a.ld;
+  const int64_t rows = (int64_t)a.n * a.H * a.W;
   h->span_begin(KID_IM2COL, st);
-  im2col_kernel<<<blocks_for(total, 256, h->sm_count * 32), 256, 0, st>>>(a);
+  im2col_kernel<<<blocks_for(rows, 8, h->sm_count * 64), 256, 0, st>>>(a);
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
   return ORYON_OK;

@@ -52,6 +52,13 @@ struct AttnArgs {
 };
 int attention(oryon_handle* h, const AttnArgs& a, cudaStream_t st);
 
+// ---- pieces of the tensor-core attention path (long sequences: CLIP vision, S = 577) -------------------------------
+// row-wise softmax of fp32 scores [rows][ld_in] (S valid columns) -> split probabilities [rows][ld_out], zero padded
+int softmax_split(oryon_handle* h, const float* scores, int64_t rows, int S, int ld_in, __half* hi, __half* lo, int ld_out, cudaStream_t st);
+// V^T per (sequence, head): split qkv [n_seq*S][ld] (V at column off_v + head*d) -> [n_seq*heads][d][ld_out] with zero padding s >= S
+int transpose_v(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, int64_t ld, int off_v, int n_seq, int S, int heads, int d,
+                __half* vt_hi, __half* vt_lo, int ld_out, cudaStream_t st);
+
 // ---- CLIP embeddings ---------------------------------------------------------------------------------------
 // x[n][0] = cls + pos[0]; x[n][1+i] = patch[n*T+i] + pos[1+i]; then ln_pre.  (vlm.py:49-51)
 int clip_embed_ln(oryon_handle* h, const float* patch, const float* cls, const float* pos, const float* gamma, const float* beta, int n,

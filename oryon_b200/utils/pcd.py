@@ -89,6 +89,52 @@ def match_nn(feat_a: Tensor, feat_q: Tensor, roi_a: Optional[Tensor] = None, roi
     return idx, dist
 
 
+def match_nn_streamed(feat_a: Tensor, feat_q: Tensor, *, chunk_pairs: int = 4, out: Optional[Tuple[Tensor, Tensor]] = None
+                      ) -> Tuple[Tensor, Tensor]:
+    """Dense ``match_nn`` for HOST feature maps ``[B,D,H,W]`` (pinned memory for full speed): the batch is cut into
+    chunks of ``chunk_pairs`` pairs whose host-to-device copies run on a side stream, double buffered, while the
+    previous chunk is being matched -- the PCIe transfer (the slower of the two) hides the kernels.  Returns
+    device ``(idx int32 [B,HW], dist float32 [B,HW])``; the work is ordered on the current stream."""
+    dev = device_of()
+    if feat_a.is_cuda or feat_q.is_cuda:
+        return match_nn(feat_a, feat_q, out=out)
+    B, D = feat_a.shape[:2]
+    hw = feat_a[0, 0].numel()
+    if out is None:
+        out = (torch.empty(B, hw, dtype=torch.int32, device=dev), torch.empty(B, hw, dtype=torch.float32, device=dev))
+    idx, dist = out
+    cur = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    bufs = [(torch.empty(chunk_pairs, *feat_a.shape[1:], dtype=torch.float32, device=dev),
+             torch.empty(chunk_pairs, *feat_q.shape[1:], dtype=torch.float32, device=dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    starts = list(range(0, B, chunk_pairs))
+    side.wait_stream(cur)
+
+    def upload(i):
+        b0, k = starts[i], i % 2
+        n = min(chunk_pairs, B - b0)
+        with torch.cuda.stream(side):
+            if i >= 2:
+                side.wait_event(freed[k])
+            bufs[k][0][:n].copy_(feat_a[b0:b0 + n], non_blocking=True)
+            bufs[k][1][:n].copy_(feat_q[b0:b0 + n], non_blocking=True)
+            ready[k].record(side)
+
+    upload(0)
+    for i, b0 in enumerate(starts):
+        if i + 1 < len(starts):
+            upload(i + 1)
+        k, n = i % 2, min(chunk_pairs, B - b0)
+        cur.wait_event(ready[k])
+        match_nn(bufs[k][0][:n], bufs[k][1][:n], out=(idx[b0:b0 + n], dist[b0:b0 + n]))
+        freed[k].record(cur)
+    for a, q in bufs:
+        a.record_stream(cur), q.record_stream(cur)
+    return idx, dist
+
+
 def match_last_stats(device: Optional[torch.device] = None) -> dict:
     dev = device or device_of()
     s = (ctypes.c_int64 * 4)()
