@@ -1,0 +1,336 @@
+// attn_tc_kernel<NPASS>: fused softmax attention for long sequences on tcgen05 (CLIP vision tower, S = 577, d = 64;
+// reference call site models/vlm.py:54 -> nn.MultiheadAttention inside clip's ResidualAttentionBlock).
+//
+// One CTA = 128 queries of one (sequence, head).  Scores never leave the SM:
+//   warp 0      TMA producer   Q tile once; K tiles through a 2-stage ring; V^T tiles (single stage)
+//   warp 1      MMA issuer     S = Q K^T (M=128, N=128, K=64) into a double-buffered TMEM accumulator;
+//                              O += P V (M=128, N=64, K=128) into a third TMEM region
+//   warps 2..5  softmax        thread <-> query row (TMEM lane).  Pass 1 over the key tiles: exact row maximum.
+//                              Pass 2: S is recomputed (K = 64: cheap), p = exp2((s - max) * scale * log2 e), the row
+//                              sum accumulates in a register, p is written as an fp16 split pair straight into the
+//                              128B-swizzled K-major shared-memory layout the P V MMA consumes.  Finally O / sum is
+//                              stored as a split pair into the concatenated-heads activation.
+// Two passes instead of an online rescale keep the exact max-subtracted softmax of the reference and need no TMEM
+// read-modify-write of O; the extra Q K^T costs 1/3 more tensor work on a kernel that is bound by the exp / convert
+// work of the softmax warps.  Operands are fp16 split pairs; NPASS = 3 evaluates hi*hi + lo*hi + hi*lo (see gemm.cuh).
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx_sm100.cuh"
+
+namespace oryon {
+namespace attn {
+
+constexpr int kQ = 128;      // queries per CTA
+constexpr int kKT = 128;     // keys per tile
+constexpr int kD = 64;       // head dim
+constexpr int kThreads = 192;
+constexpr int kTileBytes = 128 * 64 * 2;   // one [128][64] fp16 tile, 128-byte rows, SWIZZLE_128B
+
+template <int NPASS>
+struct Cfg {
+  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kQBytes = kHalves * kTileBytes;
+  static constexpr int kKStage = kHalves * kTileBytes;
+  static constexpr int kVBytes = kHalves * kTileBytes;        // [64 d][128 keys] = two [64][64] sub-tiles per half
+  static constexpr int kPBytes = kHalves * 2 * kTileBytes;    // [128 q][128 keys] = two [128][64] sub-tiles per half
+  static constexpr int kOffK = kQBytes;
+  static constexpr int kOffV = kOffK + 2 * kKStage;
+  static constexpr int kOffP = kOffV + kVBytes;
+  static constexpr int kOffBar = kOffP + kPBytes;
+  static constexpr int kTotal = 1024 + kOffBar + 256;
+};
+
+struct Args {
+  int S, heads, T;            // T = key tiles
+  float scale_log2e;          // head_dim^-0.5 * log2(e)
+  __half* out_hi;
+  __half* out_lo;
+  int64_t ldh;
+};
+
+__device__ __forceinline__ void tma_load_2d_(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) { ptx::tma_load_2d(dst, m, bar, c0, c1); }
+
+__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_constant__ CUtensorMap tm_qkv_lo,
+               const __grid_constant__ CUtensorMap tm_vt_hi, const __grid_constant__ CUtensorMap tm_vt_lo, Args a, int width) {
+  using L = Cfg<NPASS>;
+  constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0);
+  constexpr uint32_t kIdescO = ptx::make_idesc_f16(128, 64, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + L::kOffK;
+  uint8_t* sV = smem + L::kOffV;
+  uint8_t* sP = smem + L::kOffP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* s_full = bars + 7;    // [2]
+  uint64_t* s_empty = bars + 9;   // [2]
+  uint64_t* p_full = bars + 11;
+  uint64_t* p_empty = bars + 12;
+  uint64_t* o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQ, head = blockIdx.y, seq = blockIdx.z;
+  const int T = a.T;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_qkv_hi);
+    ptx::prefetch_tensormap(&tm_vt_hi);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], 4);
+    ptx::mbar_init(v_full, 1), ptx::mbar_init(v_empty, 1), ptx::mbar_init(p_full, 4), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int row0 = seq * a.S;
+      ptx::mbar_arrive_expect_tx(q_full, L::kQBytes);
+      tma_load_2d_(sQ, &tm_qkv_hi, q_full, head * kD, row0 + q0);
+      if (NPASS == 3) tma_load_2d_(sQ + kTileBytes, &tm_qkv_lo, q_full, head * kD, row0 + q0);
+      for (int i = 0; i < 2 * T; ++i) {
+        const int st = i & 1, kt = i % T;
+        ptx::mbar_wait(&k_empty[st], ((i >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[st], L::kKStage);
+        tma_load_2d_(sK + st * L::kKStage, &tm_qkv_hi, &k_full[st], width + head * kD, row0 + kt * kKT);
+        if (NPASS == 3) tma_load_2d_(sK + st * L::kKStage + kTileBytes, &tm_qkv_lo, &k_full[st], width + head * kD, row0 + kt * kKT);
+        if (i >= T) {
+          const int j = i - T;
+          ptx::mbar_wait(v_empty, (j & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(v_full, L::kVBytes);
+          const int vrow = (seq * a.heads + head) * kD;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            tma_load_2d_(sV + sub * (kTileBytes / 2), &tm_vt_hi, v_full, j * kKT + sub * 64, vrow);
+            if (NPASS == 3) tma_load_2d_(sV + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, v_full, j * kKT + sub * 64, vrow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    auto issue_pv = [&](int j) {
+      ptx::mbar_wait(p_full, j & 1);
+      ptx::mbar_wait(v_full, j & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV);
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+          // pass 0: P_hi V_hi   pass 1: P_lo V_hi   pass 2: P_hi V_lo
+          const uint32_t pa = p_addr + (pass == 1 ? 2 * kTileBytes : 0);
+          const uint32_t va = v_addr + (pass == 2 ? kTileBytes : 0);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dp = ptx::make_smem_desc_kmajor(pa + sub * kTileBytes + k * 32, 128);
+              const uint64_t dv = ptx::make_smem_desc_kmajor(va + sub * (kTileBytes / 2) + k * 32, 128);
+              ptx::umma_f16(tmem_o, dp, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
+            }
+        }
+        ptx::umma_commit(v_empty);
+        ptx::umma_commit(p_empty);
+      }
+      __syncwarp();
+    };
+    ptx::mbar_wait(q_full, 0);
+    for (int i = 0; i < 2 * T; ++i) {
+      const int st = i & 1;
+      ptx::mbar_wait(&k_full[st], (i >> 1) & 1);
+      ptx::mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + st * L::kKStage);
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+          const uint32_t qa = q_addr + (pass == 1 ? kTileBytes : 0);
+          const uint32_t ka = k_addr + (pass == 2 ? kTileBytes : 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_f16(tmem_base + st * 128, ptx::make_smem_desc_kmajor(qa + k * 32, 128), ptx::make_smem_desc_kmajor(ka + k * 32, 128),
+                          kIdescS, (pass | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&k_empty[st]);
+        ptx::umma_commit(&s_full[st]);
+      }
+      __syncwarp();
+      if (i > T) issue_pv(i - 1 - T);
+    }
+    issue_pv(T - 1);
+    if (lane == 0) ptx::umma_commit(o_full);
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
+    const int r = quarter * 32 + lane;                  // row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float m = -INFINITY;
+    // ---- pass 1: exact row maximum ----
+    for (int i = 0; i < T; ++i) {
+      const int st = i & 1;
+      ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      const int key0 = i * kKT;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + g * 32, v);
+        ptx::tmem_ld_wait();
+        if (key0 + g * 32 + 32 <= a.S) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (key0 + g * 32 + c < a.S) m = fmaxf(m, __uint_as_float(v[c]));
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[st]);
+    }
+    // ---- pass 2: probabilities -> shared memory (swizzled K-major), row sum ----
+    float l = 0.f;
+    const float ms = m * a.scale_log2e;
+    uint8_t* prow_base = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int j = 0; j < T; ++j) {
+      const int i = T + j, st = i & 1;
+      ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      const int key0 = j * kKT;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + g * 32, v);
+        ptx::tmem_ld_wait();
+        __align__(16) __half hi[32];
+        __align__(16) __half lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float p = exp2f(fmaf(__uint_as_float(v[c]), a.scale_log2e, -ms));
+          if (key0 + g * 32 + c >= a.S) p = 0.f;
+          l += p;
+          split_half(p, hi[c], lo[c]);
+        }
+        if (g == 0 && j > 0) ptx::mbar_wait(p_empty, (j - 1) & 1);   // P V of the previous tile has consumed the buffer
+        // sub-tile (g / 2), 16-byte chunks (g % 2) * 4 .. + 3 of this row, XOR-swizzled with the row index
+        uint8_t* dst = prow_base + (g >> 1) * kTileBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int chunk = ((g & 1) * 4 + c) ^ (r & 7);
+          *reinterpret_cast<uint4*>(dst + chunk * 16) = reinterpret_cast<const uint4*>(hi)[c];
+          if (NPASS == 3) *reinterpret_cast<uint4*>(dst + 2 * kTileBytes + chunk * 16) = reinterpret_cast<const uint4*>(lo)[c];
+        }
+      }
+      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(p_full);
+        ptx::mbar_arrive(&s_empty[st]);
+      }
+    }
+    // ---- output: O / l -> split pair, concatenated heads ----
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    const int q = q0 + r;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + g * 32, v);
+      ptx::tmem_ld_wait();
+      if (q < a.S) {
+        __align__(16) __half hi[32];
+        __align__(16) __half lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) split_half(__uint_as_float(v[c]) * inv, hi[c], lo[c]);
+        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + g * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          reinterpret_cast<uint4*>(a.out_hi + o)[c] = reinterpret_cast<const uint4*>(hi)[c];
+          if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = reinterpret_cast<const uint4*>(lo)[c];
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int make_map_2d(oryon_handle* h, CUtensorMap* tm, const __half* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = h->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attn_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return ORYON_ERR_CUDA;
+  }
+  return ORYON_OK;
+}
+
+// qkv split pair [n_seq*S][3*width] (q | k | v column blocks, heads of 64), vt split pair [n_seq*heads*64][ld_vt] (V^T, zero padded
+// for keys >= S up to a multiple of 128) -> out split pair [n_seq*S][ldh] (heads concatenated).
+int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
+           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st) {
+  ORYON_REQUIRE(width == heads * kD, "attn_tc: head dim must be 64");
+  const int T = (S + kKT - 1) / kKT;
+  ORYON_REQUIRE(ld_vt >= T * kKT, "attn_tc: V^T rows must be padded to %d keys", T * kKT);
+  CUtensorMap tq_hi, tq_lo, tv_hi, tv_lo;
+  int rc;
+  const int64_t rows = (int64_t)n_seq * S;
+  if ((rc = make_map_2d(h, &tq_hi, qkv_hi, 3 * width, rows, 3 * width, 64, 128))) return rc;
+  if ((rc = make_map_2d(h, &tv_hi, vt_hi, ld_vt, (int64_t)n_seq * heads * kD, ld_vt, 64, 64))) return rc;
+  tq_lo = tq_hi, tv_lo = tv_hi;
+  if (precision == 3) {
+    if ((rc = make_map_2d(h, &tq_lo, qkv_lo, 3 * width, rows, 3 * width, 64, 128))) return rc;
+    if ((rc = make_map_2d(h, &tv_lo, vt_lo, ld_vt, (int64_t)n_seq * heads * kD, ld_vt, 64, 64))) return rc;
+  }
+  Args a;
+  a.S = S, a.heads = heads, a.T = T;
+  a.scale_log2e = (1.f / sqrtf((float)kD)) * 1.4426950408889634f;
+  a.out_hi = out_hi, a.out_lo = precision == 3 ? out_lo : nullptr, a.ldh = ldh;
+  const dim3 grid((S + kQ - 1) / kQ, heads, n_seq);
+  h->span_begin(KID_ATTN, st);
+  if (precision == 3) {
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::kTotal));
+    attn_tc_kernel<3><<<grid, kThreads, Cfg<3>::kTotal, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
+  } else {
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kTotal));
+    attn_tc_kernel<1><<<grid, kThreads, Cfg<1>::kTotal, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
+  }
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+}  // namespace attn
+}  // namespace oryon

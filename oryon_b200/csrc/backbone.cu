@@ -11,6 +11,7 @@
 // tcgen05 GEMM (gemm.cu); everything else is in net_kernels.cu.  Activations are fp32 token-major (NHWC); the two
 // images of every pair are processed together (N = 2B rows blocks: anchors first, then queries).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <string>
 
@@ -18,6 +19,10 @@
 #include "net_kernels.cuh"
 
 namespace oryon {
+namespace attn {
+int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
+           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st);
+}
 namespace net {
 
 using gemm::round_up;
@@ -488,11 +493,14 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
   float* qkv = nullptr;
   SplitA qkvh{}, P{}, vt{};
   float* scores = nullptr;
-  const int ldS = round_up(S, 4), ldP = round_up(S, 64);
+  static const bool materialized = getenv("ORYON_ATTN_MATERIALIZED") != nullptr;   // A/B switch: scores through HBM (two batched GEMMs)
+  const int ldS = round_up(S, 4), ldP = round_up(S, 128);
   if (tc_attn) {
     qkvh = c.split(M, 3 * width);
-    scores = c.ar.take<float>((size_t)n_seq * heads * S * ldS);
-    P = c.split((size_t)n_seq * heads * S, ldP);
+    if (materialized) {
+      scores = c.ar.take<float>((size_t)n_seq * heads * S * ldS);
+      P = c.split((size_t)n_seq * heads * S, ldP);
+    }
     vt = c.split((size_t)n_seq * heads * d, ldP);
   } else {
     qkv = c.ar.take<float>((size_t)M * 3 * width);
@@ -505,6 +513,10 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
     if (tc_attn) {
       c.gemm(hsp, M, b.qkv, ep_split(qkvh, b.qkv_b, gemm::ACT_NONE));
       if (!c.dry && !c.rc) c.rc = transpose_v(c.h, qkvh.hi, qkvh.lo, 3 * width, 2 * width, n_seq, S, heads, d, vt.hi, vt.lo, ldP, c.st);
+      if (!materialized) {
+        if (!c.dry && !c.rc)
+          c.rc = attn::launch(c.h, qkvh.hi, qkvh.lo, vt.hi, vt.lo, ldP, n_seq, S, heads, width, c.prec, att.hi, att.lo, width, c.st);
+      } else {
       if (!c.dry && !c.rc) {  // scores[seq][head] = scale * Q K^T
         gemm::Problem p;
         p.M = S, p.N = S, p.K = d, p.nb0 = heads, p.nb1 = n_seq, p.precision = c.prec;
@@ -521,6 +533,7 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
         p.W.hi = vt.hi, p.W.lo = vt.lo, p.W.ld = ldP, p.W.stride_b0 = (int64_t)d * ldP, p.W.stride_b1 = (int64_t)heads * d * ldP;
         p.ep.out_hi = att.hi, p.ep.out_lo = att.lo, p.ep.ldh = width, p.ep.outh_b0 = d, p.ep.outh_b1 = (int64_t)S * width;
         c.rc = gemm::launch(c.h, p, c.st);
+      }
       }
     } else {
       c.gemm(hsp, M, b.qkv, ep_f32(qkv, 3 * width, b.qkv_b));
