@@ -73,7 +73,7 @@ int64_t oryon_workspace_bytes(const oryon_handle* h);
  * Kernel ids: 0 prep_rows, 1 match_tc (tcgen05 similarity + argmax epilogue), 2 refine_rows,
  * 3 exact_rows, 4 mask_to_roi, 5 lift/corrs_to_pcd, 6 pointdsc SC matrix, 7 pointdsc NonLocalNet,
  * 8 pointdsc seeds/kNN/power/Kabsch/fitness, 9 pointdsc refinement, 10 backbone GEMM (tcgen05), 11 attention,
- * 12 normalisations, 13 element-wise / small fused heads, 14 im2col. */
+ * 12 normalisations, 13 element-wise / small fused heads, 14 im2col, 15 fused tcgen05 attention, 16 V transpose. */
 int oryon_profile_enable(oryon_handle* h, int enable);
 int oryon_profile_read(oryon_handle* h, double* total_ms, int64_t* launches, int n_ids);
 

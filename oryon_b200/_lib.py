@@ -145,7 +145,8 @@ def destroy_all() -> None:
 
 KERNEL_IDS = {"prep_rows": 0, "match_tc": 1, "refine_rows": 2, "exact_rows": 3, "mask_to_roi": 4, "lift": 5,
               "pointdsc_sc": 6, "pointdsc_net": 7, "pointdsc_seeds": 8, "pointdsc_refine": 9,
-              "gemm_tc": 10, "attention": 11, "norm": 12, "eltwise": 13, "im2col": 14}
+              "gemm_tc": 10, "attention": 11, "norm": 12, "eltwise": 13, "im2col": 14,
+              "attn_tc": 15, "transpose_v": 16}
 
 
 def profile_enable(device_index: int, enable: bool) -> None:

@@ -2,17 +2,23 @@
 // reference call site models/vlm.py:54 -> nn.MultiheadAttention inside clip's ResidualAttentionBlock).
 //
 // One CTA = 128 queries of one (sequence, head).  Scores never leave the SM:
-//   warp 0      TMA producer   Q tile once; K tiles through a 2-stage ring; V^T tiles (single stage)
+//   warp 0      TMA producer   Q tile once; K tiles and V^T tiles through 2-stage rings (both requested two tiles ahead:
+//                              a single V^T stage exposed one full TMA latency per key tile, 37k -> cycles per CTA)
 //   warp 1      MMA issuer     S = Q K^T (M=128, N=128, K=64) into a double-buffered TMEM accumulator;
 //                              O += P V (M=128, N=64, K=128) into a third TMEM region
-//   warps 2..5  softmax        thread <-> query row (TMEM lane).  Pass 1 over the key tiles: exact row maximum.
-//                              Pass 2: S is recomputed (K = 64: cheap), p = exp2((s - max) * scale * log2 e), the row
-//                              sum accumulates in a register, p is written as an fp16 split pair straight into the
-//                              128B-swizzled K-major shared-memory layout the P V MMA consumes.  Finally O / sum is
-//                              stored as a split pair into the concatenated-heads activation.
-// Two passes instead of an online rescale keep the exact max-subtracted softmax of the reference and need no TMEM
-// read-modify-write of O; the extra Q K^T costs 1/3 more tensor work on a kernel that is bound by the exp / convert
-// work of the softmax warps.  Operands are fp16 split pairs; NPASS = 3 evaluates hi*hi + lo*hi + hi*lo (see gemm.cuh).
+//   warps 2..9  softmax        thread <-> query row (TMEM lane); two warps per lane quarter, each owning 64 of the 128
+//                              key columns of a tile.  Pass 1 over the key tiles: row maximum (a single hi*hi product
+//                              is enough: softmax is invariant to the subtracted constant).  Pass 2: S is recomputed
+//                              (K = 64: cheap), p = exp2((s - max) * scale * log2 e), the row sum accumulates in a
+//                              register, p is held in registers as packed fp16 split pairs until the P V MMA of the
+//                              previous tile has released the buffer, then written straight into the 128B-swizzled
+//                              K-major shared-memory layout the P V MMA consumes.  Finally O / sum is stored as a
+//                              split pair into the concatenated-heads activation.
+// Two passes instead of an online rescale keep a max-subtracted softmax and need no TMEM read-modify-write of O; the
+// extra Q K^T costs little tensor work on a kernel that is bound by the exp / convert work of the softmax warps.
+// Operands are fp16 split pairs; NPASS = 3 evaluates hi*hi + lo*hi + hi*lo (see gemm.cuh).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "ptx_sm100.cuh"
@@ -23,7 +29,7 @@ namespace attn {
 constexpr int kQ = 128;      // queries per CTA
 constexpr int kKT = 128;     // keys per tile
 constexpr int kD = 64;       // head dim
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA, MMA, 8 softmax warps
 constexpr int kTileBytes = 128 * 64 * 2;   // one [128][64] fp16 tile, 128-byte rows, SWIZZLE_128B
 
 template <int NPASS>
@@ -35,9 +41,11 @@ struct Cfg {
   static constexpr int kPBytes = kHalves * 2 * kTileBytes;    // [128 q][128 keys] = two [128][64] sub-tiles per half
   static constexpr int kOffK = kQBytes;
   static constexpr int kOffV = kOffK + 2 * kKStage;
-  static constexpr int kOffP = kOffV + kVBytes;
+  static constexpr int kOffP = kOffV + 2 * kVBytes;
   static constexpr int kOffBar = kOffP + kPBytes;
-  static constexpr int kTotal = 1024 + kOffBar + 256;
+  static constexpr int kOffRed = kOffBar + 256;               // [2][128] floats: cross-warp max / sum exchange
+  static constexpr int kTotal = 1024 + kOffRed + 2 * 128 * 4;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 struct Args {
@@ -46,6 +54,7 @@ struct Args {
   __half* out_hi;
   __half* out_lo;
   int64_t ldh;
+  long long* dbg;             // optional per-phase clock64 stamps of CTA (0,0,0) (ORYON_ATTN_DEBUG)
 };
 
 __device__ __forceinline__ void tma_load_2d_(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) { ptx::tma_load_2d(dst, m, bar, c0, c1); }
@@ -72,25 +81,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
-  uint64_t* s_full = bars + 7;    // [2]
-  uint64_t* s_empty = bars + 9;   // [2]
-  uint64_t* p_full = bars + 11;
-  uint64_t* p_empty = bars + 12;
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_empty = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;
+  uint64_t* p_empty = bars + 14;
+  uint64_t* o_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQ, head = blockIdx.y, seq = blockIdx.z;
   const int T = a.T;
+  const bool dbg = a.dbg && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5;
+#define STAMP(slot) do { if (dbg && lane == 0) a.dbg[slot] = clock64(); } while (0)
+  if (dbg && threadIdx.x == 0) a.dbg[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_qkv_hi);
     ptx::prefetch_tensormap(&tm_vt_hi);
     ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], 4);
-    ptx::mbar_init(v_full, 1), ptx::mbar_init(v_empty, 1), ptx::mbar_init(p_full, 4), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], 8);
+      ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
+    }
+    ptx::mbar_init(p_full, 8), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -116,14 +131,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
         tma_load_2d_(sK + st * L::kKStage, &tm_qkv_hi, &k_full[st], width + head * kD, row0 + kt * kKT);
         if (NPASS == 3) tma_load_2d_(sK + st * L::kKStage + kTileBytes, &tm_qkv_lo, &k_full[st], width + head * kD, row0 + kt * kKT);
         if (i >= T) {
-          const int j = i - T;
-          ptx::mbar_wait(v_empty, (j & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(v_full, L::kVBytes);
+          const int j = i - T, vs = j & 1;
+          ptx::mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&v_full[vs], L::kVBytes);
           const int vrow = (seq * a.heads + head) * kD;
+          uint8_t* dst = sV + vs * L::kVBytes;
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            tma_load_2d_(sV + sub * (kTileBytes / 2), &tm_vt_hi, v_full, j * kKT + sub * 64, vrow);
-            if (NPASS == 3) tma_load_2d_(sV + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, v_full, j * kKT + sub * 64, vrow);
+            tma_load_2d_(dst + sub * (kTileBytes / 2), &tm_vt_hi, &v_full[vs], j * kKT + sub * 64, vrow);
+            if (NPASS == 3) tma_load_2d_(dst + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, &v_full[vs], j * kKT + sub * 64, vrow);
           }
         }
       }
@@ -131,10 +147,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
   } else if (warp == 1) {
     auto issue_pv = [&](int j) {
       ptx::mbar_wait(p_full, j & 1);
-      ptx::mbar_wait(v_full, j & 1);
+      STAMP(50 + j);
+      ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      STAMP(60 + j);
       ptx::tc_fence_after();
       if (lane == 0) {
-        const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV);
+        const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV + (j & 1) * L::kVBytes);
 #pragma unroll
         for (int pass = 0; pass < NPASS; ++pass) {
           // pass 0: P_hi V_hi   pass 1: P_lo V_hi   pass 2: P_hi V_lo
@@ -149,21 +167,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
               ptx::umma_f16(tmem_o, dp, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
             }
         }
-        ptx::umma_commit(v_empty);
+        ptx::umma_commit(&v_empty[j & 1]);
         ptx::umma_commit(p_empty);
       }
       __syncwarp();
     };
     ptx::mbar_wait(q_full, 0);
+    STAMP(1);
     for (int i = 0; i < 2 * T; ++i) {
       const int st = i & 1;
       ptx::mbar_wait(&k_full[st], (i >> 1) & 1);
+      STAMP(10 + i);
       ptx::mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
+      STAMP(30 + i);
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + st * L::kKStage);
+        const int npass = i < T ? 1 : NPASS;   // pass 1 only needs an approximate maximum
 #pragma unroll
         for (int pass = 0; pass < NPASS; ++pass) {
+          if (pass >= npass) break;
           const uint32_t qa = q_addr + (pass == 1 ? kTileBytes : 0);
           const uint32_t ka = k_addr + (pass == 2 ? kTileBytes : 0);
 #pragma unroll
@@ -182,19 +205,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     __syncwarp();
   } else {
     const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
+    const int half = (warp - 2) >> 2;                   // which 64 key columns of every tile this warp owns
     const int r = quarter * 32 + lane;                  // row of the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float* red = reinterpret_cast<float*>(smem + L::kOffRed);   // [2][128]
     float m = -INFINITY;
-    // ---- pass 1: exact row maximum ----
+    const bool dbg2 = dbg && warp == 2;
+    // ---- pass 1: row maximum ----
     for (int i = 0; i < T; ++i) {
       const int st = i & 1;
       ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
+      if (dbg2 && lane == 0) a.dbg[70 + i] = clock64();
       ptx::tc_fence_after();
-      const int key0 = i * kKT;
+      const int key0 = i * kKT + half * 64;
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + g * 32, v);
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + half * 64 + g * 32, v);
         ptx::tmem_ld_wait();
         if (key0 + g * 32 + 32 <= a.S) {
 #pragma unroll
@@ -209,73 +236,96 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[st]);
     }
-    // ---- pass 2: probabilities -> shared memory (swizzled K-major), row sum ----
+    red[half * 128 + r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(red[r], red[128 + r]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- pass 2: probabilities -> registers -> shared memory (swizzled K-major), row sum ----
     float l = 0.f;
     const float ms = m * a.scale_log2e;
-    uint8_t* prow_base = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* prow = sP + half * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;   // this row inside sub-tile `half`
     for (int j = 0; j < T; ++j) {
       const int i = T + j, st = i & 1;
       ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
+      if (dbg2 && lane == 0) a.dbg[70 + i] = clock64();
       ptx::tc_fence_after();
-      const int key0 = j * kKT;
-#pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
+      const int key0 = j * kKT + half * 64;
+      uint32_t ph[32], pl[32];   // packed half2: element 2c, 2c+1 of this warp's 64 columns
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + g * 32, v);
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + half * 64 + g * 32, v);
         ptx::tmem_ld_wait();
-        __align__(16) __half hi[32];
-        __align__(16) __half lo[32];
+        const bool full = key0 + g * 32 + 32 <= a.S;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float p = exp2f(fmaf(__uint_as_float(v[c]), a.scale_log2e, -ms));
-          if (key0 + g * 32 + c >= a.S) p = 0.f;
-          l += p;
-          split_half(p, hi[c], lo[c]);
-        }
-        if (g == 0 && j > 0) ptx::mbar_wait(p_empty, (j - 1) & 1);   // P V of the previous tile has consumed the buffer
-        // sub-tile (g / 2), 16-byte chunks (g % 2) * 4 .. + 3 of this row, XOR-swizzled with the row index
-        uint8_t* dst = prow_base + (g >> 1) * kTileBytes;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = ((g & 1) * 4 + c) ^ (r & 7);
-          *reinterpret_cast<uint4*>(dst + chunk * 16) = reinterpret_cast<const uint4*>(hi)[c];
-          if (NPASS == 3) *reinterpret_cast<uint4*>(dst + 2 * kTileBytes + chunk * 16) = reinterpret_cast<const uint4*>(lo)[c];
+        for (int c = 0; c < 16; ++c) {
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[2 * c]), a.scale_log2e, -ms)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[2 * c + 1]), a.scale_log2e, -ms)));
+          if (!full) {
+            if (key0 + g * 32 + 2 * c >= a.S) p0 = 0.f;
+            if (key0 + g * 32 + 2 * c + 1 >= a.S) p1 = 0.f;
+          }
+          l += p0 + p1;
+          const __half2 h2 = __floats2half2_rn(p0, p1);
+          const float2 back = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(p0 - back.x, p1 - back.y);
+          ph[g * 16 + c] = *reinterpret_cast<const uint32_t*>(&h2);
+          pl[g * 16 + c] = *reinterpret_cast<const uint32_t*>(&l2);
         }
       }
-      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(p_full);
-        ptx::mbar_arrive(&s_empty[st]);
+      if (lane == 0) ptx::mbar_arrive(&s_empty[st]);              // S buffer drained: the next Q K^T may overwrite it
+      if (dbg2 && lane == 0) a.dbg[90 + j] = clock64();
+      if (j > 0) ptx::mbar_wait(p_empty, (j - 1) & 1);             // P V of the previous tile has consumed the buffer
+      if (dbg2 && lane == 0) a.dbg[100 + j] = clock64();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                                // 8 chunks of 16 bytes = this warp's 64 columns
+        const int chunk = c ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
+        if (NPASS == 3)
+          *reinterpret_cast<uint4*>(prow + 2 * kTileBytes + chunk * 16) = make_uint4(pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
       }
+      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    // ---- output: O / l -> split pair, concatenated heads ----
+    red[half * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l = red[r] + red[128 + r];
+    // ---- output: O / l -> split pair, concatenated heads; this warp stores columns half*32 .. +31 ----
     ptx::mbar_wait(o_full, 0);
+    if (dbg2 && lane == 0) a.dbg[110] = clock64();
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     const int q = q0 + r;
-#pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
+    {
       uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + g * 32, v);
+      ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + half * 32, v);
       ptx::tmem_ld_wait();
       if (q < a.S) {
-        __align__(16) __half hi[32];
-        __align__(16) __half lo[32];
+        uint32_t oh[16], ol[16];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) split_half(__uint_as_float(v[c]) * inv, hi[c], lo[c]);
-        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + g * 32;
+        for (int c = 0; c < 16; ++c) {
+          const float x0 = __uint_as_float(v[2 * c]) * inv, x1 = __uint_as_float(v[2 * c + 1]) * inv;
+          const __half2 h2 = __floats2half2_rn(x0, x1);
+          const float2 back = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
+          oh[c] = *reinterpret_cast<const uint32_t*>(&h2), ol[c] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + half * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          reinterpret_cast<uint4*>(a.out_hi + o)[c] = reinterpret_cast<const uint4*>(hi)[c];
-          if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = reinterpret_cast<const uint4*>(lo)[c];
+          reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
+          if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
         }
       }
     }
     ptx::tc_fence_before();
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) a.dbg[111] = clock64();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -318,8 +368,17 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
   a.S = S, a.heads = heads, a.T = T;
   a.scale_log2e = (1.f / sqrtf((float)kD)) * 1.4426950408889634f;
   a.out_hi = out_hi, a.out_lo = precision == 3 ? out_lo : nullptr, a.ldh = ldh;
+  a.dbg = nullptr;
+  static const bool want_dbg = getenv("ORYON_ATTN_DEBUG") != nullptr;
+  static long long* dbg_dev = nullptr;
+  static int dbg_calls = 0;
+  if (want_dbg) {
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 128 * sizeof(long long));
+    cudaMemsetAsync(dbg_dev, 0, 128 * sizeof(long long), st);
+    a.dbg = dbg_dev;
+  }
   const dim3 grid((S + kQ - 1) / kQ, heads, n_seq);
-  h->span_begin(KID_ATTN, st);
+  h->span_begin(KID_ATTN_TC, st);
   if (precision == 3) {
     ORYON_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::kTotal));
     attn_tc_kernel<3><<<grid, kThreads, Cfg<3>::kTotal, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
@@ -329,6 +388,17 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
   }
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
+  if (want_dbg && ++dbg_calls == 30) {
+    long long t[128];
+    cudaMemcpyAsync(t, dbg_dev, sizeof(t), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    auto rel = [&](int i) { return t[i] ? (long long)(t[i] - t[0]) : -1; };
+    fprintf(stderr, "attn_tc dbg: q_full %lld end %lld o_full %lld\n", rel(1), rel(111), rel(110));
+    for (int i = 0; i < 2 * T; ++i)
+      fprintf(stderr, "  i=%d k_full %lld s_empty %lld | softmax s_full %lld\n", i, rel(10 + i), rel(30 + i), rel(70 + i));
+    for (int j = 0; j < T; ++j)
+      fprintf(stderr, "  j=%d mma p_full %lld v_full %lld | softmax exp_done %lld p_empty %lld\n", j, rel(50 + j), rel(60 + j), rel(90 + j), rel(100 + j));
+  }
   return ORYON_OK;
 }
 

@@ -56,7 +56,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 namespace oryon {
 // Optional per-kernel timing (oryon_profile_enable): CUDA events recorded on the caller's stream around
 // each kernel launch, summed per kernel id when read.  Off by default (no events are recorded).
-enum KernelId { KID_PREP = 0, KID_MATCH_TC = 1, KID_REFINE = 2, KID_EXACT = 3, KID_MASK_ROI = 4, KID_LIFT = 5, KID_PDSC_SC = 6, KID_PDSC_NET = 7, KID_PDSC_SEEDS = 8, KID_PDSC_REFINE = 9, KID_GEMM = 10, KID_ATTN = 11, KID_NORM = 12, KID_ELTWISE = 13, KID_IM2COL = 14, KID_COUNT = 32 };
+enum KernelId { KID_PREP = 0, KID_MATCH_TC = 1, KID_REFINE = 2, KID_EXACT = 3, KID_MASK_ROI = 4, KID_LIFT = 5, KID_PDSC_SC = 6, KID_PDSC_NET = 7, KID_PDSC_SEEDS = 8, KID_PDSC_REFINE = 9, KID_GEMM = 10, KID_ATTN = 11, KID_NORM = 12, KID_ELTWISE = 13, KID_IM2COL = 14, KID_ATTN_TC = 15, KID_TRANSPOSE = 16, KID_COUNT = 32 };
 struct ProfSpan {
   int id;
   cudaEvent_t a, b;

@@ -91,6 +91,56 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
   }
 }
 
+// Dense fast path (no ROI list, HW % 2 == 0): 64 consecutive pixels per CTA, float2 loads (256 contiguous bytes per channel
+// row instead of 128), the tile is normalised in place once and then written twice (fp32 rows, fp16 rows) with
+// lane <-> channel so that every store instruction covers a contiguous 128 / 64 bytes of one output row.
+constexpr int kPrepPix = 64;
+
+__global__ void __launch_bounds__(256) prep_dense_kernel(PrepArgs a) {
+  extern __shared__ float tile[];  // [D][kPrepPix + 1]
+  __shared__ float red[4][kPrepPix];
+  __shared__ float nrm[kPrepPix];
+  constexpr int LD = kPrepPix + 1;
+  const int side = blockIdx.z, b = blockIdx.y, r0 = blockIdx.x * kPrepPix;
+  const int hw = a.hw[side];
+  if (r0 >= hw) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = a.feat[side] + (size_t)b * a.D * hw + r0;
+  const int npix = min(kPrepPix, hw - r0);
+  for (int d = warp; d < a.D; d += 8) {
+    float2 v = make_float2(0.f, 0.f);
+    if (2 * lane + 1 < npix) v = __ldg(reinterpret_cast<const float2*>(src + (size_t)d * hw) + lane);
+    else if (2 * lane < npix) v.x = __ldg(src + (size_t)d * hw + 2 * lane);
+    tile[d * LD + 2 * lane] = v.x, tile[d * LD + 2 * lane + 1] = v.y;
+  }
+  __syncthreads();
+  {
+    const int p = threadIdx.x & (kPrepPix - 1), part = threadIdx.x / kPrepPix;
+    float ss = 0.f;
+    for (int d = part; d < a.D; d += 4) ss = fmaf(tile[d * LD + p], tile[d * LD + p], ss);
+    red[part][p] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x < kPrepPix) {
+    const int p = threadIdx.x;
+    // same accumulation grouping as prep_rows_kernel is not required: both feed sqrt -> fp32 norm (1 ulp differences
+    // in the norm cannot change a row's direction by more than fp32 rounding, covered by the refine pass tolerance)
+    nrm[p] = fmaxf(sqrtf(red[0][p] + red[1][p] + red[2][p] + red[3][p]), 1e-8f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.D * kPrepPix; i += 256) {
+    const int d = i / kPrepPix, p = i % kPrepPix;
+    tile[d * LD + p] = __fdiv_rn(tile[d * LD + p], nrm[p]);
+  }
+  __syncthreads();
+  float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;
+  __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
+  for (int row = warp; row < npix; row += 8) {
+    for (int d = lane; d < a.D4; d += 32) d32[(size_t)row * a.D4 + d] = d < a.D ? tile[d * LD + row] : 0.f;
+    for (int d = lane; d < a.Dpad; d += 32) d16[(size_t)row * a.Dpad + d] = __float2half_rn(d < a.D ? tile[d * LD + row] : 0.f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // exact fp32 rows (mode ORYON_MATCH_EXACT_FP32 and overflow fallback)
 // ------------------------------------------------------------------------------------------------
@@ -656,11 +706,18 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     pa.rows32[0] = h->rows32_a.as<float>(), pa.rows32[1] = h->rows32_q.as<float>();
     pa.meta = d_meta;
     pa.D = D, pa.D4 = D4, pa.Dpad = Dpad;
-    const dim3 grid((std::max(max_a, max_q) + 31) / 32, B, 2);
-    const size_t smem = (size_t)D * 33 * sizeof(float);
-    ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     h->span_begin(KID_PREP, st);
-    prep_rows_kernel<<<grid, 256, smem, st>>>(pa);
+    if (!roi_a && !roi_q && (HW_a % 2) == 0 && (HW_q % 2) == 0) {
+      const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, B, 2);
+      const size_t smem = (size_t)D * (kPrepPix + 1) * sizeof(float);
+      ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prep_dense_kernel<<<grid, 256, smem, st>>>(pa);
+    } else {
+      const dim3 grid((std::max(max_a, max_q) + 31) / 32, B, 2);
+      const size_t smem = (size_t)D * 33 * sizeof(float);
+      ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prep_rows_kernel<<<grid, 256, smem, st>>>(pa);
+    }
     h->span_end(st);
     ORYON_CUDA_CHECK(cudaGetLastError());
     ++h->last_launches;

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* qkv_hi, 
 
 int transpose_v(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, int64_t ld, int off_v, int n_seq, int S, int heads, int d,
                 __half* vt_hi, __half* vt_lo, int ld_out, cudaStream_t st) {
-  h->span_begin(KID_ATTN, st);
+  h->span_begin(KID_TRANSPOSE, st);
   transpose_v_kernel<<<dim3((ld_out + 31) / 32, (d + 31) / 32, n_seq * heads), 256, 0, st>>>(qkv_hi, qkv_lo, ld, off_v, S, heads, d, vt_hi, vt_lo,
                                                                                          ld_out);
   h->span_end(st);
