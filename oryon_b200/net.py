@@ -6,6 +6,7 @@ no fallback: without the library or an sm_100 device every call raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_void_p
 from typing import Dict, List, Optional, Sequence
 
@@ -17,6 +18,7 @@ from ._torch_glue import as_device, ptr, require_cuda, stream_ptr
 
 N_PROMPTS, CTX, EMBED = 80, 77, 768
 FEAT_C, FEAT_HW = 32, 192
+DEFAULT_BPE = "pretrained_models/bpe_simple_vocab_16e6.txt.gz"
 
 
 class Oryon:
@@ -35,6 +37,9 @@ class Oryon:
             if torch.cuda.is_available() else require_cuda()
         self.vis_layers, self.txt_layers, self.precision = int(vis_layers), int(txt_layers), int(precision)
         self.max_pairs_per_pass = int(max_pairs_per_pass)
+        if tokenizer is None and os.path.exists(DEFAULT_BPE):   # the path the reference hard-codes (models/vlm.py:23)
+            from .models.tokenizer import SimpleTokenizer
+            tokenizer = SimpleTokenizer(DEFAULT_BPE)
         self.tokenizer = tokenizer
         self.training = False
         self._loaded = False
