@@ -142,8 +142,9 @@ def full_path_measure(pairs, local, peaks):
     pipe = FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver)
     batch = synth.synthetic_batch(5, pairs)
     emb = model.encode_tokens(batch["prompt_tokens"][0].cuda())[None].expand(pairs, -1, -1).contiguous()   # cached prompt set
-    for key in ("anchor", "query"):
+    for key in ("anchor", "query"):     # the batch as the B200 collate stages it: pinned RGB, depth frames stacked + pinned
         batch[key]["rgb"] = batch[key]["rgb"].pin_memory()
+        batch[key]["orig_depth"] = torch.stack(batch[key]["orig_depth"]).pin_memory()
     batch["prompt_emb"] = emb
     del batch["prompt_tokens"]
     pipe.on_test_start()
@@ -167,6 +168,15 @@ def full_path_measure(pairs, local, peaks):
     prof = _lib.profile_read(local)
     _lib.profile_enable(local, False)
     n_gemm, flops = gemm_counters(local)
+    _lib.profile_enable(local, True)
+    t1 = time.perf_counter()
+    pipe.test_step(batch, 0)
+    torch.cuda.synchronize()
+    step_profiled_ms = (time.perf_counter() - t1) * 1e3
+    prof_step = _lib.profile_read(local)
+    _lib.profile_enable(local, False)
+    net_ids = {"gemm_tc", "attention", "norm", "eltwise", "im2col", "attn_tc", "transpose_v"}
+    post = {str(k): round(v[0], 3) for k, v in prof_step.items() if k not in net_ids}
     gemm_ms = prof.get("gemm_tc", (0.0, 0))[0]
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
@@ -175,6 +185,9 @@ def full_path_measure(pairs, local, peaks):
             "pairs_per_s": pairs / dt, "ms_per_step": dt * 1e3, "network_ms": e0.elapsed_time(e1),
             "status": {s: sum(r["status"] == s for r in rows) for s in ("ok", "no_corrs", "invalid_mask")},
             "network_kernels_ms": {str(k): round(v[0], 3) for k, v in prof.items()},
+            "post_network_ms": dt * 1e3 - e0.elapsed_time(e1), "post_network_kernels_ms": post,
+            "post_network_note": "matching + two CPU-generator draws per pair + selection/lifting + PointDSC + pose rows; kernel times from "
+                                 f"one extra profiled step ({step_profiled_ms:.1f} ms with per-kernel events)",
             "network_kernel_launches": int(sum(v[1] for v in prof.values())),
             "gemm": {"launches": n_gemm, "algorithmic_tflop": flops / 1e12, "tflops": tf, "precision": "fp16 split pairs, 3 tcgen05 products "
                      "per algorithmic product (float32-equivalent)", "tensor_pipe_tflops": (3 * tf if tf else None),

@@ -125,6 +125,23 @@ int oryon_corrs_to_pcd(oryon_handle* h, const int64_t* corrs, int n, int feat_h,
                        const void* depth_q, int depth_dtype, int Ha, int Wa, int Hq, int Wq, const double* cam_a,
                        const double* cam_q, float* pcd_a, float* pcd_q, int32_t* n_valid, void* stream);
 
+/* Batched form of the tail of nn_correspondences plus the function above, for B pairs in one launch: the
+ * row selection utils/pcd.py:207-212 (roi1[valid], roi2[argmin][valid], final_corrs[idxs]) followed by
+ * pipeline.py:447-460.  The caller performs the random draws (they stay on torch's generator) and passes, per pair,
+ * the positions in the anchor ROI list of the max_corrs selected rows.
+ *   rows            DEVICE  int32 [B][n]  positions in pair b's anchor list; rows[b][0] < 0: pair has no correspondences
+ *   roi_a, roi_q    DEVICE  int32 [B][cap_a] / [B][cap_q]  pixel-id lists given to oryon_match_nn
+ *   nn_idx          DEVICE  int32 [B][cap_a]               out_idx of oryon_match_nn
+ *   depth_a/q       DEVICE  [B][Ha][Wa] / [B][Hq][Wq] of `depth_dtype` (one frame size per call)
+ *   cams_a, cams_q  HOST    float64 [B][9]
+ *   corrs           DEVICE  int64 [B][n][4]  (y1,x1,y2,x2) feature-map coordinates == nn_correspondences' result
+ *   pcd_a, pcd_q    DEVICE  float32 [B][n][3] metres, first n_valid[b] rows of pair b written
+ *   n_valid         DEVICE  int32 [B]  (-1 for pairs without correspondences) */
+int oryon_select_lift(oryon_handle* h, const int32_t* rows, int B, int n, const int32_t* roi_a, const int32_t* roi_q,
+                      const int32_t* nn_idx, int cap_a, int cap_q, int feat_h, int feat_w, const void* depth_a, const void* depth_q,
+                      int depth_dtype, int Ha, int Wa, int Hq, int Wq, const double* cams_a, const double* cams_q, int64_t* corrs,
+                      float* pcd_a, float* pcd_q, int32_t* n_valid, void* stream);
+
 /* utils/pcd.py:35-81 lift_pcd with xy_idxs: out[i] = ((x-cx)*z/fx, (y-cy)*z/fy, z), z = depth[y][x].
  *   xs, ys DEVICE int64 [n]; out DEVICE float32 [n][3] in depth units (the caller divides by 1000). */
 int oryon_lift_pcd(oryon_handle* h, const void* depth, int depth_dtype, int H, int W, const double* cam,

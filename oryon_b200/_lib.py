@@ -62,6 +62,9 @@ SIGNATURES = {
     "oryon_mask_to_roi": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "oryon_corrs_to_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "oryon_select_lift": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "oryon_lift_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),
     "oryon_gemm_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -57,6 +57,8 @@ namespace lift {
 int run_lift(oryon_handle*, const void*, int, int, int, const double*, const int64_t*, const int64_t*, int, float*, cudaStream_t);
 int run_corrs_to_pcd(oryon_handle*, const int64_t*, int, int, int, const void*, const void*, int, int, int, int, int, const double*,
                      const double*, float*, float*, int32_t*, cudaStream_t);
+int run_select_lift(oryon_handle*, const int32_t*, int, int, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, const void*,
+                    const void*, int, int, int, int, int, const double*, const double*, int64_t*, float*, float*, int32_t*, cudaStream_t);
 }  // namespace lift
 namespace gemm {
 int run_gemm_f32(oryon_handle*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, float, int,
@@ -202,6 +204,14 @@ int oryon_corrs_to_pcd(oryon_handle* h, const int64_t* corrs, int n, int feat_h,
                        float* pcd_q, int32_t* n_valid, void* stream) {
   return oryon::lift::run_corrs_to_pcd(h, corrs, n, feat_h, feat_w, depth_a, depth_q, depth_dtype, Ha, Wa, Hq, Wq, cam_a, cam_q, pcd_a,
                                        pcd_q, n_valid, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_select_lift(oryon_handle* h, const int32_t* rows, int B, int n, const int32_t* roi_a, const int32_t* roi_q, const int32_t* nn_idx,
+                      int cap_a, int cap_q, int feat_h, int feat_w, const void* depth_a, const void* depth_q, int depth_dtype, int Ha, int Wa,
+                      int Hq, int Wq, const double* cams_a, const double* cams_q, int64_t* corrs, float* pcd_a, float* pcd_q,
+                      int32_t* n_valid, void* stream) {
+  return oryon::lift::run_select_lift(h, rows, B, n, roi_a, roi_q, nn_idx, cap_a, cap_q, feat_h, feat_w, depth_a, depth_q, depth_dtype, Ha,
+                                      Wa, Hq, Wq, cams_a, cams_q, corrs, pcd_a, pcd_q, n_valid, static_cast<cudaStream_t>(stream));
 }
 
 int oryon_lift_pcd(oryon_handle* h, const void* depth, int depth_dtype, int H, int W, const double* cam, const int64_t* xs,

@@ -29,7 +29,7 @@ from . import _lib
 from ._torch_glue import as_device, ptr, stream_ptr
 from .net import Oryon
 from .utils import pcd as _pcd
-from .utils.pcd import corrs_to_pcd, mask_to_roi, match_nn, nn_correspondences, torch_sample_select
+from .utils.pcd import corrs_to_pcd, mask_to_roi, match_nn, nn_correspondences, select_lift_batched, torch_sample_select
 from .utils.pointdsc.init import get_pointdsc_pose, get_pointdsc_solver, pointdsc_poses
 
 
@@ -88,6 +88,9 @@ class FPM_Pipeline:
         self.featmap_size = tuple(_get(args, "model.image_encoder.img_size", (192, 192)))
         self.pred_file = None
         self.rows: List[dict] = []
+        self.batched_tail = bool(_get(args, "test.batched_tail", True))   # False: per-pair selection / lifting (any frame sizes)
+        self._host_dist: Optional[Tensor] = None
+        self._host_rows: Optional[Tensor] = None
 
     # ---- LightningModule surface -----------------------------------------------------------------------
     def forward(self, x: dict) -> Dict[str, Tensor]:
@@ -208,6 +211,91 @@ class FPM_Pipeline:
                 out[b] = final[sel2]
         return out
 
+    # ---- batched tail: one host round trip for the draws, one launch for selection + lifting -----------------
+    def _stacked_depth(self, view: dict) -> Optional[Tensor]:
+        """``orig_depth`` as one ``[B,H,W]`` device tensor, or ``None`` when the frames of the batch differ in size
+        (then the per-pair path is used).  A stacked (ideally pinned) tensor from the collate goes up in one copy."""
+        d = view["orig_depth"]
+        if isinstance(d, Tensor):
+            d = d.reshape(d.shape[0], *d.shape[-2:]) if d.dim() == 4 else d
+            return as_device(d, self.device)
+        frames = [f.squeeze() for f in d]
+        if any(f.shape != frames[0].shape or f.dtype != frames[0].dtype for f in frames):
+            return None
+        out = torch.empty(len(frames), *frames[0].shape, dtype=frames[0].dtype, device=self.device)
+        for b, f in enumerate(frames):
+            out[b].copy_(f, non_blocking=True)
+        return out
+
+    def _uniform_sizes(self, batch: dict, key: str, depth: Optional[Tensor]) -> bool:
+        if depth is None:
+            return False
+        sz = batch[key]["sizes"]
+        sz = sz.cpu() if isinstance(sz, Tensor) else torch.as_tensor(sz)
+        return bool((sz[:, 0] == depth.shape[1]).all()) and bool((sz[:, 1] == depth.shape[2]).all())
+
+    def draw_rows(self, dist: Tensor, n_a: List[int], valid: List[bool]) -> Tensor:
+        """The two draws of ``nn_correspondences`` (utils/pcd.py:187-190, :211) for every valid pair, in the
+        reference's order, on the CPU generator, from the HOST copy of the nearest-neighbour distances.  Returns
+        ``int32 [B,n_corrs]`` positions in each pair's anchor ROI list (first entry -1: no correspondences)."""
+        B = dist.shape[0]
+        rows = torch.full((B, self.n_corrs), -1, dtype=torch.int32)
+        for b in range(B):
+            if not valid[b]:
+                continue
+            n1 = n_a[b]
+            sel = None
+            if self.src_sampling is not None and n1 > self.src_sampling:
+                sel = torch_sample_select(torch.empty(n1, 0), int(self.src_sampling))
+                db = dist[b].index_select(0, sel)
+            else:
+                db = dist[b, :n1]
+            ok = torch.nonzero(db < self.dist_th).squeeze(1)
+            if ok.shape[0] > 1:
+                r = ok[torch_sample_select(torch.empty(ok.shape[0], 0), self.n_corrs)]
+                rows[b] = (sel[r] if sel is not None else r).to(torch.int32)
+        return rows
+
+    def _batched_tail(self, batch: dict, outputs: dict, results: dict, valid: List[bool]):
+        """Matching -> draws -> selection + lifting -> registration with two host synchronisations per BATCH (the
+        distances for the draws, the per-pair point counts) instead of several per pair.  Returns ``(corrs, poses)``
+        or ``None`` when the batch does not qualify (frames of different sizes, CUDA-generator draws)."""
+        if str(self.corrs_device) != "cpu" or not any(valid):
+            return None
+        depth_a, depth_q = self._stacked_depth(batch["anchor"]), self._stacked_depth(batch["query"])
+        if not (self._uniform_sizes(batch, "anchor", depth_a) and self._uniform_sizes(batch, "query", depth_q)):
+            return None
+        ma, mq, na, nq = self._masks_and_counts(results)
+        fa, fq = outputs["featmap_a"], outputs["featmap_q"]
+        B = fa.shape[0]
+        roi_a, cnt_a = mask_to_roi(ma)
+        roi_q, cnt_q = mask_to_roi(mq)
+        n_a = [n if v else 0 for n, v in zip(cnt_a.tolist(), valid)]
+        n_q = [n if v else 0 for n, v in zip(cnt_q.tolist(), valid)]
+        idx, dist = match_nn(fa, fq, roi_a, roi_q, n_a, n_q)
+        if self._host_dist is None or self._host_dist.shape != dist.shape:
+            self._host_dist = torch.empty(dist.shape, dtype=torch.float32).pin_memory()
+            self._host_rows = torch.empty(B, self.n_corrs, dtype=torch.int32).pin_memory()
+        self._host_dist.copy_(dist, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()                  # sync 1: distances for the draws
+        self._host_rows.copy_(self.draw_rows(self._host_dist, n_a, valid))
+        corrs, pa, pq, nv = select_lift_batched(self._host_rows, roi_a, roi_q, idx, depth_a, depth_q, batch["anchor"]["camera"],
+                                                batch["query"]["camera"], self.featmap_size)
+        counts = nv.tolist()                                                    # sync 2: points that survived the bounds test
+        todo = [b for b in range(B) if counts[b] >= 0]
+        poses = {}
+        if todo:
+            if self.solver != "pointdsc":
+                raise RuntimeError(f"Solver {self.solver} not implemented")
+            if len(todo) == B:
+                src, tgt = pa, pq
+            else:
+                sel = torch.tensor(todo, device=self.device)
+                src, tgt = pa.index_select(0, sel), pq.index_select(0, sel)
+            T = pointdsc_poses(self.pointdsc_solver.to(self.device), src, tgt, counts=[counts[b] for b in todo]).cpu().to(torch.float32)
+            poses = {b: T[i] for i, b in enumerate(todo)}
+        return [corrs[b] if counts[b] >= 0 else None for b in range(B)], poses
+
     def test_step(self, batch: dict, batch_idx: int = 0) -> List[dict]:
         """The reference's hot loop (pipeline.py:306-355) for one batch; returns (and accumulates in ``self.rows``)
         one record per pair: ids, ``pred_pose_rel`` (identity on failure, :335-350), ``pred_pose`` =
@@ -217,19 +305,23 @@ class FPM_Pipeline:
         B = outputs["featmap_a"].shape[0]
         _, _, na, nq = self._masks_and_counts(results)
         valid = [(a > 0 and q > 0) for a, q in zip(na.tolist(), nq.tolist())]
-        corrs = self.select_correspondences(results, outputs, valid)
-        # lifting per pair, registration for all pairs with correspondences at once
-        todo, pa, pq = [], [], []
-        for b in range(B):
-            if corrs[b] is not None:
-                a, q = self._lift(batch, corrs[b], b)
-                todo.append(b), pa.append(a), pq.append(q)
-        poses = {}
-        if todo:
-            if self.solver != "pointdsc":
-                raise RuntimeError(f"Solver {self.solver} not implemented")
-            T = pointdsc_poses(self.pointdsc_solver.to(self.device), pa, pq).cpu().to(torch.float32)
-            poses = {b: T[i] for i, b in enumerate(todo)}
+        tail = self._batched_tail(batch, outputs, results, valid) if self.batched_tail else None
+        if tail is not None:
+            corrs, poses = tail
+        else:
+            corrs = self.select_correspondences(results, outputs, valid)
+            # lifting per pair, registration for all pairs with correspondences at once
+            todo, pa, pq = [], [], []
+            for b in range(B):
+                if corrs[b] is not None:
+                    a, q = self._lift(batch, corrs[b], b)
+                    todo.append(b), pa.append(a), pq.append(q)
+            poses = {}
+            if todo:
+                if self.solver != "pointdsc":
+                    raise RuntimeError(f"Solver {self.solver} not implemented")
+                T = pointdsc_poses(self.pointdsc_solver.to(self.device), pa, pq).cpu().to(torch.float32)
+                poses = {b: T[i] for i, b in enumerate(todo)}
         iou_a = results["iou_a"].cpu().numpy() if results["iou_a"] is not None else np.full(B, np.nan, np.float32)
         iou_q = results["iou_q"].cpu().numpy() if results["iou_q"] is not None else np.full(B, np.nan, np.float32)
         rows = []

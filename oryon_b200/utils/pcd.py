@@ -243,3 +243,35 @@ def corrs_to_pcd(corrs: Tensor, depth_a: Tensor, depth_q: Tensor, camera_a: Tens
                                       ptr(pa), ptr(pq), ptr(nv), stream_ptr(dev)))
     m = int(nv.item())
     return pa[:m], pq[:m]
+
+
+def select_lift_batched(rows: Tensor, roi_a: Tensor, roi_q: Tensor, nn_idx: Tensor, depth_a: Tensor, depth_q: Tensor,
+                        cameras_a: Tensor, cameras_q: Tensor, featmap_size: Sequence[int]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``oryon_select_lift``: for B pairs in one launch, the row selection at the end of ``nn_correspondences``
+    (reference utils/pcd.py:207-212) and the scaling / bounds test / lifting of pipeline.py:447-460.
+
+    ``rows int32 [B,n]``: positions in each pair's anchor ROI list chosen by the caller's draws (``rows[b,0] < 0`` for a
+    pair without correspondences); ``roi_a/roi_q/nn_idx``: what went into / came out of ``match_nn``; ``depth_x
+    [B,H,W]`` raw frames (mm); ``cameras_x [B,3,3]``.  Returns ``(corrs int64 [B,n,4], pcd_a [B,n,3], pcd_q [B,n,3],
+    n_valid int32 [B])`` on the GPU; rows ``>= n_valid[b]`` of the clouds are undefined."""
+    dev = device_of(roi_a, nn_idx)
+    rows = as_device(rows, dev, torch.int32)
+    B, n = rows.shape
+    if depth_a.dtype != depth_q.dtype or depth_a.dtype not in _DEPTH_DTYPES:
+        depth_a, depth_q = depth_a.to(torch.float32), depth_q.to(torch.float32)
+    da, dq = as_device(depth_a, dev), as_device(depth_q, dev)
+    if da.dim() != 3 or dq.dim() != 3 or da.shape[0] != B or dq.shape[0] != B:
+        raise ValueError("select_lift_batched: depth frames must be [B,H,W]")
+    ka = cameras_a.detach().to("cpu", torch.float64).reshape(B, 9).contiguous()
+    kq = cameras_q.detach().to("cpu", torch.float64).reshape(B, 9).contiguous()
+    corrs = torch.empty(B, n, 4, dtype=torch.int64, device=dev)
+    pa = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+    pq = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+    nv = torch.empty(B, dtype=torch.int32, device=dev)
+    c_dbl = ctypes.POINTER(ctypes.c_double)
+    _lib.check(_lib.load().oryon_select_lift(
+        _lib.handle(dev.index), ptr(rows), B, n, ptr(roi_a), ptr(roi_q), ptr(nn_idx), roi_a.shape[1], roi_q.shape[1],
+        int(featmap_size[0]), int(featmap_size[1]), ptr(da), ptr(dq), _DEPTH_DTYPES[da.dtype], da.shape[1], da.shape[2], dq.shape[1],
+        dq.shape[2], ctypes.cast(ka.data_ptr(), c_dbl), ctypes.cast(kq.data_ptr(), c_dbl), ptr(corrs), ptr(pa), ptr(pq), ptr(nv),
+        stream_ptr(dev)))
+    return corrs, pa, pq, nv

@@ -90,22 +90,32 @@ def get_pointdsc_solver(ckpt_path: str, device) -> PointDSCSolver:
                           k=config["k"], nms_radius=config["inlier_threshold"], device=device)
 
 
-def pointdsc_poses(model: PointDSCSolver, pcd1: Sequence[Tensor], pcd2: Sequence[Tensor], *, return_debug: bool = False):
-    """Batched form: ``P`` correspondence sets ``[n_p,3]`` -> ``[P,4,4]`` float32 on the GPU (one library call)."""
+def pointdsc_poses(model: PointDSCSolver, pcd1, pcd2, *, counts: Optional[Sequence[int]] = None, return_debug: bool = False):
+    """Batched form: ``P`` correspondence sets ``[n_p,3]`` -> ``[P,4,4]`` float32 on the GPU (one library call).
+    ``pcd1/pcd2``: sequences of ``[n_p,3]`` tensors, or padded device tensors ``[P,cap,3]`` with ``counts[p]`` valid rows."""
     dev = model.device if (model.device is not None and model.device.type == "cuda") else require_cuda()
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
     model.ensure_loaded(dev)
     P = len(pcd1)
-    ns = [int(a.shape[0]) for a in pcd1]
-    if P == 0 or any(a.shape != b.shape or a.dim() != 2 or a.shape[1] != 3 for a, b in zip(pcd1, pcd2)):
-        raise ValueError("pointdsc_poses: pcd1[p] and pcd2[p] must both be [n_p,3]")
-    cap = max(ns)
-    src = torch.zeros(P, cap, 3, dtype=torch.float32, device=dev)
-    tgt = torch.zeros(P, cap, 3, dtype=torch.float32, device=dev)
-    for p in range(P):
-        src[p, :ns[p]] = as_device(pcd1[p], dev, torch.float32)
-        tgt[p, :ns[p]] = as_device(pcd2[p], dev, torch.float32)
+    if counts is not None:
+        if not (isinstance(pcd1, Tensor) and isinstance(pcd2, Tensor)) or pcd1.shape != pcd2.shape or pcd1.dim() != 3 or pcd1.shape[2] != 3:
+            raise ValueError("pointdsc_poses: with `counts`, pcd1 and pcd2 must be padded [P,cap,3] tensors")
+        ns = [int(v) for v in counts]
+        cap = pcd1.shape[1]
+        if len(ns) != P or max(ns) > cap:
+            raise ValueError("pointdsc_poses: `counts` does not fit the padded clouds")
+        src, tgt = as_device(pcd1, dev, torch.float32), as_device(pcd2, dev, torch.float32)
+    else:
+        ns = [int(a.shape[0]) for a in pcd1]
+        if P == 0 or any(a.shape != b.shape or a.dim() != 2 or a.shape[1] != 3 for a, b in zip(pcd1, pcd2)):
+            raise ValueError("pointdsc_poses: pcd1[p] and pcd2[p] must both be [n_p,3]")
+        cap = max(ns)
+        src = torch.zeros(P, cap, 3, dtype=torch.float32, device=dev)
+        tgt = torch.zeros(P, cap, 3, dtype=torch.float32, device=dev)
+        for p in range(P):
+            src[p, :ns[p]] = as_device(pcd1[p], dev, torch.float32)
+            tgt[p, :ns[p]] = as_device(pcd2[p], dev, torch.float32)
     out = torch.empty(P, 4, 4, dtype=torch.float32, device=dev)
     n_arr = (c_int32 * P)(*ns)
     dbg_struct, dbg = None, None

@@ -54,3 +54,39 @@ def test_no_valid_rows():
     K = torch.tensor(synth.NOCS_INTRINSICS, dtype=torch.float64)
     pa, pq = pcd.corrs_to_pcd(corrs.cuda(), depth.cuda(), depth.cuda(), K, K, (192, 192), (48, 64), (48, 64))
     assert pa.shape == (0, 3) and pq.shape == (0, 3)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int16, torch.float32])
+def test_select_lift_batched_bit_exact_vs_oracle(dtype):
+    """oryon_select_lift (B pairs, one launch) == per-pair row selection (utils/pcd.py:207-212) followed by the
+    oracle's corrs_to_pcds (pipeline.py:447-460), including a pair without correspondences and out-of-bounds rows."""
+    need_gpu()
+    B, n, W, cap_a, cap_q = 5, 500, 192, 3000, 4000
+    raw = (120, 200)                                # smaller than the feature map in y: rows fall out of bounds
+    gen = torch.Generator().manual_seed(3)
+    roi_a = torch.stack([torch.randperm(192 * W, generator=gen)[:cap_a].sort().values for _ in range(B)]).int()
+    roi_q = torch.stack([torch.randperm(192 * W, generator=gen)[:cap_q].sort().values for _ in range(B)]).int()
+    nn_idx = torch.randint(0, cap_q, (B, cap_a), generator=gen).int()
+    rows = torch.randint(0, cap_a, (B, n), generator=gen).int()
+    rows[2] = -1
+    depth_a = torch.randint(400, 1600, (B, *raw), generator=gen).to(dtype)
+    depth_q = torch.randint(400, 1600, (B, *raw), generator=gen).to(dtype)
+    K = torch.tensor(synth.NOCS_INTRINSICS, dtype=torch.float64).reshape(1, 3, 3).repeat(B, 1, 1)
+    K[:, 0, 0] += torch.arange(B, dtype=torch.float64) * 3.25          # per-pair intrinsics
+    Kq = K.clone()
+    Kq[:, 1, 2] -= 7.5
+    corrs, pa, pq, nv = pcd.select_lift_batched(rows.cuda(), roi_a.cuda(), roi_q.cuda(), nn_idx.cuda(), depth_a.cuda(), depth_q.cuda(),
+                                                K, Kq, (192, W))
+    nv = nv.cpu().tolist()
+    assert nv[2] == -1
+    for b in range(B):
+        if b == 2:
+            continue
+        r = rows[b].long()
+        p1, p2 = roi_a[b, r].long(), roi_q[b, nn_idx[b, r].long()].long()
+        ref_c = torch.stack((p1 // W, p1 % W, p2 // W, p2 % W), dim=1)
+        assert torch.equal(corrs[b].cpu(), ref_c)
+        ra, rq = oracle.corrs_to_pcds(ref_c, depth_a[b], depth_q[b], K[b], Kq[b], (192, W), raw, raw)
+        assert 0 < ra.shape[0] < n and nv[b] == ra.shape[0]
+        assert np.array_equal(pa[b, :nv[b]].cpu().numpy(), ra.float().numpy())
+        assert np.array_equal(pq[b, :nv[b]].cpu().numpy(), rq.float().numpy())

@@ -55,10 +55,21 @@ def _cuda_batch(batch):
     return out
 
 
+def _stacked_batch(batch):
+    """The batch as the B200 collate hands it over: depth frames stacked in one pinned host tensor per view."""
+    out = dict(batch)
+    for key in ("anchor", "query"):
+        v = dict(batch[key])
+        v["orig_depth"] = torch.stack(v["orig_depth"]).pin_memory()
+        out[key] = v
+    return out
+
+
+@pytest.mark.parametrize("batched_tail", [True, False])
 @pytest.mark.parametrize("mask_mode", ["predicted", "oracle"])
-def test_test_step_equals_reference_loop(system, mask_mode, tmp_path):
+def test_test_step_equals_reference_loop(system, mask_mode, batched_tail, tmp_path):
     model, solver, psd = system
-    args = dict(ARGS, test=dict(ARGS["test"], mask=mask_mode))
+    args = dict(ARGS, test=dict(ARGS["test"], mask=mask_mode, batched_tail=batched_tail))
     pipe = FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver)
     batch = synth.synthetic_batch(7, 3, empty_mask_pairs=(1,) if mask_mode == "oracle" else ())
     gb = _cuda_batch(batch)
@@ -101,11 +112,13 @@ class _PlantedModel:
         return self.outputs
 
 
-def test_post_network_path_recovers_and_matches_planted_pose(system):
+@pytest.mark.parametrize("tail", ["batched_cuda_list", "batched_pinned_stack", "per_pair"])
+def test_post_network_path_recovers_and_matches_planted_pose(system, tail):
     _, solver, psd = system
     outputs, batch = synth.planted_network_outputs(21, 4)
-    pipe = FPM_Pipeline(ARGS, test_model=True, model=_PlantedModel({k: v.cuda() for k, v in outputs.items()}), pointdsc_solver=solver)
-    gb = _cuda_batch(batch)
+    args = dict(ARGS, test=dict(ARGS["test"], batched_tail=tail != "per_pair"))
+    pipe = FPM_Pipeline(args, test_model=True, model=_PlantedModel({k: v.cuda() for k, v in outputs.items()}), pointdsc_solver=solver)
+    gb = _stacked_batch(batch) if tail == "batched_pinned_stack" else _cuda_batch(batch)
     pipe.on_test_start()
     rows = pipe.test_step(gb, 0)
     torch.manual_seed(1)
