@@ -275,6 +275,24 @@ int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops);
 int oryon_mask_postproc(oryon_handle* h, const float* logits, int B, int H, int W, float mask_th, const uint8_t* gt, int Hg, int Wg,
                         int32_t* pred_mask, int32_t* gt_resized, int32_t* n_pred, int32_t* n_gt, float* iou, void* stream);
 
+/* ---- N2: pose-error metrics of the evaluator ---------------------------------------------------------
+ * Replaces the arithmetic of Evaluator.register_eval (utils/evaluator.py:206-288) for P pose pairs per call:
+ * compute_RT_distances (utils/metrics.py:236-259), compute_add / compute_adds (:205-234, float16 model transform of
+ * utils/pcd.py:127-133), my_mssd / my_mspd (bop_toolkit_lib/pose_error.py:370-426, float16-rounded poses, first three
+ * model points -- see csrc/eval.cu for the restated quirks).  Thresholding and bookkeeping stay with the caller
+ * (oryon_b200/utils/evaluator.py).
+ *
+ * oryon_eval_set_object registers (or replaces) one object model on the handle's device (synchronous copies):
+ *   pts   HOST float64 [n][3] model points in mm        syms  HOST float64 [n_sym][3][4] symmetry transforms [R | t]
+ * oryon_eval_pose_errors:
+ *   obj_ids HOST int32 [P]; pred, gt DEVICE float64 [P][16] row-major 4x4 (metres; `pred` after the zero-pose
+ *   substitution of evaluator.py:222-223); cams DEVICE float64 [P][9]
+ *   out DEVICE float64 [P][6]: R error (deg), T error (cm), ADD or ADD-S (m), 1.0 if ADD-S was used (n_sym > 1),
+ *   MSSD (mm), MSPD (px) */
+int oryon_eval_set_object(oryon_handle* h, int obj_id, const double* pts, int n, const double* syms, int n_sym);
+int oryon_eval_pose_errors(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams,
+                           double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,11 @@ int run_match(oryon_handle*, const float*, const float*, int, int, int, int, con
 int run_mask_to_roi(oryon_handle*, const int32_t*, int, int, int, int32_t*, int32_t*, cudaStream_t);
 int read_stats(oryon_handle*, int64_t*, cudaStream_t);
 }  // namespace match
+namespace eval {
+void destroy_state(oryon_handle*);
+int set_object(oryon_handle*, int, const double*, int, const double*, int);
+int pose_errors(oryon_handle*, int, const int32_t*, const double*, const double*, const double*, double*, cudaStream_t);
+}  // namespace eval
 namespace lift {
 int run_lift(oryon_handle*, const void*, int, int, int, const double*, const int64_t*, const int64_t*, int, float*, cudaStream_t);
 int run_corrs_to_pcd(oryon_handle*, const int64_t*, int, int, int, const void*, const void*, int, int, int, int, int, const double*,
@@ -156,6 +161,7 @@ int oryon_destroy(oryon_handle* h) {
   h->cand.release(), h->counters.release(), h->overflow_rows.release(), h->pair_meta.release(), h->lift_scratch.release();
   oryon::pdsc::destroy_model(h);
   oryon::net::destroy_backbone(h);
+  oryon::eval::destroy_state(h);
   h->pdsc_ws.release();
   h->gemm_scratch.release();
   delete h;
@@ -252,6 +258,14 @@ int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops) {
   *launches = h->gemm_launches, *flops = h->gemm_flops;
   h->gemm_launches = 0, h->gemm_flops = 0.0;
   return ORYON_OK;
+}
+
+int oryon_eval_set_object(oryon_handle* h, int obj_id, const double* pts, int n, const double* syms, int n_sym) {
+  return oryon::eval::set_object(h, obj_id, pts, n, syms, n_sym);
+}
+int oryon_eval_pose_errors(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams,
+                           double* out, void* stream) {
+  return oryon::eval::pose_errors(h, P, obj_ids, pred, gt, cams, out, static_cast<cudaStream_t>(stream));
 }
 
 int oryon_mask_postproc(oryon_handle* h, const float* logits, int B, int H, int W, float mask_th, const uint8_t* gt, int Hg, int Wg,

@@ -64,13 +64,15 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
-template <int NPASS>
+// VMN = true: V tiles are fetched straight from the QKV buffer ([128 keys][64 d], the same box as a K tile) and fed to the
+// P V MMA as an MN-major B operand; VMN = false: from a pre-transposed V^T buffer as a K-major operand (transpose_v_kernel).
+template <int NPASS, bool VMN>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_constant__ CUtensorMap tm_qkv_lo,
                const __grid_constant__ CUtensorMap tm_vt_hi, const __grid_constant__ CUtensorMap tm_vt_lo, Args a, int width) {
   using L = Cfg<NPASS>;
   constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0);
-  constexpr uint32_t kIdescO = ptx::make_idesc_f16(128, 64, 0);
+  constexpr uint32_t kIdescO = ptx::make_idesc_f16(128, 64, 0, VMN ? 1 : 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -99,7 +101,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_qkv_hi);
-    ptx::prefetch_tensormap(&tm_vt_hi);
+    if (!VMN) ptx::prefetch_tensormap(&tm_vt_hi);
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], 8);
@@ -134,12 +136,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
           const int j = i - T, vs = j & 1;
           ptx::mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(&v_full[vs], L::kVBytes);
-          const int vrow = (seq * a.heads + head) * kD;
           uint8_t* dst = sV + vs * L::kVBytes;
+          if (VMN) {   // rows past S belong to the next sequence (or are zero-filled past the end): their probabilities are exactly 0
+            tma_load_2d_(dst, &tm_qkv_hi, &v_full[vs], 2 * width + head * kD, row0 + j * kKT);
+            if (NPASS == 3) tma_load_2d_(dst + kTileBytes, &tm_qkv_lo, &v_full[vs], 2 * width + head * kD, row0 + j * kKT);
+          } else {
+            const int vrow = (seq * a.heads + head) * kD;
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            tma_load_2d_(dst + sub * (kTileBytes / 2), &tm_vt_hi, &v_full[vs], j * kKT + sub * 64, vrow);
-            if (NPASS == 3) tma_load_2d_(dst + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, &v_full[vs], j * kKT + sub * 64, vrow);
+            for (int sub = 0; sub < 2; ++sub) {
+              tma_load_2d_(dst + sub * (kTileBytes / 2), &tm_vt_hi, &v_full[vs], j * kKT + sub * 64, vrow);
+              if (NPASS == 3) tma_load_2d_(dst + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, &v_full[vs], j * kKT + sub * 64, vrow);
+            }
           }
         }
       }
@@ -163,7 +170,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t dp = ptx::make_smem_desc_kmajor(pa + sub * kTileBytes + k * 32, 128);
-              const uint64_t dv = ptx::make_smem_desc_kmajor(va + sub * (kTileBytes / 2) + k * 32, 128);
+              // 16 keys per MMA: K-major V^T advances 32 bytes inside the swizzled row; MN-major V advances two 8-key groups
+              const uint64_t dv = VMN ? ptx::make_smem_desc_mnmajor_sw128(va + (sub * 4 + k) * 2048, 0, 1024)
+                                      : ptx::make_smem_desc_kmajor(va + sub * (kTileBytes / 2) + k * 32, 128);
               ptx::umma_f16(tmem_o, dp, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
             }
         }
@@ -347,22 +356,31 @@ static int make_map_2d(oryon_handle* h, CUtensorMap* tm, const __half* base, int
   return ORYON_OK;
 }
 
-// qkv split pair [n_seq*S][3*width] (q | k | v column blocks, heads of 64), vt split pair [n_seq*heads*64][ld_vt] (V^T, zero padded
-// for keys >= S up to a multiple of 128) -> out split pair [n_seq*S][ldh] (heads concatenated).
+bool v_from_qkv() {
+  static const bool vt = getenv("ORYON_ATTN_VT") != nullptr;   // A/B switch: pre-transposed V^T operand
+  return !vt;
+}
+
+// qkv split pair [n_seq*S][3*width] (q | k | v column blocks, heads of 64) -> out split pair [n_seq*S][ldh] (heads concatenated).
+// vt split pair [n_seq*heads*64][ld_vt] (V^T, zero padded for keys >= S up to a multiple of 128) is only read when
+// v_from_qkv() is false.
 int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
            int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st) {
   ORYON_REQUIRE(width == heads * kD, "attn_tc: head dim must be 64");
   const int T = (S + kKT - 1) / kKT;
-  ORYON_REQUIRE(ld_vt >= T * kKT, "attn_tc: V^T rows must be padded to %d keys", T * kKT);
+  const bool vmn = v_from_qkv();
+  ORYON_REQUIRE(vmn || ld_vt >= T * kKT, "attn_tc: V^T rows must be padded to %d keys", T * kKT);
   CUtensorMap tq_hi, tq_lo, tv_hi, tv_lo;
   int rc;
   const int64_t rows = (int64_t)n_seq * S;
   if ((rc = make_map_2d(h, &tq_hi, qkv_hi, 3 * width, rows, 3 * width, 64, 128))) return rc;
-  if ((rc = make_map_2d(h, &tv_hi, vt_hi, ld_vt, (int64_t)n_seq * heads * kD, ld_vt, 64, 64))) return rc;
+  tv_hi = tq_hi;
+  if (!vmn && (rc = make_map_2d(h, &tv_hi, vt_hi, ld_vt, (int64_t)n_seq * heads * kD, ld_vt, 64, 64))) return rc;
   tq_lo = tq_hi, tv_lo = tv_hi;
   if (precision == 3) {
     if ((rc = make_map_2d(h, &tq_lo, qkv_lo, 3 * width, rows, 3 * width, 64, 128))) return rc;
-    if ((rc = make_map_2d(h, &tv_lo, vt_lo, ld_vt, (int64_t)n_seq * heads * kD, ld_vt, 64, 64))) return rc;
+    tv_lo = tq_lo;
+    if (!vmn && (rc = make_map_2d(h, &tv_lo, vt_lo, ld_vt, (int64_t)n_seq * heads * kD, ld_vt, 64, 64))) return rc;
   }
   Args a;
   a.S = S, a.heads = heads, a.T = T;
@@ -379,14 +397,15 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
   }
   const dim3 grid((S + kQ - 1) / kQ, heads, n_seq);
   h->span_begin(KID_ATTN_TC, st);
-  if (precision == 3) {
-    ORYON_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::kTotal));
-    attn_tc_kernel<3><<<grid, kThreads, Cfg<3>::kTotal, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
-  } else {
-    ORYON_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kTotal));
-    attn_tc_kernel<1><<<grid, kThreads, Cfg<1>::kTotal, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
-  }
+  auto run = [&](auto kernel, int smem) -> int {
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kernel<<<grid, kThreads, smem, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
+    return ORYON_OK;
+  };
+  if (precision == 3) rc = vmn ? run(attn_tc_kernel<3, true>, Cfg<3>::kTotal) : run(attn_tc_kernel<3, false>, Cfg<3>::kTotal);
+  else rc = vmn ? run(attn_tc_kernel<1, true>, Cfg<1>::kTotal) : run(attn_tc_kernel<1, false>, Cfg<1>::kTotal);
   h->span_end(st);
+  if (rc) return rc;
   ORYON_CUDA_CHECK(cudaGetLastError());
   if (want_dbg && ++dbg_calls == 30) {
     long long t[128];

@@ -22,6 +22,7 @@ namespace oryon {
 namespace attn {
 int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
            int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st);
+bool v_from_qkv();
 }
 namespace net {
 
@@ -495,13 +496,14 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
   float* scores = nullptr;
   static const bool materialized = getenv("ORYON_ATTN_MATERIALIZED") != nullptr;   // A/B switch: scores through HBM (two batched GEMMs)
   const int ldS = round_up(S, 4), ldP = round_up(S, 128);
+  const bool need_vt = materialized || !attn::v_from_qkv();   // the fused kernel reads V in place (MN-major operand)
   if (tc_attn) {
     qkvh = c.split(M, 3 * width);
     if (materialized) {
       scores = c.ar.take<float>((size_t)n_seq * heads * S * ldS);
       P = c.split((size_t)n_seq * heads * S, ldP);
     }
-    vt = c.split((size_t)n_seq * heads * d, ldP);
+    if (need_vt) vt = c.split((size_t)n_seq * heads * d, ldP);
   } else {
     qkv = c.ar.take<float>((size_t)M * 3 * width);
   }
@@ -512,7 +514,7 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
     c.ln(l);
     if (tc_attn) {
       c.gemm(hsp, M, b.qkv, ep_split(qkvh, b.qkv_b, gemm::ACT_NONE));
-      if (!c.dry && !c.rc) c.rc = transpose_v(c.h, qkvh.hi, qkvh.lo, 3 * width, 2 * width, n_seq, S, heads, d, vt.hi, vt.lo, ldP, c.st);
+      if (need_vt && !c.dry && !c.rc) c.rc = transpose_v(c.h, qkvh.hi, qkvh.lo, 3 * width, 2 * width, n_seq, S, heads, d, vt.hi, vt.lo, ldP, c.st);
       if (!materialized) {
         if (!c.dry && !c.rc)
           c.rc = attn::launch(c.h, qkvh.hi, qkvh.lo, vt.hi, vt.lo, ldP, n_seq, S, heads, width, c.prec, att.hi, att.lo, width, c.st);

@@ -99,5 +99,8 @@ struct oryon_handle {
   double gemm_flops = 0.0;
   void* backbone = nullptr;                 // oryon::net::Backbone
 
+  // ---- evaluator (see eval.cu) ----
+  void* eval_state = nullptr;               // oryon::eval::State
+
   int64_t workspace_bytes() const;
 };

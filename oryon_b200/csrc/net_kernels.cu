@@ -169,11 +169,90 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
   }
 }
 
+// Vectorised form (C % 128 == 0, 16-byte aligned rows): lane holds columns 128*i + 4*lane .. +3, float4 loads / 8-byte split
+// stores -- a quarter of the memory instructions of the scalar kernel for the 768 / 1024-wide rows of the towers.
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nq = a.C >> 7;   // float4 per lane, <= 8
+  for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < a.rows; r += gridDim.x * 8) {
+    const int src = a.row_map ? a.row_map[r] : r;
+    float4 v[8];
+    if (src >= 0) {
+      const float4* xr = reinterpret_cast<const float4*>(a.x + (int64_t)src * a.ldx) + lane;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nq) v[i] = xr[32 * i];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nq) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float mean = warp_sum(s) / (float)a.C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nq) {
+          const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+          q = fmaf(d0, d0, q), q = fmaf(d1, d1, q), q = fmaf(d2, d2, q), q = fmaf(d3, d3, q);
+        }
+      const float rstd = rsqrtf(warp_sum(q) / (float)a.C + a.eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nq) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + 32 * i + lane);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta) + 32 * i + lane);
+          v[i].x = (v[i].x - mean) * rstd * g.x + b.x, v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
+          v[i].z = (v[i].z - mean) * rstd * g.z + b.z, v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (a.out32) {
+      float4* o = reinterpret_cast<float4*>(a.out32 + (int64_t)r * a.ld32) + lane;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nq) o[32 * i] = v[i];
+    }
+    if (a.out_hi) {
+      const int64_t o = (int64_t)r * a.ldh;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nq) {
+          __half h0, h1, h2, h3, l0, l1, l2, l3;
+          split_half(v[i].x, h0, l0), split_half(v[i].y, h1, l1), split_half(v[i].z, h2, l2), split_half(v[i].w, h3, l3);
+          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned*>(&ha), pk.y = *reinterpret_cast<const unsigned*>(&hb);
+          *reinterpret_cast<uint2*>(a.out_hi + o + 128 * i + 4 * lane) = pk;
+          if (a.out_lo) {
+            const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+            pk.x = *reinterpret_cast<const unsigned*>(&la), pk.y = *reinterpret_cast<const unsigned*>(&lb);
+            *reinterpret_cast<uint2*>(a.out_lo + o + 128 * i + 4 * lane) = pk;
+          }
+        }
+      for (int c = a.C + lane; c < a.ldh; c += 32) {
+        float x = 0.f;
+        if (c < a.C + a.cat_C && src >= 0) x = a.cat[(int64_t)src * a.cat_C + (c - a.C)];
+        __half hh, ll;
+        split_half(x, hh, ll);
+        a.out_hi[o + c] = hh;
+        if (a.out_lo) a.out_lo[o + c] = ll;
+      }
+    }
+  }
+}
+
 int layernorm(oryon_handle* h, const LnArgs& a, cudaStream_t st) {
   ORYON_REQUIRE(a.C > 0 && a.C % 32 == 0 && a.C <= 1024, "layernorm: C=%d unsupported", a.C);
   if (a.rows <= 0) return ORYON_OK;
   h->span_begin(KID_NORM, st);
-  layernorm_kernel<<<std::min((a.rows + 7) / 8, h->sm_count * 16), 256, 0, st>>>(a);
+  auto al = [](const void* p, size_t n) { return (reinterpret_cast<uintptr_t>(p) % n) == 0; };
+  const bool vec = a.C % 128 == 0 && a.gamma && a.beta && al(a.x, 16) && a.ldx % 4 == 0 && al(a.gamma, 16) && al(a.beta, 16) &&
+                   (!a.out32 || (al(a.out32, 16) && a.ld32 % 4 == 0)) &&
+                   (!a.out_hi || (al(a.out_hi, 8) && a.ldh % 4 == 0 && (!a.out_lo || al(a.out_lo, 8))));
+  const int grid = std::min((a.rows + 7) / 8, h->sm_count * 16);
+  if (vec) layernorm_vec_kernel<<<grid, 256, 0, st>>>(a);
+  else layernorm_kernel<<<grid, 256, 0, st>>>(a);
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
   return ORYON_OK;

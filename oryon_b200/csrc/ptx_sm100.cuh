@@ -151,13 +151,26 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, ui
   return d;
 }
 
+// MN-major operand (the M / N index is the contiguous one), 128-byte swizzle: rows of 64 fp16 along M/N (one swizzle atom wide),
+// one row per K index; 8 consecutive K rows form a 1024-byte atom, `sbo_bytes` is the distance between such 8-row groups,
+// `lbo_bytes` the distance between 64-element atoms along M/N (0 when the tile is one atom wide).
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: fp32 accumulator, fp16 (fmt 0) or bf16 (fmt 1) operands,
 // both K-major, dense, M x N tile.
 //   [4,6) c_format=1 (f32)  [7,10) a_format  [10,13) b_format  [15] a_major=0  [16] b_major=0
 //   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int ab_format) {
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int ab_format, int b_mn_major = 0) {
   return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace ptx

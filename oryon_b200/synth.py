@@ -8,6 +8,8 @@ golden fixtures additionally store a checksum of the generated inputs).
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from typing import Dict, Tuple
 
 import torch
@@ -270,3 +272,64 @@ def planted_network_outputs(seed: int, B: int, shift=(2, 3), noise: float = 0.02
     outputs = dict(featmap_a=torch.stack(feats_a), featmap_q=torch.stack(feats_q),
                    mask_a=torch.stack(logit_a).unsqueeze(1), mask_q=torch.stack(logit_q).unsqueeze(1))
     return outputs, batch
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluator inputs: synthetic object models / symmetry sets / pose pairs
+# ------------------------------------------------------------------------------------------------
+def _axis_rotation(axis, angle: float) -> np.ndarray:
+    a = np.asarray(axis, dtype=np.float64)
+    a = a / np.linalg.norm(a)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + math.sin(angle) * K + (1 - math.cos(angle)) * (K @ K)
+
+
+def eval_objects(seed: int = 0) -> Dict:
+    """Three synthetic objects in the format of the reference datasets' ``get_object_info()`` (datasets.py:509-513):
+    ``models[id]['pts'] [n,3] float64`` (mm), ``diams[id]`` (mm), ``syms[id]`` = list of ``{'R': [3,3], 't': [3,1]}``.
+    1: asymmetric, 2: continuous symmetry about z discretised in 36 steps, 3: one discrete 180-degree symmetry
+    with an offset."""
+    rng = np.random.RandomState(seed)
+    models, diams, syms = {}, {}, {}
+    pts = (rng.rand(700, 3) - 0.5) * np.array([60.0, 90.0, 120.0])
+    models[1], syms[1] = dict(pts=pts), [dict(R=np.eye(3), t=np.zeros((3, 1)))]
+    ang, h = rng.rand(1500) * 2 * np.pi, (rng.rand(1500) - 0.5) * 150.0
+    models[2] = dict(pts=np.stack([40.0 * np.cos(ang), 40.0 * np.sin(ang), h], axis=1))
+    syms[2] = [dict(R=_axis_rotation([0, 0, 1], 2 * np.pi * i / 36), t=np.zeros((3, 1))) for i in range(36)]
+    pts = (rng.rand(300, 3) - 0.5) * np.array([200.0, 50.0, 80.0]) + np.array([5.0, 0.0, 0.0])
+    R180 = _axis_rotation([0, 1, 0], np.pi)
+    off = np.array([[5.0], [0.0], [0.0]])
+    models[3] = dict(pts=pts)
+    syms[3] = [dict(R=np.eye(3), t=np.zeros((3, 1))), dict(R=R180, t=-R180 @ off + off)]
+    for k, m in models.items():
+        p = m["pts"]
+        diams[k] = float(np.sqrt(((p[:, None, :] - p[None, ::7, :]) ** 2).sum(-1)).max())
+    return dict(models=models, diams=diams, syms=syms)
+
+
+def eval_cases(seed: int = 0, n: int = 18) -> Dict:
+    """``n`` (prediction, ground truth) pose pairs in the shapes ``test_step`` hands to ``Evaluator.register_test``
+    (pipeline.py:321-331): ``pred_pose`` / ``pred_pose_rel`` float32 ``[n,4,4]``, ``gt_pose`` float64, metres; errors
+    from a fraction of a degree / millimetre up to gross failures; entry 4 is an identity ``pred_pose_rel`` (failed
+    registration), entry 5 an all-zero one."""
+    g = _gen(7000 + seed)
+    pose_a, gt, pred, rel, cls = [], [], [], [], []
+    for i in range(n):
+        Ta, Tq = torch.eye(4, dtype=torch.float64), torch.eye(4, dtype=torch.float64)
+        Ta[:3, :3], Tq[:3, :3] = random_rotation(g, 180.0), random_rotation(g, 180.0)
+        Ta[:3, 3] = torch.tensor([0.0, 0.0, 0.9], dtype=torch.float64) + 0.15 * torch.randn(3, generator=g, dtype=torch.float64)
+        Tq[:3, 3] = torch.tensor([0.0, 0.0, 0.8], dtype=torch.float64) + 0.15 * torch.randn(3, generator=g, dtype=torch.float64)
+        scale = [0.2, 1.0, 3.0, 8.0, 20.0, 60.0][i % 6]
+        E = torch.eye(4, dtype=torch.float64)
+        E[:3, :3] = random_rotation(g, scale)
+        E[:3, 3] = 0.002 * scale * torch.randn(3, generator=g, dtype=torch.float64)
+        Trel = (E @ Tq @ torch.linalg.inv(Ta)).to(torch.float32)
+        if i == 4:
+            Trel = torch.eye(4)
+        if i == 5:
+            Trel = torch.zeros(4, 4)
+        pose_a.append(Ta), gt.append(Tq), rel.append(Trel), pred.append(Trel @ Ta.to(torch.float32)), cls.append(1 + i % 3)
+    K = torch.tensor(NOCS_INTRINSICS, dtype=torch.float64).reshape(3, 3)
+    return dict(pose_a=torch.stack(pose_a), gt_pose=torch.stack(gt), pred_pose=torch.stack(pred), pred_pose_rel=torch.stack(rel),
+                cls_id=cls, camera=K, iou_a=torch.rand(n, generator=g), iou_q=torch.rand(n, generator=g),
+                instance_id=[f"scene_{i}" for i in range(n)])

@@ -62,7 +62,8 @@ def test_select_lift_batched_bit_exact_vs_oracle(dtype):
     oracle's corrs_to_pcds (pipeline.py:447-460), including a pair without correspondences and out-of-bounds rows."""
     need_gpu()
     B, n, W, cap_a, cap_q = 5, 500, 192, 3000, 4000
-    raw = (120, 200)                                # smaller than the feature map in y: rows fall out of bounds
+    raw = (120, 200)
+    FM = (150, W)                                   # nominal map height < 192: rows with y >= 150 scale out of bounds
     gen = torch.Generator().manual_seed(3)
     roi_a = torch.stack([torch.randperm(192 * W, generator=gen)[:cap_a].sort().values for _ in range(B)]).int()
     roi_q = torch.stack([torch.randperm(192 * W, generator=gen)[:cap_q].sort().values for _ in range(B)]).int()
@@ -76,7 +77,7 @@ def test_select_lift_batched_bit_exact_vs_oracle(dtype):
     Kq = K.clone()
     Kq[:, 1, 2] -= 7.5
     corrs, pa, pq, nv = pcd.select_lift_batched(rows.cuda(), roi_a.cuda(), roi_q.cuda(), nn_idx.cuda(), depth_a.cuda(), depth_q.cuda(),
-                                                K, Kq, (192, W))
+                                                K, Kq, FM)
     nv = nv.cpu().tolist()
     assert nv[2] == -1
     for b in range(B):
@@ -86,7 +87,7 @@ def test_select_lift_batched_bit_exact_vs_oracle(dtype):
         p1, p2 = roi_a[b, r].long(), roi_q[b, nn_idx[b, r].long()].long()
         ref_c = torch.stack((p1 // W, p1 % W, p2 // W, p2 % W), dim=1)
         assert torch.equal(corrs[b].cpu(), ref_c)
-        ra, rq = oracle.corrs_to_pcds(ref_c, depth_a[b], depth_q[b], K[b], Kq[b], (192, W), raw, raw)
+        ra, rq = oracle.corrs_to_pcds(ref_c, depth_a[b], depth_q[b], K[b], Kq[b], FM, raw, raw)
         assert 0 < ra.shape[0] < n and nv[b] == ra.shape[0]
         assert np.array_equal(pa[b, :nv[b]].cpu().numpy(), ra.float().numpy())
         assert np.array_equal(pq[b, :nv[b]].cpu().numpy(), rq.float().numpy())
