@@ -129,9 +129,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       for (int i = 0; i < 2 * T; ++i) {
         const int st = i & 1, kt = i % T;
         ptx::mbar_wait(&k_empty[st], ((i >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&k_full[st], L::kKStage);
+        const bool need_lo = NPASS == 3 && i >= T;   // pass 1 (row maximum) multiplies the hi halves only
+        ptx::mbar_arrive_expect_tx(&k_full[st], need_lo ? L::kKStage : kTileBytes);
         tma_load_2d_(sK + st * L::kKStage, &tm_qkv_hi, &k_full[st], width + head * kD, row0 + kt * kKT);
-        if (NPASS == 3) tma_load_2d_(sK + st * L::kKStage + kTileBytes, &tm_qkv_lo, &k_full[st], width + head * kD, row0 + kt * kKT);
+        if (need_lo) tma_load_2d_(sK + st * L::kKStage + kTileBytes, &tm_qkv_lo, &k_full[st], width + head * kD, row0 + kt * kKT);
         if (i >= T) {
           const int j = i - T, vs = j & 1;
           ptx::mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);

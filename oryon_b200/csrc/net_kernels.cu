@@ -585,11 +585,62 @@ __global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
   }
 }
 
+// Vectorised form (channel counts and row pitch multiples of 4): one warp per output row, every lane moves 4 consecutive
+// channels of one tap per step -- a float4 load, an 8-byte hi store and an 8-byte lo store (256 contiguous bytes per warp
+// store instead of 64), the zero padding up to `ld` included in the same loop.
+__global__ void __launch_bounds__(256) im2col_vec_kernel(Im2colArgs a) {
+  const int Ct = a.C0 + a.C1, Cq = Ct >> 2, C0q = a.C0 >> 2, kk = a.k * a.k, half = a.k / 2;
+  const int nvec = kk * Cq, ldq = a.ld >> 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)a.n * a.H * a.W;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 8) {
+    const int x = (int)(row % a.W), y = (int)((row / a.W) % a.H), n = (int)(row / ((int64_t)a.W * a.H));
+    uint2* hi = reinterpret_cast<uint2*>(a.hi + row * a.ld);
+    uint2* lo = a.lo ? reinterpret_cast<uint2*>(a.lo + row * a.ld) : nullptr;
+    for (int v = lane; v < ldq; v += 32) {
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < nvec) {
+        const int tap = v / Cq, cq = v - tap * Cq;
+        const int yy = y + tap / a.k - half, xx = x + tap % a.k - half;
+        if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+          const float* src;
+          if (cq < C0q) {
+            if (a.shuffle0) {
+              const int64_t p = ((int64_t)n * (a.H / 2) + yy / 2) * (a.W / 2) + xx / 2;
+              src = a.src0 + p * 4 * a.C0 + ((yy & 1) * 2 + (xx & 1)) * a.C0 + 4 * cq;
+            } else {
+              src = a.src0 + (((int64_t)n * a.H + yy) * a.W + xx) * a.C0 + 4 * cq;
+            }
+          } else {
+            src = a.src1 + (((int64_t)n * a.H + yy) * a.W + xx) * a.C1 + 4 * (cq - C0q);
+          }
+          val = __ldg(reinterpret_cast<const float4*>(src));
+        }
+      }
+      __half h0, h1, h2, h3, l0, l1, l2, l3;
+      split_half(val.x, h0, l0), split_half(val.y, h1, l1), split_half(val.z, h2, l2), split_half(val.w, h3, l3);
+      const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const unsigned*>(&ha), pk.y = *reinterpret_cast<const unsigned*>(&hb);
+      hi[v] = pk;
+      if (lo) {
+        const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+        pk.x = *reinterpret_cast<const unsigned*>(&la), pk.y = *reinterpret_cast<const unsigned*>(&lb);
+        lo[v] = pk;
+      }
+    }
+  }
+}
+
 int im2col(oryon_handle* h, const Im2colArgs& a, cudaStream_t st) {
   ORYON_REQUIRE(a.ld >= a.k * a.k * (a.C0 + a.C1), "im2col: ld too small");
   const int64_t rows = (int64_t)a.n * a.H * a.W;
   h->span_begin(KID_IM2COL, st);
-  im2col_kernel<<<blocks_for(rows, 8, h->sm_count * 64), 256, 0, st>>>(a);
+  auto al = [](const void* p, size_t n) { return (reinterpret_cast<uintptr_t>(p) % n) == 0; };
+  const bool vec = a.C0 % 4 == 0 && a.C1 % 4 == 0 && a.ld % 4 == 0 && al(a.src0, 16) && (!a.C1 || al(a.src1, 16)) && al(a.hi, 8) &&
+                   (!a.lo || al(a.lo, 8));
+  if (vec) im2col_vec_kernel<<<blocks_for(rows, 8, h->sm_count * 64), 256, 0, st>>>(a);
+  else im2col_kernel<<<blocks_for(rows, 8, h->sm_count * 64), 256, 0, st>>>(a);
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
   return ORYON_OK;
