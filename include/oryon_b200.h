@@ -275,6 +275,16 @@ int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops);
 int oryon_mask_postproc(oryon_handle* h, const float* logits, int B, int H, int W, float mask_th, const uint8_t* gt, int Hg, int Wg,
                         int32_t* pred_mask, int32_t* gt_resized, int32_t* n_pred, int32_t* n_gt, float* iou, void* stream);
 
+/* ---- N1: batch staging (decoded frames -> network inputs) -------------------------------------------------
+ * Replaces, for B frames in one launch, preprocess_item's rgb / 255. and mask == mask_id (utils/data/common.py:48-49,
+ * :62-64), the test-time resize (utils/augmentations.py:129-141 under the reference's pinned torchvision 0.13: bilinear
+ * without antialiasing for rgb, nearest for the mask) and CollateWrapper's casts (datasets.py:205-207).
+ *   rgb       DEVICE uint8 [B][H][W][3] decoded frames            mask  DEVICE uint8 or int32 [B][H][W] label image, or NULL
+ *   mask_ids  DEVICE int32 [B] label of the object in each frame, or NULL (label 1)
+ *   out_rgb   DEVICE float32 [B][3][out_h][out_w] in [0,1]        out_mask DEVICE uint8 [B][out_h][out_w] in {0,1} */
+int oryon_stage_inputs(oryon_handle* h, const uint8_t* rgb, const void* mask, int mask_is_i32, const int32_t* mask_ids, int B, int H,
+                       int W, int out_h, int out_w, float* out_rgb, uint8_t* out_mask, void* stream);
+
 /* ---- N2: pose-error metrics of the evaluator ---------------------------------------------------------
  * Replaces the arithmetic of Evaluator.register_eval (utils/evaluator.py:206-288) for P pose pairs per call:
  * compute_RT_distances (utils/metrics.py:236-259), compute_add / compute_adds (:205-234, float16 model transform of

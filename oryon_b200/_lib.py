@@ -77,6 +77,8 @@ SIGNATURES = {
     "oryon_gemm_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double)]),
     "oryon_mask_postproc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "oryon_stage_inputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
     "oryon_eval_set_object": (c_int, [c_void_p, c_int, POINTER(c_double), c_int, POINTER(c_double), c_int]),
     "oryon_eval_pose_errors": (c_int, [c_void_p, c_int, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "oryon_pointdsc_load": (c_int, [c_void_p, POINTER(PointDSCConfig), c_void_p, c_int64, c_void_p]),

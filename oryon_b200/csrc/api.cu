@@ -53,6 +53,9 @@ int run_match(oryon_handle*, const float*, const float*, int, int, int, int, con
 int run_mask_to_roi(oryon_handle*, const int32_t*, int, int, int, int32_t*, int32_t*, cudaStream_t);
 int read_stats(oryon_handle*, int64_t*, cudaStream_t);
 }  // namespace match
+namespace stage {
+int run(oryon_handle*, const uint8_t*, const void*, int, const int32_t*, int, int, int, int, int, float*, uint8_t*, cudaStream_t);
+}  // namespace stage
 namespace eval {
 void destroy_state(oryon_handle*);
 int set_object(oryon_handle*, int, const double*, int, const double*, int);
@@ -258,6 +261,11 @@ int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops) {
   *launches = h->gemm_launches, *flops = h->gemm_flops;
   h->gemm_launches = 0, h->gemm_flops = 0.0;
   return ORYON_OK;
+}
+
+int oryon_stage_inputs(oryon_handle* h, const uint8_t* rgb, const void* mask, int mask_is_i32, const int32_t* mask_ids, int B, int H, int W,
+                       int out_h, int out_w, float* out_rgb, uint8_t* out_mask, void* stream) {
+  return oryon::stage::run(h, rgb, mask, mask_is_i32, mask_ids, B, H, W, out_h, out_w, out_rgb, out_mask, static_cast<cudaStream_t>(stream));
 }
 
 int oryon_eval_set_object(oryon_handle* h, int obj_id, const double* pts, int n, const double* syms, int n_sym) {

@@ -357,10 +357,21 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
     ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
+  static const bool log_shapes = getenv("ORYON_GEMM_LOG") != nullptr;   // diagnostic: synchronous per-launch timing to stderr
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (log_shapes) cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventRecord(e0, st);
   h->span_begin(KID_GEMM, st);
   kern<<<grid, kThreads, L::kTotal, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, ka);
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
+  if (log_shapes) {
+    cudaEventRecord(e1, st), cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "gemm M=%d N=%d K=%d batch=%dx%d TN=%d npass=%d tasks=%lld  %.1f us  %.0f TFLOP/s (algorithmic)\n", p.M, p.N, p.K, p.nb0,
+            p.nb1, TN, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  }
   ++h->gemm_launches;
   h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
   return ORYON_OK;

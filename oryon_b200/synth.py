@@ -333,3 +333,21 @@ def eval_cases(seed: int = 0, n: int = 18) -> Dict:
     return dict(pose_a=torch.stack(pose_a), gt_pose=torch.stack(gt), pred_pose=torch.stack(pred), pred_pose_rel=torch.stack(rel),
                 cls_id=cls, camera=K, iou_a=torch.rand(n, generator=g), iou_q=torch.rand(n, generator=g),
                 instance_id=[f"scene_{i}" for i in range(n)])
+
+
+def raw_frames(seed: int, n: int, hw: Tuple[int, int] = (480, 640)):
+    """``n`` decoded frames as the dataset readers return them (utils/data/nocs.py ``get_item_data``): ``rgb`` uint8 HWC,
+    ``mask`` uint8 label image (several instances, one of them ``mask_id``), ``depth`` int32 mm."""
+    rng = np.random.RandomState(9000 + seed)
+    H, W = hw
+    out = []
+    for i in range(n):
+        yy, xx = np.mgrid[0:H, 0:W]
+        base = np.stack([(xx * 255 // W), (yy * 255 // H), ((xx + yy) * 255 // (H + W))], axis=2).astype(np.int32)
+        rgb = np.clip(base + rng.randint(-60, 60, size=(H, W, 3)), 0, 255).astype(np.uint8)
+        mask = np.zeros((H, W), np.uint8)
+        for lab, (cy, cx, ry, rx) in enumerate([(0.3, 0.3, 0.12, 0.1), (0.55, 0.6, 0.2, 0.17), (0.8, 0.2, 0.08, 0.15)], start=3):
+            mask[((yy - cy * H) / (ry * H)) ** 2 + ((xx - cx * W) / (rx * W)) ** 2 <= 1.0] = lab
+        depth = rng.randint(400, 1800, size=(H, W)).astype(np.int32)
+        out.append(dict(rgb=rgb, mask=mask, depth=depth, mask_id=4, instance_id=f"frame_{seed}_{i}"))
+    return out
