@@ -123,21 +123,20 @@ __global__ void __launch_bounds__(256) prep_dense_kernel(PrepArgs a) {
   __syncthreads();
   if (threadIdx.x < kPrepPix) {
     const int p = threadIdx.x;
-    // same accumulation grouping as prep_rows_kernel is not required: both feed sqrt -> fp32 norm (1 ulp differences
-    // in the norm cannot change a row's direction by more than fp32 rounding, covered by the refine pass tolerance)
-    nrm[p] = fmaxf(sqrtf(red[0][p] + red[1][p] + red[2][p] + red[3][p]), 1e-8f);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < a.D * kPrepPix; i += 256) {
-    const int d = i / kPrepPix, p = i % kPrepPix;
-    tile[d * LD + p] = __fdiv_rn(tile[d * LD + p], nrm[p]);
+    // x / max(|x|, eps) evaluated as x * (1 / max(|x|, eps)): one division per pixel instead of one per element; the unit
+    // rows differ from a true division by <= 1 ulp, inside the tolerance of the fp32 re-scoring they feed
+    nrm[p] = __fdiv_rn(1.f, fmaxf(sqrtf(red[0][p] + red[1][p] + red[2][p] + red[3][p]), 1e-8f));
   }
   __syncthreads();
   float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;
   __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
   for (int row = warp; row < npix; row += 8) {
-    for (int d = lane; d < a.D4; d += 32) d32[(size_t)row * a.D4 + d] = d < a.D ? tile[d * LD + row] : 0.f;
-    for (int d = lane; d < a.Dpad; d += 32) d16[(size_t)row * a.Dpad + d] = __float2half_rn(d < a.D ? tile[d * LD + row] : 0.f);
+    const float inv = nrm[row];
+    for (int d = lane; d < a.Dpad || d < a.D4; d += 32) {
+      const float v = d < a.D ? tile[d * LD + row] * inv : 0.f;
+      if (d < a.D4) d32[(size_t)row * a.D4 + d] = v;
+      if (d < a.Dpad) d16[(size_t)row * a.Dpad + d] = __float2half_rn(v);
+    }
   }
 }
 
@@ -436,27 +435,52 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * kTileN) + rblk * kTileN;
         const int col_base = j * kTileN;
         const bool ragged = col_base + kTileN > pm.n_q;
-#pragma unroll
-        for (int g = 0; g < kTileN / 32; ++g) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(taddr + g * 32, v);
-          ptx::tmem_ld_wait();
+        // two register buffers: the TMEM load of group g + 1 is in flight while group g is scanned
+        uint32_t va[32], vb[32];
+        auto scan = [&](uint32_t (&v)[32], int g) {
           if (ragged) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (col_base + g * 32 + i >= pm.n_q) v[i] = 0xff800000u;  // -inf
           }
+          // all chunk maxima of the group first (four independent FMNMX chains), ONE test per 32 columns in the common
+          // case; the per-chunk bookkeeping runs only when some chunk of the group can enter the band
+          float cm[32 / kChunk];
 #pragma unroll
-          for (int c = 0; c < 32 / kChunk; ++c) {
-            const float cm = max8(v + c * kChunk);
-            if (cm >= thr) {
-              if (cm > m_run + args.ambiguity) cnt = 0;  // every earlier candidate is now out of range
-              if (cnt < kCandCap) my_list[cnt] = static_cast<uint32_t>((col_base + g * 32) / kChunk + c);
-              ++cnt;
-              m_run = fmaxf(m_run, cm);
-              thr = m_run - args.ambiguity;
+          for (int c = 0; c < 32 / kChunk; ++c) cm[c] = max8(v + c * kChunk);
+          float gm = cm[0];
+#pragma unroll
+          for (int c = 1; c < 32 / kChunk; ++c) gm = fmaxf(gm, cm[c]);
+          if (gm >= thr) {
+#pragma unroll
+            for (int c = 0; c < 32 / kChunk; ++c) {
+              if (cm[c] >= thr) {
+                if (cm[c] > m_run + args.ambiguity) cnt = 0;  // every earlier candidate is now out of range
+                if (cnt < kCandCap) {
+                  // which columns of the chunk can still win: within the band of the CHUNK maximum (a superset of the
+                  // columns within the band of the final row maximum, which is >= cm)
+                  const float lim = cm[c] - args.ambiguity;
+                  uint32_t bits = 0;
+#pragma unroll
+                  for (int i = 0; i < kChunk; ++i) bits |= (__uint_as_float(v[c * kChunk + i]) >= lim ? 1u : 0u) << i;
+                  my_list[cnt] = static_cast<uint32_t>((col_base + g * 32) / kChunk + c) | (bits << 24);
+                }
+                ++cnt;
+                m_run = fmaxf(m_run, cm[c]);
+                thr = m_run - args.ambiguity;
+              }
             }
           }
+        };
+        ptx::tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
+        for (int g = 0; g < kTileN / 32; g += 2) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x32b_x32(taddr + (g + 1) * 32, vb);
+          scan(va, g);
+          ptx::tmem_ld_wait();
+          if (g + 2 < kTileN / 32) ptx::tmem_ld_32x32b_x32(taddr + (g + 2) * 32, va);
+          scan(vb, g + 1);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -498,7 +522,6 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int col_in_chunk = lane >> 2, part = lane & 3;
   const int nvec = a.D4 >> 2;
   unsigned long long n_rows = 0, n_chunks = 0, n_over = 0;
   for (int item = wid; item < a.B * a.npad_a; item += nwarps) {
@@ -533,29 +556,28 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
       if (a.cand_m[slot] < m_all - a.ambiguity) continue;  // nothing in this split can win
       const int cnt = a.cand_cnt[slot];
       for (int e = 0; e < cnt; ++e) {
-        const int col = (int)a.cand_chunk[slot * kCandCap + e] * kChunk + col_in_chunk;
-        float acc = 0.f;
-        if (col < pm.n_q) {
+        const uint32_t ent = a.cand_chunk[slot * kCandCap + e];
+        const int col0 = (int)(ent & 0xFFFFFFu) * kChunk;
+        uint32_t bits = ent >> 24;
+        while (bits) {   // usually a single column: the whole warp scores it (one float4 per lane at D = 128)
+          const int col = col0 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (col >= pm.n_q) continue;
           const float4* qrow = reinterpret_cast<const float4*>(a.rows32_q + ((size_t)b * a.npad_q + col) * a.D4);
-          for (int i = part; i < nvec; i += 4) {
+          float acc = 0.f;
+          for (int i = lane; i < nvec; i += 32) {
             const float4 x = __ldg(arow + i), y = __ldg(qrow + i);
             acc = fmaf(x.x, y.x, acc);
             acc = fmaf(x.y, y.y, acc);
             acc = fmaf(x.z, y.z, acc);
             acc = fmaf(x.w, y.w, acc);
           }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (acc > best || (acc == best && col < best_j)) best = acc, best_j = col;
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (col < pm.n_q && (acc > best || (acc == best && col < best_j))) best = acc, best_j = col;
         ++n_chunks;
       }
-    }
-#pragma unroll
-    for (int off = 4; off < 32; off <<= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
-      if (ov > best || (ov == best && oj < best_j)) best = ov, best_j = oj;
     }
     if (lane == 0) {
       a.out_idx[o] = best_j;

@@ -66,7 +66,7 @@ def mask_postproc(logits: Optional[Tensor], gt: Optional[Tensor], size: Tuple[in
 
 
 class FPM_Pipeline:
-    def __init__(self, args, test_model: bool = False, *, model: Optional[Oryon] = None, pointdsc_solver=None):
+    def __init__(self, args, test_model: bool = False, *, model: Optional[Oryon] = None, pointdsc_solver=None, evaluator=None):
         self.args = args
         self.test_model = test_model
         self.device = torch.device(_get(args, "device", "cuda"))
@@ -88,6 +88,7 @@ class FPM_Pipeline:
         self.featmap_size = tuple(_get(args, "model.image_encoder.img_size", (192, 192)))
         self.pred_file = None
         self.rows: List[dict] = []
+        self.evaluator = evaluator                                        # oryon_b200.utils.evaluator.Evaluator or None
         self.batched_tail = bool(_get(args, "test.batched_tail", True))   # False: per-pair selection / lifting (any frame sizes)
         self._host_dist: Optional[Tensor] = None
         self._host_rows: Optional[Tensor] = None
@@ -337,4 +338,31 @@ class FPM_Pipeline:
             rows.append(dict(instance_id_a=id_a, instance_id_q=id_q, pred_pose_rel=pred_pose, pred_pose=pred_q, iou_a=float(iou_a[b]),
                              iou_q=float(iou_q[b]), status=status, corrs=corrs[b]))
         self.rows.extend(rows)
+        if self.evaluator is not None:
+            self._register(batch, rows)
         return rows
+
+    def _register(self, batch: dict, rows: List[dict]) -> None:
+        """Evaluator bookkeeping of the reference's loop (pipeline.py:321-350), in pair order; consecutive successful
+        pairs go to the (batched, GPU) ``register_test`` in one call."""
+        def flush(run):
+            if not run:
+                return
+            sel = torch.tensor(run)
+            self.evaluator.register_test({
+                "iou_a": torch.tensor([rows[i]["iou_a"] for i in run]), "iou_q": torch.tensor([rows[i]["iou_q"] for i in run]),
+                "gt_pose": batch["query"]["pose"].cpu()[sel], "pred_pose": torch.stack([rows[i]["pred_pose"] for i in run]),
+                "pred_pose_rel": torch.stack([rows[i]["pred_pose_rel"] for i in run]), "cls_id": [batch["cls_id"][i] for i in run],
+                "camera": [batch["query"]["camera"][i].cpu().numpy() for i in run], "depth": [None for _ in run],
+                "instance_id": [batch["instance_id"][i] for i in run]})
+
+        run: List[int] = []
+        for i, r in enumerate(rows):
+            if r["status"] == "ok":
+                run.append(i)
+                continue
+            flush(run)
+            run = []
+            self.evaluator.register_test_failure({"iou_a": torch.tensor([r["iou_a"]]), "iou_q": torch.tensor([r["iou_q"]]),
+                                                  "cls_id": [batch["cls_id"][i]], "instance_id": [batch["instance_id"][i]]})
+        flush(run)

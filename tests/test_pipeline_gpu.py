@@ -178,3 +178,34 @@ def test_mask_postproc_bit_exact():
     assert mp["n_pred"].cpu().tolist() == [int((ref_mask[i] == 1).sum()) for i in range(4)]
     for i in range(4):
         assert torch.equal(oracle.resize_mask_nearest(gt[i], (192, 192)), mp["gt_resized"][i].cpu())
+
+
+def test_test_step_feeds_evaluator(system):
+    """test_step with an Evaluator attached: the reference's register_test / register_test_failure bookkeeping
+    (pipeline.py:321-350) in pair order, pose errors on the GPU; compared with the oracle's arithmetic on the same poses."""
+    import eval_oracle
+    from oryon_b200.utils.evaluator import Evaluator, format_sym_set
+    _, solver, psd = system
+    outputs, batch = synth.planted_network_outputs(21, 4)
+    obj = synth.eval_objects(0)
+    batch["cls_id"] = [1, 2, 3, 2]
+    batch["anchor"]["mask"][2] = 0                      # pair 2 fails the detection test in oracle-mask mode
+    ev = Evaluator("planted", compute_vsd=False, compute_iou=True, device="cuda:0")
+    ev.add_object_info(obj["models"], obj["diams"], obj["syms"])
+    ev.init_test()
+    args = dict(ARGS, test=dict(ARGS["test"], mask="oracle"))
+    pipe = FPM_Pipeline(args, test_model=True, model=_PlantedModel({k: v.cuda() for k, v in outputs.items()}), pointdsc_solver=solver,
+                        evaluator=ev)
+    pipe.on_test_start()
+    rows = pipe.test_step(_cuda_batch(batch), 0)
+    assert [r["status"] for r in rows] == ["ok", "ok", "invalid_mask", "ok"]
+    assert ev.metrics["instance_id"] == batch["instance_id"] and ev.metrics["cls_id"] == batch["cls_id"]
+    assert ev.counts["Missing segm"] == [0, 0, 1, 0]
+    syms = {k: format_sym_set(s) for k, s in obj["syms"].items()}
+    for i in (0, 1, 3):
+        ref = eval_oracle.pose_errors(obj["models"], syms, [batch["cls_id"][i]], rows[i]["pred_pose"].numpy()[None],
+                                      batch["query"]["pose"][i].numpy()[None], batch["query"]["camera"][i].numpy()[None])[0]
+        assert abs(ev.metrics["T error"][i] - ref[1]) < 1e-9
+        assert ev.metrics["ADD(S)-0.1d"][i] == float(ref[2] <= ev.add_diams[batch["cls_id"][i]] * 0.1)
+        assert ev.metrics["MSSD"][i] == (ref[4] < ev.mssd_rec * obj["diams"][batch["cls_id"][i]]).mean()
+    assert ev.metrics["R error"][2] == 0.0 and ev.metrics["MSSD"][2] == 0.0
