@@ -92,7 +92,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
   uint64_t* o_full = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQ, head = blockIdx.y, seq = blockIdx.z;
   const int T = a.T;
   const bool dbg = a.dbg && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5;
@@ -159,26 +159,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
       STAMP(60 + j);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      {
+        // warp-uniform descriptors, one elected lane issues (see gemm.cu): the 8 * NPASS MMAs go out back to back
         const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV + (j & 1) * L::kVBytes);
+        const bool leader = ptx::elect_one();
 #pragma unroll
         for (int pass = 0; pass < NPASS; ++pass) {
           // pass 0: P_hi V_hi   pass 1: P_lo V_hi   pass 2: P_hi V_lo
-          const uint32_t pa = p_addr + (pass == 1 ? 2 * kTileBytes : 0);
+          const uint64_t dp0 = ptx::make_smem_desc_kmajor(p_addr + (pass == 1 ? 2 * kTileBytes : 0), 128);
           const uint32_t va = v_addr + (pass == 2 ? kTileBytes : 0);
+          const uint64_t dv0 = VMN ? ptx::make_smem_desc_mnmajor_sw128(va, 0, 1024) : ptx::make_smem_desc_kmajor(va, 128);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t dp = ptx::make_smem_desc_kmajor(pa + sub * kTileBytes + k * 32, 128);
-              // 16 keys per MMA: K-major V^T advances 32 bytes inside the swizzled row; MN-major V advances two 8-key groups
-              const uint64_t dv = VMN ? ptx::make_smem_desc_mnmajor_sw128(va + (sub * 4 + k) * 2048, 0, 1024)
-                                      : ptx::make_smem_desc_kmajor(va + sub * (kTileBytes / 2) + k * 32, 128);
-              ptx::umma_f16(tmem_o, dp, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
+              // descriptor start-address field is (bytes >> 4).  P: 16 KB per 64-key sub-tile, 32 bytes per 16 keys.
+              // 16 keys per MMA: MN-major V advances two 8-key groups (2 KB); K-major V^T 32 bytes inside the swizzled row.
+              const uint64_t dp = dp0 + (sub * (kTileBytes >> 4) + 2 * k);
+              const uint64_t dv = dv0 + (VMN ? (sub * 4 + k) * (2048 >> 4) : sub * (kTileBytes >> 5) + 2 * k);
+              if (leader) ptx::umma_f16(tmem_o, dp, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
             }
         }
-        ptx::umma_commit(&v_empty[j & 1]);
-        ptx::umma_commit(p_empty);
+        if (leader) {
+          ptx::umma_commit(&v_empty[j & 1]);
+          ptx::umma_commit(p_empty);
+        }
       }
       __syncwarp();
     };
@@ -191,27 +196,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       ptx::mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
       STAMP(30 + i);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + st * L::kKStage);
         const int npass = i < T ? 1 : NPASS;   // pass 1 only needs an approximate maximum
+        const bool leader = ptx::elect_one();
 #pragma unroll
         for (int pass = 0; pass < NPASS; ++pass) {
           if (pass >= npass) break;
-          const uint32_t qa = q_addr + (pass == 1 ? kTileBytes : 0);
-          const uint32_t ka = k_addr + (pass == 2 ? kTileBytes : 0);
+          const uint64_t dq0 = ptx::make_smem_desc_kmajor(q_addr + (pass == 1 ? kTileBytes : 0), 128);
+          const uint64_t dk0 = ptx::make_smem_desc_kmajor(k_addr + (pass == 2 ? kTileBytes : 0), 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_f16(tmem_base + st * 128, ptx::make_smem_desc_kmajor(qa + k * 32, 128), ptx::make_smem_desc_kmajor(ka + k * 32, 128),
-                          kIdescS, (pass | k) != 0 ? 1u : 0u);
+            if (leader) ptx::umma_f16(tmem_base + st * 128, dq0 + 2 * k, dk0 + 2 * k, kIdescS, (pass | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(&k_empty[st]);
-        ptx::umma_commit(&s_full[st]);
+        if (leader) {
+          ptx::umma_commit(&k_empty[st]);
+          ptx::umma_commit(&s_full[st]);
+        }
       }
       __syncwarp();
       if (i > T) issue_pv(i - 1 - T);
     }
     issue_pv(T - 1);
-    if (lane == 0) ptx::umma_commit(o_full);
+    if (ptx::elect_one()) ptx::umma_commit(o_full);
     __syncwarp();
   } else {
     const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
@@ -253,7 +260,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     // ---- pass 2: probabilities -> registers -> shared memory (swizzled K-major), row sum ----
     float l = 0.f;
     const float ms = m * a.scale_log2e;
-    uint8_t* prow = sP + half * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;   // this row inside sub-tile `half`
+    const uint32_t prow = ptx::smem_u32(sP) + half * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;   // this row inside sub-tile `half`
     for (int j = 0; j < T; ++j) {
       const int i = T + j, st = i & 1;
       ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
@@ -293,9 +300,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
 #pragma unroll
       for (int c = 0; c < 8; ++c) {                                // 8 chunks of 16 bytes = this warp's 64 columns
         const int chunk = c ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
-        if (NPASS == 3)
-          *reinterpret_cast<uint4*>(prow + 2 * kTileBytes + chunk * 16) = make_uint4(pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
+        ptx::st_shared_v4(prow + chunk * 16, ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
+        if (NPASS == 3) ptx::st_shared_v4(prow + 2 * kTileBytes + chunk * 16, pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
       }
       ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();

@@ -90,7 +90,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint64_t* t_empty = t_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a_hi);
     ptx::prefetch_tensormap(&tm_w_hi);
@@ -143,27 +143,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int kb = 0; kb < args.KB; ++kb) {
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        {
+          // every lane computes the (warp-uniform) descriptors, one elected lane issues: the UTCHMMAs of a stage go out back
+          // to back from uniform registers (an `if (lane == 0)` region rebuilt each descriptor from per-thread registers,
+          // ~15 dependent instructions per MMA on the single issuing thread)
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
           const uint32_t sw = sa + L::kABytes;
+          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS == 3 ? L::kWBlock : 0), 128);
+          const bool leader = ptx::elect_one();
 #pragma unroll
           for (int r = 0; r < kRowBlocks; ++r) {
             const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * TN) + r * TN;
+            const uint64_t da_hi = ptx::make_smem_desc_kmajor(sa + r * L::kABlock, 128);
+            const uint64_t da_lo = ptx::make_smem_desc_kmajor(sa + ((NPASS == 3 ? kRowBlocks : 0) + r) * L::kABlock, 128);
 #pragma unroll
             for (int pass = 0; pass < NPASS; ++pass) {
               // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
-              const uint32_t a_addr = sa + ((pass == 1 ? kRowBlocks : 0) + r) * L::kABlock;
-              const uint32_t w_addr = sw + (pass == 2 ? L::kWBlock : 0);
+              const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
 #pragma unroll
-              for (int k = 0; k < kKB / 16; ++k) {
-                const uint64_t da = ptx::make_smem_desc_kmajor(a_addr + k * 32, 128);
-                const uint64_t dw = ptx::make_smem_desc_kmajor(w_addr + k * 32, 128);
-                ptx::umma_f16(d_tmem, da, dw, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < kKB / 16; ++k)
+                if (leader) ptx::umma_f16(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);   // +32 bytes >> 4
             }
           }
-          ptx::umma_commit(&empty[stage]);
-          if (kb == args.KB - 1) ptx::umma_commit(&t_full[buf]);
+          if (leader) {
+            ptx::umma_commit(&empty[stage]);
+            if (kb == args.KB - 1) ptx::umma_commit(&t_full[buf]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -179,8 +184,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int ew = warp - 2, rblk = ew >> 2, quarter = warp & 3;
     const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
     const Epilogue& ep = args.ep;
-    float* stage_f = reinterpret_cast<float*>(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats;  // [32][kEpiLd]
-    float* bias_s = stage_f + 32 * kEpiLd;                                                                       // [TN]
+    // explicit shared-space addresses: generic pointers into dynamic shared memory compile to LD.E / ST.E
+    const uint32_t stage_f = ptx::smem_u32(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats * 4;   // [32][kEpiLd] floats
+    const uint32_t bias_s = stage_f + 32 * kEpiLd * 4;                                                             // [TN] floats
     const int sub_row = lane >> 2, cg = lane & 3;
     uint32_t tile_iter = 0;
     for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
@@ -196,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
       for (int j = 0; j < TN / 32; ++j) {
         const int col = nt * TN + j * 32 + lane;
-        bias_s[j * 32 + lane] = (ep.bias && col < args.N) ? __ldg(ep.bias + col) : 0.f;
+        ptx::st_shared_f1(bias_s + (j * 32 + lane) * 4, (ep.bias && col < args.N) ? __ldg(ep.bias + col) : 0.f);
       }
       __syncwarp();
       ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
@@ -212,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         float x[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 bq = *reinterpret_cast<const float4*>(bias_s + g * 16 + 4 * i);
+          const float4 bq = ptx::ld_shared_f4(bias_s + (g * 16 + 4 * i) * 4);
           x[4 * i] = fmaf(__uint_as_float(v[4 * i]), ep.alpha, bq.x), x[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), ep.alpha, bq.y);
           x[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), ep.alpha, bq.z), x[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), ep.alpha, bq.w);
         }
@@ -249,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         __syncwarp();  // previous chunk's readers are done with the staging tile
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4*>(stage_f + lane * kEpiLd + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          ptx::st_shared_f4(stage_f + (lane * kEpiLd + 4 * i) * 4, make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
         __syncwarp();
         const int col = col0 + cg * 4;
         const bool vec_ok = col + 3 < args.N;
@@ -258,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           const int r = k * 8 + sub_row;
           const int dr = __shfl_sync(0xffffffffu, drow, r);
           if (dr < 0 || col >= args.N) continue;
-          float4 y = *reinterpret_cast<const float4*>(stage_f + r * kEpiLd + cg * 4);
+          float4 y = ptx::ld_shared_f4(stage_f + (r * kEpiLd + cg * 4) * 4);
           const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
           if (vec_ok && (ep.ld32 & 3) == 0) {
             if (ep.residual) {

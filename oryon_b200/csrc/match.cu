@@ -307,7 +307,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* t_empty = t_full + 2;        // [2] accumulator drained
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
@@ -362,12 +362,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
+    // Every lane runs the (warp-uniform) control flow; one elected lane issues.  Descriptors are built once per stage /
+    // row block and advanced by adding 2 (= 32 bytes >> 4) per 16-element K step.
     uint32_t stage = 0, phase = 0, task_iter = 0, tile_iter = 0;
     for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
       const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
-      const PairMeta pm = args.meta[b];
-      if (rb * kCtaRows >= pm.n_a || pm.n_q <= 0) continue;
-      const int tiles = (pm.n_q + kTileN - 1) / kTileN;
+      const int n_a = __shfl_sync(0xffffffffu, args.meta[b].n_a, 0), n_q = __shfl_sync(0xffffffffu, args.meta[b].n_q, 0);
+      if (rb * kCtaRows >= n_a || n_q <= 0) continue;
+      const int tiles = (n_q + kTileN - 1) / kTileN;
       const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
       if (j0 >= j1) continue;
       ptx::mbar_wait(a_full, task_iter & 1);
@@ -378,19 +380,17 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int kb = 0; kb < NUM_KB; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t q_addr = ptx::smem_u32(smem_q + stage * L::kQStage);
+          const uint64_t dq0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_q + stage * L::kQStage), kRowBytes);
+          const bool leader = ptx::elect_one();
 #pragma unroll
-            for (int r = 0; r < kRowBlocks; ++r) {
-              const uint32_t a_addr = ptx::smem_u32(smem_a + (kb * kRowBlocks + r) * L::kABlock);
-              const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * kTileN) + r * kTileN;
+          for (int r = 0; r < kRowBlocks; ++r) {
+            const uint64_t da0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_a + (kb * kRowBlocks + r) * L::kABlock), kRowBytes);
+            const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * kTileN) + r * kTileN;
 #pragma unroll
-              for (int k = 0; k < kKSteps; ++k) {
-                const uint64_t da = ptx::make_smem_desc_kmajor(a_addr + k * 32, kRowBytes);
-                const uint64_t dq = ptx::make_smem_desc_kmajor(q_addr + k * 32, kRowBytes);
-                ptx::umma_f16(d_tmem, da, dq, kIdesc, (kb | k) != 0 ? 1u : 0u);
-              }
-            }
+            for (int k = 0; k < kKSteps; ++k)
+              if (leader) ptx::umma_f16(d_tmem, da0 + 2 * k, dq0 + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (leader) {
             ptx::umma_commit(&empty[stage]);                       // smem slot reusable when these MMAs retire
             if (kb == NUM_KB - 1) ptx::umma_commit(&t_full[buf]);  // accumulator complete
           }
@@ -399,7 +399,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         ++tile_iter;
       }
-      if (lane == 0) ptx::umma_commit(a_empty);
+      if (ptx::elect_one()) ptx::umma_commit(a_empty);
       __syncwarp();
       ++task_iter;
     }
