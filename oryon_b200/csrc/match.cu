@@ -13,6 +13,7 @@
 // Layouts: rows16_x [B][Npad_x][Dpad] __half, rows32_x [B][Npad_x][D4] float (D4 = D rounded up to 4,
 // zero padded).  Candidate lists: cand_m / cand_cnt [B][S][Npad_a], cand_chunk [B][S][Npad_a][CAND_CAP].
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -27,7 +28,11 @@ constexpr int kTileN = 128;        // query columns per tile
 constexpr int kChunk = 8;          // columns per candidate chunk
 constexpr int kCandCap = 16;       // candidate chunks kept per (row, split)
 constexpr int kMaxSplits = 8;
-constexpr int kTcThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// Epilogue warp sets: with 2, set e scans only the tiles that land in TMEM accumulator buffer e (twice the time per scan, one
+// candidate list per (row, set), merged by the refine pass like splits).  Measured on B200 at config 2: 2.52 ms with two sets vs
+// 2.45 ms with one -- the scan is not what bounds the kernel, so one set is used.
+constexpr int kEpiSets = 1;
+constexpr int kTcThreads = 64 + 256 * kEpiSets;   // warp 0 TMA, warp 1 MMA, 8 epilogue warps per set
 // |fp16-operand score - fp32 score| <= 2^-10 (two roundings of unit-norm operands, Cauchy-Schwarz)
 // + accumulation slack; a column can be the fp32 argmax only if its fp16 score is within twice that
 // of the fp16 row maximum.
@@ -404,8 +409,13 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       ++task_iter;
     }
   } else {
-    // ============================ epilogue (8 warps) ============================
-    const int ew = warp - 2;               // 0..7
+    // ============================ epilogue (kEpiSets x 8 warps) ============================
+    // The scan of one accumulator (4 TMEM loads + ~240 dependent ALU instructions per warp) takes longer than the MMAs that
+    // fill the other buffer.  Two warp sets therefore split the tiles by accumulator buffer: set e owns buffer e, i.e.
+    // every second tile, and has two tile periods per scan.  Each (row, set) keeps its own candidate list; the refine
+    // pass sees the sets as extra splits (slot = ((b * splits + s) * kEpiSets + set) * npad_a + row).
+    const int ew = (warp - 2) & 7;         // 0..7 within the set
+    const int set = (warp - 2) >> 3;
     const int rblk = ew >> 2;              // which 128-row block of the CTA tile
     const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
     const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
@@ -418,7 +428,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
       const int row = rb * kCtaRows + row_in_cta;
       const bool row_ok = row < pm.n_a;
-      const size_t slot = ((size_t)b * args.splits + s) * args.npad_a + row;
+      const size_t slot = (((size_t)b * args.splits + s) * kEpiSets + set) * args.npad_a + row;
       if (j0 >= j1) {
         // this split owns no tile (more splits than tiles): publish an empty list
         if (row_ok) args.cand_m[slot] = -INFINITY, args.cand_cnt[slot] = 0;
@@ -430,6 +440,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int cnt = 0;
       for (int j = j0; j < j1; ++j) {
         const uint32_t buf = tile_iter & 1;
+        if ((int)buf != set) {   // the other set's tile
+          ++tile_iter;
+          continue;
+        }
         ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * kTileN) + rblk * kTileN;
@@ -710,7 +724,8 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   const int kb_elems = sw64 ? 32 : 64;
   const int Dpad = round_up(D, kb_elems);
   const int num_kb = Dpad / kb_elems;
-  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), kTileN);
+  const int tile_n = kTileN;
+  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), tile_n);
 
   if ((rc = h->rows16_a.reserve((size_t)B * npad_a * Dpad * 2, st))) return rc;
   if ((rc = h->rows16_q.reserve((size_t)B * npad_q * Dpad * 2, st))) return rc;
@@ -764,11 +779,12 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
 
   // ---- tensor-core pass ----
   const int rb_per_pair = npad_a / kCtaRows;
-  const int tiles_max = npad_q / kTileN;
+  const int tiles_max = npad_q / tile_n;
+  const int halves = kEpiSets;   // candidate lists per (row, split): one per epilogue warp set
   int splits = 1;
   if (B * rb_per_pair < h->sm_count) splits = std::min({kMaxSplits, tiles_max, (h->sm_count + B * rb_per_pair - 1) / (B * rb_per_pair)});
   splits = std::max(splits, 1);
-  const size_t slots = (size_t)B * splits * npad_a;
+  const size_t slots = (size_t)B * splits * halves * npad_a;
   if ((rc = h->cand.reserve(slots * (4 + 4 + 4 * kCandCap), st))) return rc;
   if ((rc = h->overflow_rows.reserve((size_t)B * npad_a * 4, st))) return rc;
   TcArgs ta;
@@ -781,7 +797,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
 
   CUtensorMap tma, tmq;
   if ((rc = make_rows_tensor_map(h, &tma, h->rows16_a.ptr, B * npad_a, Dpad, kb_elems, kTileM))) return rc;
-  if ((rc = make_rows_tensor_map(h, &tmq, h->rows16_q.ptr, B * npad_q, Dpad, kb_elems, kTileN))) return rc;
+  if ((rc = make_rows_tensor_map(h, &tmq, h->rows16_q.ptr, B * npad_q, Dpad, kb_elems, tile_n))) return rc;
   const int grid = std::min(h->sm_count, B * rb_per_pair * splits);
   if (sw64) {
     rc = launch_tc<32, 1, 8>(h, tma, tmq, ta, grid, st);
@@ -800,7 +816,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   ra.rows32_a = ea.rows32_a, ra.rows32_q = ea.rows32_q;
   ra.meta = d_meta;
   ra.cand_m = ta.cand_m, ra.cand_cnt = ta.cand_cnt, ra.cand_chunk = ta.cand_chunk;
-  ra.B = B, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = splits, ra.cap_a = cap_a;
+  ra.B = B, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = splits * halves, ra.cap_a = cap_a;
   ra.ambiguity = kAmbiguity;
   ra.out_idx = out_idx, ra.out_dist = out_dist;
   ra.overflow_rows = h->overflow_rows.as<int32_t>();

@@ -351,3 +351,66 @@ def raw_frames(seed: int, n: int, hw: Tuple[int, int] = (480, 640)):
         depth = rng.randint(400, 1800, size=(H, W)).astype(np.int32)
         out.append(dict(rgb=rgb, mask=mask, depth=depth, mask_id=4, instance_id=f"frame_{seed}_{i}"))
     return out
+
+
+def eval_mesh_objects(seed: int = 0) -> Dict:
+    """Three closed triangle meshes (``pts`` mm, ``faces``) in the ``get_object_info()`` format, for the VSD / AR part of the
+    evaluator: 1 an asymmetric ellipsoid with a bump, 2 a 24-gon prism (24-fold symmetry about z), 3 a box (2-fold)."""
+    rng = np.random.RandomState(100 + seed)
+    models, diams, syms = {}, {}, {}
+
+    def lathe(profile_r, profile_z, n_seg, scale=(1.0, 1.0, 1.0), bump=None):
+        rings = len(profile_r)
+        ang = np.arange(n_seg) * 2 * np.pi / n_seg
+        pts = [[0.0, 0.0, profile_z[0] - 1e-9]]
+        for r_, z_ in zip(profile_r, profile_z):
+            for a_ in ang:
+                pts.append([r_ * np.cos(a_), r_ * np.sin(a_), z_])
+        pts.append([0.0, 0.0, profile_z[-1] + 1e-9])
+        pts = np.asarray(pts) * np.asarray(scale)
+        if bump is not None:
+            d = np.linalg.norm(pts - bump[:3], axis=1)
+            pts = pts * (1.0 + bump[3] * np.exp(-(d / bump[4]) ** 2))[:, None]
+        faces = []
+        ring = lambda k, i: 1 + k * n_seg + (i % n_seg)  # noqa: E731
+        for i in range(n_seg):
+            faces.append([0, ring(0, i + 1), ring(0, i)])
+            faces.append([len(pts) - 1, ring(rings - 1, i), ring(rings - 1, i + 1)])
+            for k in range(rings - 1):
+                faces.append([ring(k, i), ring(k, i + 1), ring(k + 1, i + 1)])
+                faces.append([ring(k, i), ring(k + 1, i + 1), ring(k + 1, i)])
+        return pts, np.asarray(faces, dtype=np.int64)
+
+    th = np.linspace(0.15, np.pi - 0.15, 14)
+    p, f = lathe(50 * np.sin(th), -50 * np.cos(th), 28, scale=(1.0, 0.7, 1.3), bump=np.array([40.0, 10.0, 20.0, 0.35, 30.0]))
+    models[1], syms[1] = dict(pts=p, faces=f), [dict(R=np.eye(3), t=np.zeros((3, 1)))]
+    p, f = lathe(np.array([45.0, 45.0, 30.0, 30.0]), np.array([-60.0, 10.0, 20.0, 60.0]), 24)
+    models[2] = dict(pts=p, faces=f)
+    syms[2] = [dict(R=_axis_rotation([0, 0, 1], 2 * np.pi * i / 24), t=np.zeros((3, 1))) for i in range(24)]
+    p, f = lathe(np.array([60.0, 60.0]) * np.sqrt(2), np.array([-25.0, 25.0]), 4, scale=(1.0, 0.5, 1.0))
+    p = p @ _axis_rotation([0, 0, 1], np.pi / 4).T
+    models[3] = dict(pts=p, faces=f)
+    syms[3] = [dict(R=np.eye(3), t=np.zeros((3, 1))), dict(R=_axis_rotation([0, 0, 1], np.pi), t=np.zeros((3, 1)))]
+    for k, m in models.items():
+        q = m["pts"]
+        diams[k] = float(np.sqrt(((q[:, None, :] - q[None, :, :]) ** 2).sum(-1)).max())
+    del rng
+    return dict(models=models, diams=diams, syms=syms)
+
+
+def eval_scene_depth(models: Dict, cls_id: int, gt_pose: np.ndarray, K: np.ndarray, seed: int, hw: Tuple[int, int] = (480, 640),
+                     render=None) -> np.ndarray:
+    """A test depth image (int32 mm) for the VSD evaluation of one pair: the object rendered in its ground-truth pose over a
+    far background plane, an occluder strip across part of it and a band of missing (zero) depth.  ``render`` is the
+    rasteriser to use (tests pass the oracle's; nothing in the product path calls this)."""
+    H, W = hw
+    rng = np.random.RandomState(500 + seed)
+    m = models[cls_id]
+    d = render(m["pts"], m["faces"], gt_pose[:3, :3], gt_pose[:3, 3] * 1000.0, K[0, 0], K[1, 1], K[0, 2], K[1, 2], H, W)
+    scene = np.where(d > 0, d + rng.randn(H, W).astype(np.float32) * 1.0, 1800.0 + rng.randn(H, W).astype(np.float32) * 2.0)
+    ys, xs = np.nonzero(d > 0)
+    if ys.size:
+        yc, xc = int(ys.mean()), int(xs.mean())
+        scene[max(0, yc - 4):yc + 5, :] = np.minimum(scene[max(0, yc - 4):yc + 5, :], float(d[d > 0].min()) - 60.0)   # occluder
+        scene[:, max(0, xc + 6):xc + 12] = 0.0                                                                          # missing depth
+    return np.round(scene).astype(np.int32)
