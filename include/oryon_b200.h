@@ -303,6 +303,20 @@ int oryon_eval_set_object(oryon_handle* h, int obj_id, const double* pts, int n,
 int oryon_eval_pose_errors(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams,
                            double* out, void* stream);
 
+/* VSD of the evaluator (bop_toolkit_lib/pose_error.py:17-96 as called from utils/evaluator.py:279-286: delta, taus,
+ * normalisation by the object diameter, 'step' cost, visibility mode 'bop19').  The depth images of the model in the two
+ * poses come from a z-buffer rasteriser that follows the conventions of bop_toolkit_lib/renderer_vispy.py (sample of
+ * pixel (r, c) at (c + 0.5, r + 0.5), nearest surface, no culling); the reference renders with OpenGL, so this one step
+ * has no reference output to be compared with.
+ *   oryon_eval_set_object_mesh: faces HOST int32 [n_faces][3] vertex indices into the points given to oryon_eval_set_object
+ *   oryon_eval_vsd: pred / gt / cams as for oryon_eval_pose_errors; depth_test DEVICE [P][H][W] int32 (depth_is_f32 = 0) or
+ *   float32 (1), millimetres, 0 = missing; taus HOST float64 [n_tau <= 16]; diameters HOST float64 [P] (mm);
+ *   out DEVICE float64 [P][n_tau] */
+int oryon_eval_set_object_mesh(oryon_handle* h, int obj_id, const int32_t* faces, int n_faces);
+int oryon_eval_vsd(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams,
+                   const void* depth_test, int depth_is_f32, int H, int W, double delta, const double* taus, int n_tau,
+                   const double* diameters, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ SIGNATURES = {
                                    c_void_p]),
     "oryon_eval_set_object": (c_int, [c_void_p, c_int, POINTER(c_double), c_int, POINTER(c_double), c_int]),
     "oryon_eval_pose_errors": (c_int, [c_void_p, c_int, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "oryon_eval_set_object_mesh": (c_int, [c_void_p, c_int, POINTER(c_int32), c_int]),
+    "oryon_eval_vsd": (c_int, [c_void_p, c_int, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double,
+                               POINTER(c_double), c_int, POINTER(c_double), c_void_p, c_void_p]),
     "oryon_pointdsc_load": (c_int, [c_void_p, POINTER(PointDSCConfig), c_void_p, c_int64, c_void_p]),
     "oryon_pointdsc_pose": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_void_p,
                                     POINTER(PointDSCDebug), c_void_p]),

@@ -60,6 +60,9 @@ namespace eval {
 void destroy_state(oryon_handle*);
 int set_object(oryon_handle*, int, const double*, int, const double*, int);
 int pose_errors(oryon_handle*, int, const int32_t*, const double*, const double*, const double*, double*, cudaStream_t);
+int set_object_mesh(oryon_handle*, int, const int32_t*, int);
+int vsd(oryon_handle*, int, const int32_t*, const double*, const double*, const double*, const void*, int, int, int, double, const double*, int,
+        const double*, double*, cudaStream_t);
 }  // namespace eval
 namespace lift {
 int run_lift(oryon_handle*, const void*, int, int, int, const double*, const int64_t*, const int64_t*, int, float*, cudaStream_t);
@@ -274,6 +277,16 @@ int oryon_eval_set_object(oryon_handle* h, int obj_id, const double* pts, int n,
 int oryon_eval_pose_errors(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams,
                            double* out, void* stream) {
   return oryon::eval::pose_errors(h, P, obj_ids, pred, gt, cams, out, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_eval_set_object_mesh(oryon_handle* h, int obj_id, const int32_t* faces, int n_faces) {
+  return oryon::eval::set_object_mesh(h, obj_id, faces, n_faces);
+}
+int oryon_eval_vsd(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams,
+                   const void* depth_test, int depth_is_f32, int H, int W, double delta, const double* taus, int n_tau,
+                   const double* diameters, double* out, void* stream) {
+  return oryon::eval::vsd(h, P, obj_ids, pred, gt, cams, depth_test, depth_is_f32, H, W, delta, taus, n_tau, diameters, out,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int oryon_mask_postproc(oryon_handle* h, const float* logits, int B, int H, int W, float mask_th, const uint8_t* gt, int Hg, int Wg,

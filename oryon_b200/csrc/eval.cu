@@ -27,12 +27,14 @@ constexpr int kTile = 1024;   // ground-truth points staged in shared memory per
 struct Object {
   double* pts = nullptr;    // [n][3] mm
   double* syms = nullptr;   // [s][12] rows of [R | t]
-  int n = 0, s = 0;
+  int32_t* faces = nullptr; // [f][3] vertex indices (VSD only)
+  int n = 0, s = 0, f = 0;
 };
 
 struct State {
   std::map<int, Object> objects;
   DeviceBuffer ws;          // partial sums [P][kChunks] doubles + counters [P] ints
+  DeviceBuffer vsd_ws;      // projected vertices, depth buffers and counters of the VSD pass
 };
 
 struct PoseObj {
@@ -251,8 +253,9 @@ static State* state(oryon_handle* h) {
 void destroy_state(oryon_handle* h) {
   if (!h->eval_state) return;
   State* s = static_cast<State*>(h->eval_state);
-  for (auto& kv : s->objects) cudaFree(kv.second.pts), cudaFree(kv.second.syms);
+  for (auto& kv : s->objects) cudaFree(kv.second.pts), cudaFree(kv.second.syms), cudaFree(kv.second.faces);
   s->ws.release();
+  s->vsd_ws.release();
   delete s;
   h->eval_state = nullptr;
 }
@@ -262,7 +265,7 @@ int set_object(oryon_handle* h, int obj_id, const double* pts, int n, const doub
   ORYON_CUDA_CHECK(cudaSetDevice(h->device));
   State* s = state(h);
   Object& o = s->objects[obj_id];
-  if (o.pts) cudaFree(o.pts), cudaFree(o.syms);
+  if (o.pts) cudaFree(o.pts), cudaFree(o.syms), cudaFree(o.faces);
   o = Object();
   ORYON_CUDA_CHECK(cudaMalloc(&o.pts, sizeof(double) * 3 * (size_t)n));
   ORYON_CUDA_CHECK(cudaMalloc(&o.syms, sizeof(double) * 12 * (size_t)n_sym));
@@ -294,6 +297,213 @@ int pose_errors(oryon_handle* h, int P, const int32_t* obj_ids, const double* pr
     }
     pose_errors_kernel<<<dim3(kChunks, np), kThreads, 0, st>>>(a);
   }
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// VSD (bop_toolkit_lib/pose_error.py:17-96 as called from utils/evaluator.py:279-286)
+//   1. depth images of the model in the estimated and the ground-truth pose.  The reference renders them with OpenGL
+//      (renderer_vispy.py); here a z-buffer rasteriser with the reference's conventions: sample of pixel (r, c) at image
+//      coordinates (c + 0.5, r + 0.5) (projection matrix of renderer_vispy.py:186-231), no culling, nearest surface,
+//      eye-space depth at the sample, float32, 0 = background.  float64 edge functions in a fixed operation order
+//      (explicit _rn intrinsics, no FMA) so coverage is bit-identical with oracle/vsd_oracle.py.  The rendering step has no
+//      reference output to compare with (OpenGL is not available offline): parity of this step is unpinned.
+//   2. distance images (misc.py:137-163), visibility masks 'bop19' (visibility.py:9-75, float32 difference), step cost per
+//      tau, (#cost + #complement) / #union.  Integer counts: identical to the reference arithmetic given the depth images.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTaus = 16;
+
+struct VsdObj {
+  const double* pts;
+  const int32_t* faces;
+  int n, f;
+};
+
+struct VsdArgs {
+  const double* pred;     // [P][16] metres
+  const double* gt;
+  const double* cams;     // [P][9]
+  double* proj;           // [P][2][maxv][3]  (u, v, z)
+  unsigned* zbuf;         // [P][2][H][W] float bits, 0xffffffff = empty
+  unsigned long long* counts;  // [P][kMaxTaus + 2]: cost counts per tau, complement, union
+  const void* depth_test; // [P][H][W] int32 or float32 (mm)
+  int depth_is_f32;
+  int H, W, maxv, n_tau, p0;
+  float delta;
+  double taus[kMaxTaus];
+  double* out;            // [P][n_tau]
+  VsdObj obj[kPosesPerLaunch];
+  double diam[kPosesPerLaunch];
+};
+
+__global__ void __launch_bounds__(256) vsd_project_kernel(const __grid_constant__ VsdArgs a) {
+  const int lp = blockIdx.z, p = a.p0 + lp, which = blockIdx.y;
+  const VsdObj o = a.obj[lp];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= o.n) return;
+  const double* T = (which == 0 ? a.pred : a.gt) + 16 * (size_t)p;
+  const double* K = a.cams + 9 * (size_t)p;
+  // evaluator.py:258-261 + renderer_vispy.py:520-521: pose rounded to half, translation to half millimetres, held in float32
+  double R[9], t[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[3 * r + c] = (double)h2f(T[4 * r + c]);
+    t[r] = (double)rh(__fmul_rn(h2f(T[4 * r + 3]), 1000.f));
+  }
+  const double* x = o.pts + 3 * (size_t)i;
+  double cam[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    cam[j] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3 * j], x[0]), __dmul_rn(R[3 * j + 1], x[1])), __dmul_rn(R[3 * j + 2], x[2])), t[j]);
+  double* q = a.proj + (((size_t)p * 2 + which) * a.maxv + i) * 3;
+  q[0] = __dadd_rn(__ddiv_rn(__dmul_rn(K[0], cam[0]), cam[2]), K[2]);
+  q[1] = __dadd_rn(__ddiv_rn(__dmul_rn(K[4], cam[1]), cam[2]), K[5]);
+  q[2] = cam[2];
+}
+
+__global__ void __launch_bounds__(128) vsd_raster_kernel(const __grid_constant__ VsdArgs a) {
+  const int lp = blockIdx.z, p = a.p0 + lp, which = blockIdx.y;
+  const VsdObj o = a.obj[lp];
+  const int f = blockIdx.x * 128 + threadIdx.x;
+  if (f >= o.f) return;
+  const double* pr = a.proj + ((size_t)p * 2 + which) * a.maxv * 3;
+  const int ia = o.faces[3 * f], ib = o.faces[3 * f + 1], ic = o.faces[3 * f + 2];
+  const double ua = pr[3 * ia], va = pr[3 * ia + 1], za = pr[3 * ia + 2];
+  const double ub = pr[3 * ib], vb = pr[3 * ib + 1], zb = pr[3 * ib + 2];
+  const double uc = pr[3 * ic], vc = pr[3 * ic + 1], zc = pr[3 * ic + 2];
+  if (!(za > 0 && zb > 0 && zc > 0)) return;
+  const int c0 = max(0, (int)ceil(fmin(fmin(ua, ub), uc) - 0.5)), c1 = min(a.W - 1, (int)floor(fmax(fmax(ua, ub), uc) - 0.5));
+  const int r0 = max(0, (int)ceil(fmin(fmin(va, vb), vc) - 0.5)), r1 = min(a.H - 1, (int)floor(fmax(fmax(va, vb), vc) - 0.5));
+  unsigned* zb_img = a.zbuf + ((size_t)p * 2 + which) * a.H * a.W;
+  for (int r = r0; r <= r1; ++r) {
+    const double py = (double)r + 0.5;
+    for (int c = c0; c <= c1; ++c) {
+      const double px = (double)c + 0.5;
+      const double w0 = __dsub_rn(__dmul_rn(__dsub_rn(ub, px), __dsub_rn(vc, py)), __dmul_rn(__dsub_rn(uc, px), __dsub_rn(vb, py)));
+      const double w1 = __dsub_rn(__dmul_rn(__dsub_rn(uc, px), __dsub_rn(va, py)), __dmul_rn(__dsub_rn(ua, px), __dsub_rn(vc, py)));
+      const double w2 = __dsub_rn(__dmul_rn(__dsub_rn(ua, px), __dsub_rn(vb, py)), __dmul_rn(__dsub_rn(ub, px), __dsub_rn(va, py)));
+      const bool inside = (w0 >= 0 && w1 >= 0 && w2 >= 0) || (w0 <= 0 && w1 <= 0 && w2 <= 0);
+      const double s = __dadd_rn(__dadd_rn(w0, w1), w2);
+      if (!inside || s == 0) continue;
+      const double invz = __ddiv_rn(__dadd_rn(__dadd_rn(__ddiv_rn(w0, za), __ddiv_rn(w1, zb)), __ddiv_rn(w2, zc)), s);
+      const float d = (float)__ddiv_rn(1.0, invz);
+      if (d == d) atomicMin(zb_img + (size_t)r * a.W + c, __float_as_uint(d));   // positive floats order like their bit patterns
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) vsd_reduce_kernel(const __grid_constant__ VsdArgs a) {
+  __shared__ unsigned long long sh[kMaxTaus + 2];
+  const int lp = blockIdx.y, p = a.p0 + lp;
+  if (threadIdx.x < kMaxTaus + 2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const double* K = a.cams + 9 * (size_t)p;
+  const unsigned* z_est = a.zbuf + ((size_t)p * 2) * a.H * a.W;
+  const unsigned* z_gt = z_est + (size_t)a.H * a.W;
+  const double diam = a.diam[lp];
+  unsigned cost[kMaxTaus];
+#pragma unroll
+  for (int k = 0; k < kMaxTaus; ++k) cost[k] = 0;
+  unsigned n_union = 0, n_comp = 0;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < a.H * a.W; e += gridDim.x * 256) {
+    const int r = e / a.W, c = e - r * a.W;
+    const double pre_x = __ddiv_rn(__dsub_rn((double)c, K[2]), K[0]), pre_y = __ddiv_rn(__dsub_rn((double)r, K[5]), K[4]);
+    auto dist = [&](double d) {
+      const double x = __dmul_rn(pre_x, d), y = __dmul_rn(pre_y, d);
+      return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(d, d)));
+    };
+    const size_t o = (size_t)p * a.H * a.W + e;
+    const double dt = a.depth_is_f32 ? (double)reinterpret_cast<const float*>(a.depth_test)[o] : (double)reinterpret_cast<const int32_t*>(a.depth_test)[o];
+    const unsigned be = z_est[e], bg = z_gt[e];
+    const double d_test = dist(dt), d_est = dist(be == 0xffffffffu ? 0.0 : (double)__uint_as_float(be)),
+                 d_gt = dist(bg == 0xffffffffu ? 0.0 : (double)__uint_as_float(bg));
+    const bool v_gt = (__fsub_rn((float)d_gt, (float)d_test) <= a.delta || d_test == 0) && d_gt > 0;
+    const bool v_est = ((__fsub_rn((float)d_est, (float)d_test) <= a.delta || d_test == 0) && d_est > 0) || (v_gt && d_est > 0);
+    if (v_gt || v_est) ++n_union;
+    if (v_gt && v_est) {
+      const double dd = __ddiv_rn(fabs(__dsub_rn(d_gt, d_est)), diam);
+#pragma unroll
+      for (int k = 0; k < kMaxTaus; ++k)
+        if (k < a.n_tau && dd >= a.taus[k]) ++cost[k];
+    } else if (v_gt || v_est) {
+      ++n_comp;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxTaus; ++k)
+    if (k < a.n_tau && cost[k]) atomicAdd(&sh[k], (unsigned long long)cost[k]);
+  if (n_comp) atomicAdd(&sh[kMaxTaus], (unsigned long long)n_comp);
+  if (n_union) atomicAdd(&sh[kMaxTaus + 1], (unsigned long long)n_union);
+  __syncthreads();
+  if (threadIdx.x < kMaxTaus + 2 && sh[threadIdx.x]) atomicAdd(a.counts + (size_t)p * (kMaxTaus + 2) + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void vsd_finish_kernel(const unsigned long long* counts, int P, int n_tau, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * n_tau) return;
+  const int p = i / n_tau, k = i - p * n_tau;
+  const unsigned long long* c = counts + (size_t)p * (kMaxTaus + 2);
+  out[i] = c[kMaxTaus + 1] == 0 ? 1.0 : (double)(c[k] + c[kMaxTaus]) / (double)c[kMaxTaus + 1];
+}
+
+int set_object_mesh(oryon_handle* h, int obj_id, const int32_t* faces, int n_faces) {
+  ORYON_REQUIRE(h && faces && n_faces > 0, "oryon_eval_set_object_mesh: bad argument");
+  ORYON_CUDA_CHECK(cudaSetDevice(h->device));
+  State* s = state(h);
+  auto it = s->objects.find(obj_id);
+  ORYON_REQUIRE(it != s->objects.end(), "oryon_eval_set_object_mesh: object %d has no points yet (oryon_eval_set_object)", obj_id);
+  for (int i = 0; i < 3 * n_faces; ++i)
+    ORYON_REQUIRE(faces[i] >= 0 && faces[i] < it->second.n, "oryon_eval_set_object_mesh: face index %d out of range", faces[i]);
+  if (it->second.faces) cudaFree(it->second.faces);
+  it->second.faces = nullptr;
+  ORYON_CUDA_CHECK(cudaMalloc(&it->second.faces, sizeof(int32_t) * 3 * (size_t)n_faces));
+  ORYON_CUDA_CHECK(cudaMemcpy(it->second.faces, faces, sizeof(int32_t) * 3 * (size_t)n_faces, cudaMemcpyHostToDevice));
+  it->second.f = n_faces;
+  return ORYON_OK;
+}
+
+int vsd(oryon_handle* h, int P, const int32_t* obj_ids, const double* pred, const double* gt, const double* cams, const void* depth_test,
+        int depth_is_f32, int H, int W, double delta, const double* taus, int n_tau, const double* diameters, double* out,
+        cudaStream_t st) {
+  ORYON_REQUIRE(h && obj_ids && pred && gt && cams && depth_test && taus && diameters && out, "oryon_eval_vsd: null argument");
+  ORYON_REQUIRE(P > 0 && H > 0 && W > 0 && n_tau > 0 && n_tau <= kMaxTaus, "oryon_eval_vsd: bad sizes (n_tau <= %d)", kMaxTaus);
+  ORYON_CUDA_CHECK(cudaSetDevice(h->device));
+  State* s = state(h);
+  int maxv = 0, maxf = 0;
+  for (int p = 0; p < P; ++p) {
+    auto it = s->objects.find(obj_ids[p]);
+    ORYON_REQUIRE(it != s->objects.end() && it->second.faces, "oryon_eval_vsd: object %d has no mesh (oryon_eval_set_object_mesh)", obj_ids[p]);
+    maxv = std::max(maxv, it->second.n), maxf = std::max(maxf, it->second.f);
+  }
+  const size_t proj_bytes = sizeof(double) * 3 * (size_t)maxv * 2 * P;
+  const size_t z_bytes = sizeof(unsigned) * (size_t)H * W * 2 * P;
+  const size_t cnt_bytes = sizeof(unsigned long long) * (kMaxTaus + 2) * (size_t)P;
+  if (int rc = s->vsd_ws.reserve(proj_bytes + z_bytes + cnt_bytes, st)) return rc;
+  VsdArgs a;
+  a.pred = pred, a.gt = gt, a.cams = cams;
+  a.proj = s->vsd_ws.as<double>();
+  a.zbuf = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s->vsd_ws.ptr) + proj_bytes);
+  a.counts = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(s->vsd_ws.ptr) + proj_bytes + z_bytes);
+  a.depth_test = depth_test, a.depth_is_f32 = depth_is_f32;
+  a.H = H, a.W = W, a.maxv = maxv, a.n_tau = n_tau, a.delta = (float)delta, a.out = out;
+  for (int k = 0; k < kMaxTaus; ++k) a.taus[k] = k < n_tau ? taus[k] : 0.0;
+  ORYON_CUDA_CHECK(cudaMemsetAsync(a.zbuf, 0xff, z_bytes, st));
+  ORYON_CUDA_CHECK(cudaMemsetAsync(a.counts, 0, cnt_bytes, st));
+  for (int p0 = 0; p0 < P; p0 += kPosesPerLaunch) {
+    const int np = std::min(kPosesPerLaunch, P - p0);
+    a.p0 = p0;
+    for (int i = 0; i < np; ++i) {
+      const Object& o = s->objects[obj_ids[p0 + i]];
+      a.obj[i] = VsdObj{o.pts, o.faces, o.n, o.f};
+      a.diam[i] = diameters[p0 + i];
+    }
+    vsd_project_kernel<<<dim3((maxv + 255) / 256, 2, np), 256, 0, st>>>(a);
+    vsd_raster_kernel<<<dim3((maxf + 127) / 128, 2, np), 128, 0, st>>>(a);
+    vsd_reduce_kernel<<<dim3(64, np), 256, 0, st>>>(a);
+  }
+  vsd_finish_kernel<<<(P * n_tau + 127) / 128, 128, 0, st>>>(a.counts, P, n_tau, out);
   ORYON_CUDA_CHECK(cudaGetLastError());
   return ORYON_OK;
 }

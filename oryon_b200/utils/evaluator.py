@@ -4,8 +4,10 @@ scripts/evaluation/compute_metrics.py:14-49 (the CSV wire format ``FPM_Pipeline.
 
 The pose-error arithmetic of ``register_eval`` (utils/evaluator.py:206-288: R/T error, ADD or ADD-S, MSSD, MSPD) runs in
 liboryon_b200.so (``oryon_eval_pose_errors``, csrc/eval.cu) for a whole batch of pairs at once; what stays here is the
-bookkeeping (lists, thresholds, means).  VSD / AR need the reference's OpenGL depth renderer
-(bop_toolkit_lib/renderer_vispy.py): ``compute_vsd=True`` raises until a rasteriser is part of the library.
+bookkeeping (lists, thresholds, means).  With ``compute_vsd=True`` the VSD errors (bop_toolkit_lib/pose_error.py:17-96) come
+from ``oryon_eval_vsd``: a CUDA z-buffer rasteriser in place of the reference's OpenGL renderer
+(bop_toolkit_lib/renderer_vispy.py) followed by the reference's visibility / cost arithmetic; object models then need
+``faces``.  AR = (MSSD + MSPD + VSD) / 3 as in utils/evaluator.py:286.
 """
 from __future__ import annotations
 
@@ -75,6 +77,32 @@ class CudaPoseErrors:
         _lib.check(_lib.load().oryon_eval_set_object(_lib.handle(self.device.index), oid, pts.ctypes.data_as(dbl), pts.shape[0],
                                                      sym.ctypes.data_as(dbl), sym.shape[0]))
 
+    def add_mesh(self, key, faces: np.ndarray) -> None:
+        from .. import _lib
+        f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32).reshape(-1, 3))
+        _lib.check(_lib.load().oryon_eval_set_object_mesh(_lib.handle(self.device.index), self._ids[key],
+                                                          f.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), f.shape[0]))
+
+    def vsd(self, cls_ids: Sequence, pred: np.ndarray, gt: np.ndarray, cams: np.ndarray, depths: Sequence, diameters: Sequence[float],
+            delta: float, taus: Sequence[float]) -> np.ndarray:
+        """``[P, len(taus)]`` VSD errors; ``depths``: P test depth images ``[H,W]`` in mm (integer or float, 0 = missing)."""
+        from .. import _lib
+        from .._torch_glue import ptr, stream_ptr
+        P, dev = len(cls_ids), self.device
+        ids = (ctypes.c_int32 * P)(*[self._ids[c] for c in cls_ids])
+        d = np.stack([np.asarray(x).squeeze() for x in depths])
+        is_f32 = not np.issubdtype(d.dtype, np.integer)
+        td = torch.as_tensor(np.ascontiguousarray(d, dtype=np.float32 if is_f32 else np.int32)).to(dev)
+        tp = torch.as_tensor(np.ascontiguousarray(pred, dtype=np.float64).reshape(P, 16)).to(dev)
+        tg = torch.as_tensor(np.ascontiguousarray(gt, dtype=np.float64).reshape(P, 16)).to(dev)
+        tk = torch.as_tensor(np.ascontiguousarray(cams, dtype=np.float64).reshape(P, 9)).to(dev)
+        out = torch.empty(P, len(taus), dtype=torch.float64, device=dev)
+        c_taus = (ctypes.c_double * len(taus))(*[float(t) for t in taus])
+        c_diam = (ctypes.c_double * P)(*[float(x) for x in diameters])
+        _lib.check(_lib.load().oryon_eval_vsd(_lib.handle(dev.index), P, ids, ptr(tp), ptr(tg), ptr(tk), ptr(td), int(is_f32), d.shape[1],
+                                              d.shape[2], float(delta), c_taus, len(taus), c_diam, ptr(out), stream_ptr(dev)))
+        return out.cpu().numpy()
+
     def __call__(self, cls_ids: Sequence, pred: np.ndarray, gt: np.ndarray, cams: np.ndarray) -> np.ndarray:
         from .. import _lib
         from .._torch_glue import ptr, stream_ptr
@@ -94,13 +122,14 @@ class Evaluator(object):
 
     def __init__(self, exp_tag: str, compute_vsd: bool = True, compute_iou: bool = True, *, pose_errors: Optional[Callable] = None,
                  device=None):
-        if compute_vsd:
-            raise NotImplementedError("VSD / AR need a depth renderer (reference bop_toolkit_lib/renderer_vispy.py); "
-                                      "construct with compute_vsd=False")
         self.exp_tag = exp_tag
         self.mssd_rec = np.arange(0.05, 0.51, 0.05)
         self.mspd_rec = np.arange(5, 51, 5)
         self.compute_vsd, self.compute_iou = compute_vsd, compute_iou
+        if self.compute_vsd:   # utils/evaluator.py:96-101
+            self.vsd_taus = list(np.arange(0.05, 0.51, 0.05))
+            self.vsd_rec = np.arange(0.05, 0.51, 0.05)
+            self.vsd_delta = 15.
         self.pose_recall_th = POSE_RECALL_TH
         self.metrics: Dict[str, list] = {}
         self.counts: Dict[str, list] = {}
@@ -118,6 +147,10 @@ class Evaluator(object):
         if hasattr(self._pose_errors, "add_object"):
             for k, m in obj_models.items():
                 self._pose_errors.add_object(k, m["pts"], self.obj_symms[k])
+                if self.compute_vsd:
+                    if "faces" not in m:
+                        raise ValueError(f"compute_vsd=True needs a triangle mesh: object {k} has no 'faces'")
+                    self._pose_errors.add_mesh(k, m["faces"])
 
     def get_obj_info(self, obj_id):
         return self.obj_models[obj_id], self.obj_diams[obj_id], self.obj_symms[obj_id]
@@ -134,7 +167,7 @@ class Evaluator(object):
 
     def init_validation(self):
         self.init_training()
-        for k in ("R error", "T error", "ADD(S)-0.1d", "MSSD", "MSPD"):
+        for k in ("R error", "T error", "ADD(S)-0.1d") + (("AR", "VSD") if self.compute_vsd else ()) + ("MSSD", "MSPD"):
             self.metrics[k] = []
         for k in ("Missing segm", "Failed pose", "Zero pose"):
             self.counts[k] = []
@@ -187,10 +220,20 @@ class Evaluator(object):
         for r_th, t_th in self.pose_recall_th:
             ok = np.logical_and(err_R <= r_th, err_T <= t_th).astype(float)
             self.metrics[f"Recall ({r_th}deg, {t_th}cm)"].extend(ok.tolist())
+        vsd_errs = None
+        if self.compute_vsd:
+            vsd_errs = self._pose_errors.vsd(list(results["cls_id"]), pred_poses, gt_poses, cams, results["depth"],
+                                             [self.obj_diams[c] for c in results["cls_id"]], self.vsd_delta, self.vsd_taus)
         for i, cls_id in enumerate(results["cls_id"]):
             self.metrics["ADD(S)-0.1d"].append(float(err[i, 2] <= self.add_diams[cls_id] * 0.1))
-            self.metrics["MSSD"].append((err[i, 4] < self.mssd_rec * self.obj_diams[cls_id]).mean())
-            self.metrics["MSPD"].append((err[i, 5] < self.mspd_rec).mean())
+            mean_mssd = (err[i, 4] < self.mssd_rec * self.obj_diams[cls_id]).mean()
+            mean_mspd = (err[i, 5] < self.mspd_rec).mean()
+            self.metrics["MSSD"].append(mean_mssd)
+            self.metrics["MSPD"].append(mean_mspd)
+            if self.compute_vsd:   # utils/evaluator.py:279-286: every (tau, recall threshold) pair counts
+                mean_vsd = np.stack([vsd_errs[i] < rec_i for rec_i in self.vsd_rec], axis=1).mean()
+                self.metrics["VSD"].append(mean_vsd)
+                self.metrics["AR"].append((mean_mssd + mean_mspd + mean_vsd) / 3.)
 
     def register_test(self, results: dict, clear: bool = False):
         self.register_eval(results, clear)
@@ -198,7 +241,7 @@ class Evaluator(object):
         self.metrics["instance_id"].extend(results["instance_id"])
 
     def register_valid_failure(self, results):
-        for k in ("R error", "T error", "ADD(S)-0.1d", "MSSD", "MSPD"):
+        for k in ("R error", "T error", "ADD(S)-0.1d") + (("VSD", "AR") if self.compute_vsd else ()) + ("MSSD", "MSPD"):
             self.metrics[k].append(0.)
         if self.compute_iou:
             self.metrics["Anchor IoU"].extend(self._np(results["iou_a"]).tolist())
@@ -235,7 +278,8 @@ class Evaluator(object):
                 if name not in ["cls_id", "instance_id"] and len(value) > 0}
 
     def _row(self, tag, means) -> str:
-        s = f"{tag} & - & - & {means['MSSD']*100:.1f} & {means['MSPD']*100:.1f} & {means['ADD(S)-0.1d']*100:.1f} &"
+        head = f"{means['AR']*100:.1f} & {means['VSD']*100:.1f}" if self.compute_vsd else "- & -"
+        s = f"{tag} & {head} & {means['MSSD']*100:.1f} & {means['MSPD']*100:.1f} & {means['ADD(S)-0.1d']*100:.1f} &"
         return s + (f" {means['Mean IoU']*100:.1f} \\\\" if self.compute_iou else " - \\\\")
 
     def test_summary(self):

@@ -97,31 +97,64 @@ def test_evaluator_bookkeeping_matches_reference(data, batched):
     assert ev.get_latex_str() == gold["latex"]
 
 
-def test_vsd_is_loud():
-    with pytest.raises(NotImplementedError):
-        Evaluator("x", compute_vsd=True)
+class _OracleBackend:
+    """Error backend for CPU tests: the oracles in place of the CUDA library."""
+
+    def __init__(self, models, syms):
+        self.models, self.syms = models, syms
+
+    def __call__(self, cls_ids, pred, gt, cams):
+        return eval_oracle.pose_errors(self.models, self.syms, cls_ids, pred, gt, cams)
+
+    def vsd(self, cls_ids, pred, gt, cams, depths, diameters, delta, taus):
+        import vsd_oracle
+        out = np.zeros((len(cls_ids), len(taus)))
+        for i, cid in enumerate(cls_ids):
+            m, K = self.models[cid], np.asarray(cams[i]).reshape(3, 3)
+            H, W = np.asarray(depths[i]).shape
+
+            def render(T):
+                p16 = np.asarray(T).astype(np.float16)
+                R, t = p16[:3, :3].astype(np.float32), (p16[:3, 3] * np.float16(1000)).astype(np.float16).astype(np.float32)
+                return vsd_oracle.rasterize_depth(m["pts"], m["faces"], R, t, K[0, 0], K[1, 1], K[0, 2], K[1, 2], H, W)
+
+            out[i] = vsd_oracle.vsd_errors(render(pred[i]), render(gt[i]), np.asarray(depths[i]), K, delta, taus, diameters[i])
+        return out
 
 
-def test_prediction_csv_round_trip(tmp_path):
-    from oryon_b200.pipeline import FPM_Pipeline
-    pipe = FPM_Pipeline.__new__(FPM_Pipeline)
-    path = tmp_path / "pred.csv"
-    pipe.pred_file = open(path, "w")
-    rng = np.random.RandomState(0)
-    poses = [np.vstack([rng.randn(3, 4).astype(np.float32), [[0, 0, 0, 1]]]) for _ in range(3)]
-    for i, p in enumerate(poses):
-        pipe.add_pred_pose(f"scene{i} {10 + i} mug", f"scene{i} {20 + i} mug", np.float32(0.5 + 0.1 * i), np.float32(0.25), p)
-    pipe.pred_file.close()
-    preds, ia, iq, present = dict_from_preds(str(path))
-    assert present and len(preds) == 3
-    for i, p in enumerate(poses):
-        key = f"scene{i}_{10 + i}_scene{i}_{20 + i}_mug"
-        np.testing.assert_array_equal(preds[key].astype(np.float32), p[:3].astype(np.float32))   # str(float32) round-trips
-        assert np.float32(ia[key]) == np.float32(0.5 + 0.1 * i) and iq[key] == 0.25      # shortest repr of a float32 round-trips
-    three = tmp_path / "three.csv"
-    three.write_text("s 1 mug,s 2 mug," + " ".join(["1.0"] * 12) + "\n")
-    assert dict_from_preds(str(three))[3] is False
-    bad = tmp_path / "bad.csv"
-    bad.write_text("a,b\n")
-    with pytest.raises(RuntimeError):
-        dict_from_preds(str(bad))
+def _vsd_inputs():
+    import vsd_oracle
+    obj, cs = synth.eval_mesh_objects(0), synth.eval_cases(1, n=9)
+    K = cs["camera"].numpy()
+    depths = [synth.eval_scene_depth(obj["models"], cs["cls_id"][i], cs["gt_pose"][i].numpy(), K, i, render=vsd_oracle.rasterize_depth)
+              for i in range(9)]
+    g = np.load(os.path.join(GOLDEN, "vsd_0.npz"))
+    assert list(g["depth_sum"]) == [synth.tensor_checksum(torch.from_numpy(d)) for d in depths], "synthetic scenes drifted"
+    return obj, cs, K, depths, g["errs"], json.load(open(os.path.join(GOLDEN, "vsd_0.json")))
+
+
+def test_vsd_oracle_and_evaluator_match_reference():
+    """VSD errors of the oracle == the reference's vsd() on the same rendered depth images (tests/golden/vsd_0.npz), and the
+    Evaluator mirror with compute_vsd=True reproduces the reference Evaluator's VSD / AR / LaTeX row (vsd_0.json)."""
+    obj, cs, K, depths, errs, gold = _vsd_inputs()
+    syms = {k: format_sym_set(s) for k, s in obj["syms"].items()}
+    be = _OracleBackend(obj["models"], syms)
+    ev = Evaluator("synthetic", compute_vsd=True, compute_iou=True, pose_errors=be)
+    ev.add_object_info(obj["models"], obj["diams"], obj["syms"])
+    ev.init_test()
+    idx = list(range(9))
+    sl = torch.tensor(idx)
+    ev.register_test({"iou_a": cs["iou_a"][sl], "iou_q": cs["iou_q"][sl], "gt_pose": cs["gt_pose"][sl], "pred_pose": cs["pred_pose"][sl],
+                      "pred_pose_rel": cs["pred_pose_rel"][sl], "cls_id": list(cs["cls_id"]), "camera": [K] * 9, "depth": depths,
+                      "instance_id": list(cs["instance_id"])})
+    pred = cs["pred_pose"].numpy().astype(np.float64)
+    for i in range(9):
+        if np.count_nonzero(cs["pred_pose_rel"][i].numpy()) <= 1:
+            pred[i] = np.eye(4)
+    got = be.vsd(cs["cls_id"], pred, cs["gt_pose"].numpy(), np.stack([K] * 9), depths, [obj["diams"][c] for c in cs["cls_id"]], 15.,
+                 list(np.arange(0.05, 0.51, 0.05)))
+    np.testing.assert_array_equal(got, errs)                       # integer pixel counts: exact
+    for k in ("VSD", "AR", "MSSD", "MSPD", "ADD(S)-0.1d"):
+        assert [float(x) for x in ev.metrics[k]] == gold["metrics"][k], k
+    assert list(ev.metrics.keys()) == list(gold["metrics"].keys())   # same key order -> same JSON from save()
+    assert ev.get_latex_str() == gold["latex"]

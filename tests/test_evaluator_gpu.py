@@ -120,3 +120,60 @@ def test_evaluator_mirror_on_cuda_matches_reference_state():
             assert [float(x) for x in ev.metrics[k]] == v, k          # every thresholded metric identical
     assert {k: [int(x) for x in v] for k, v in ev.counts.items()} == gold["counts"]
     assert ev.get_latex_str() == gold["latex"]
+
+
+def _vsd_inputs():
+    import vsd_oracle
+    obj, cs = synth.eval_mesh_objects(0), synth.eval_cases(1, n=9)
+    K = cs["camera"].numpy()
+    depths = [synth.eval_scene_depth(obj["models"], cs["cls_id"][i], cs["gt_pose"][i].numpy(), K, i, render=vsd_oracle.rasterize_depth)
+              for i in range(9)]
+    g = np.load(os.path.join(GOLDEN, "vsd_0.npz"))
+    assert list(g["depth_sum"]) == [synth.tensor_checksum(torch.from_numpy(d)) for d in depths], "synthetic scenes drifted"
+    return obj, cs, K, depths, g["errs"], json.load(open(os.path.join(GOLDEN, "vsd_0.json")))
+
+
+def test_vsd_matches_reference_arithmetic():
+    """oryon_eval_vsd (CUDA rasteriser + visibility / cost reduction) == the reference's vsd() run on the oracle rasteriser's
+    depth images (tests/golden/vsd_0.npz): the counts are integers, so the errors must be identical, which also shows the two
+    rasterisers agree pixel for pixel on these scenes."""
+    need_gpu()
+    obj, cs, K, depths, errs, _ = _vsd_inputs()
+    syms = {k: format_sym_set(s) for k, s in obj["syms"].items()}
+    be = CudaPoseErrors("cuda:0")
+    for k, m in obj["models"].items():
+        be.add_object(k, m["pts"], syms[k])
+        be.add_mesh(k, m["faces"])
+    pred = cs["pred_pose"].numpy().astype(np.float64)
+    for i in range(9):
+        if np.count_nonzero(cs["pred_pose_rel"][i].numpy()) <= 1:
+            pred[i] = np.eye(4)
+    taus = list(np.arange(0.05, 0.51, 0.05))
+    got = be.vsd(cs["cls_id"], pred, cs["gt_pose"].numpy(), np.stack([K] * 9), depths, [obj["diams"][c] for c in cs["cls_id"]], 15., taus)
+    np.testing.assert_array_equal(got, errs)
+    got_f = be.vsd(cs["cls_id"], pred, cs["gt_pose"].numpy(), np.stack([K] * 9), [d.astype(np.float32) for d in depths],
+                   [obj["diams"][c] for c in cs["cls_id"]], 15., taus)
+    np.testing.assert_array_equal(got_f, errs)                      # float32 test depth, same values
+    with pytest.raises(Exception):                                   # an object without a mesh cannot be rendered
+        be2 = CudaPoseErrors("cuda:0")
+        be2.add_object("nomesh", obj["models"][1]["pts"], syms[1])
+        be2.vsd(["nomesh"], pred[:1], cs["gt_pose"].numpy()[:1], K[None], depths[:1], [100.0], 15., taus)
+
+
+def test_evaluator_with_vsd_on_cuda_matches_reference_state():
+    need_gpu()
+    obj, cs, K, depths, _, gold = _vsd_inputs()
+    ev = Evaluator("synthetic", compute_vsd=True, compute_iou=True, device="cuda:0")
+    ev.add_object_info(obj["models"], obj["diams"], obj["syms"])
+    ev.init_test()
+    for lo, hi in ((0, 4), (4, 9)):                                  # two batches
+        sl = torch.arange(lo, hi)
+        ev.register_test({"iou_a": cs["iou_a"][sl], "iou_q": cs["iou_q"][sl], "gt_pose": cs["gt_pose"][sl], "pred_pose": cs["pred_pose"][sl],
+                          "pred_pose_rel": cs["pred_pose_rel"][sl], "cls_id": cs["cls_id"][lo:hi], "camera": [K] * (hi - lo),
+                          "depth": depths[lo:hi], "instance_id": cs["instance_id"][lo:hi]})
+    for k in ("VSD", "AR", "MSSD", "MSPD", "ADD(S)-0.1d"):
+        assert [float(x) for x in ev.metrics[k]] == gold["metrics"][k], k
+    assert ev.get_latex_str() == gold["latex"]
+    with pytest.raises(ValueError):
+        bad = Evaluator("x", compute_vsd=True, device="cuda:0")
+        bad.add_object_info(synth.eval_objects(0)["models"], synth.eval_objects(0)["diams"], synth.eval_objects(0)["syms"])
