@@ -440,7 +440,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int cnt = 0;
       for (int j = j0; j < j1; ++j) {
         const uint32_t buf = tile_iter & 1;
-        if ((int)buf != set) {   // the other set's tile
+        if (kEpiSets > 1 && (int)buf != set) {   // the other set's tile
           ++tile_iter;
           continue;
         }
