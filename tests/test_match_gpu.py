@@ -195,3 +195,24 @@ def test_config2_full_size_recovers_planted_permutation():
     d = 0.5 * (1 - (a * q).sum(1))
     assert float((d - dist).abs().max()) <= 2e-6
     assert pcd.match_last_stats()["rows_overflowed"] == 0
+
+
+def test_config5_full_size_properties():
+    """BASELINE config 5 (D=256, 240x320 -> 76 800 positions per image; 2 pairs = 6 TFLOP) through size-independent
+    properties: the planted permutation is recovered, the reported distance equals a float32 re-evaluation of the reported
+    neighbour, and matching a map against itself is the identity at distance ~0 (idempotence)."""
+    need_gpu()
+    B, D, h, w = 2, 256, 240, 320
+    fa, fq, perm = synth.permuted_feature_batch(5, B, D, h, w, noise=0.1, device="cuda")
+    idx, dist = pcd.match_nn(fa, fq)
+    torch.cuda.synchronize()
+    assert torch.equal(idx.long(), perm)
+    a = torch.nn.functional.normalize(fa.view(B, D, -1), dim=1)
+    q = torch.nn.functional.normalize(torch.gather(fq.view(B, D, -1), 2, perm[:, None, :].expand(B, D, -1)), dim=1)
+    assert float((0.5 * (1 - (a * q).sum(1)) - dist).abs().max()) <= 2e-6
+    del a, q, fq
+    idx2, dist2 = pcd.match_nn(fa, fa)
+    torch.cuda.synchronize()
+    n = h * w
+    assert torch.equal(idx2.long(), torch.arange(n, device="cuda")[None].expand(B, n))
+    assert float(dist2.abs().max()) <= 2e-6
