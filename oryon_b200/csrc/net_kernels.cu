@@ -2,6 +2,8 @@
 // along the channel / column index, one warp per row for the normalisations, grids sized by the data.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "net_kernels.cuh"
 
 namespace oryon {
@@ -370,9 +372,140 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// window attention (Swin: S = 49 or 144 tokens per window, d = 32): one CTA per (window, head), one query per lane
+// ------------------------------------------------------------------------------------------------
+// The generic kernel above spends its time in block-wide barriers: a 49-token window gives a 256-thread CTA a few hundred
+// FMAs between __syncthreads.  Here the ceil(S / 32) warps of a CTA stage K and V of their (window, head) in shared memory
+// once (coalesced 128-byte rows, one barrier), then every lane owns one query: q[32] and the output accumulator stay in
+// registers, the key loop reads k_j / v_j as shared-memory broadcasts (no bank conflicts, no further barriers).  First sweep:
+// score + bias + mask -> row maximum; second sweep: exp / sum / P V.  KEEP = true parks the scores of the first sweep in a
+// per-lane shared-memory row (S <= 64); KEEP = false recomputes the dot product instead (S = 144: the rows would not fit next
+// to K and V at a useful occupancy).  Same max-subtracted softmax as the reference.
+constexpr int kWinD = 32;
+
+template <bool KEEP>
+__global__ void __launch_bounds__(160) window_attention_kernel(AttnArgs a, int s_ld) {
+  extern __shared__ __align__(16) float wsm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int seq = blockIdx.x, hh = blockIdx.y;
+  const int S = a.S;
+  float* Ks = wsm;                  // [S][32]
+  float* Vs = Ks + S * kWinD;       // [S][32]
+  float* Sc = Vs + S * kWinD;       // KEEP: [warps][32 lanes][s_ld]
+  const float* base = a.qkv + (int64_t)seq * S * a.ld;
+  {
+    // K and V ([S][32] each, adjacent in shared memory) as 2 * S * 8 float4: every thread issues all of its loads before the
+    // first store, so the staging costs one memory latency instead of one per row
+    constexpr int kMaxIt = 16;   // 2 * 160 * 8 / 160 threads
+    const int total = 2 * S * 8;
+    float4 tmp[kMaxIt];
+#pragma unroll
+    for (int i = 0; i < kMaxIt; ++i) {
+      const int f = threadIdx.x + i * blockDim.x;
+      if (f < total) {
+        const int which = f >= S * 8, g = f - which * S * 8;
+        tmp[i] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)(g >> 3) * a.ld + (which ? a.off_v : a.off_k) + hh * kWinD) + (g & 7));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxIt; ++i) {
+      const int f = threadIdx.x + i * blockDim.x;
+      if (f < total) reinterpret_cast<float4*>(Ks)[f] = tmp[i];
+    }
+  }
+  __syncthreads();
+  const int qi = w * 32 + lane;
+  const bool ok = qi < S;
+  const int qrow = ok ? qi : 0;
+  const float* bias = a.bias ? a.bias + ((int64_t)hh * S + qrow) * S : nullptr;
+  const float* mask = a.mask ? a.mask + ((int64_t)(seq % a.n_win) * S + qrow) * S : nullptr;
+  float* my = Sc + (size_t)(w * 32 + lane) * s_ld;
+  float q[kWinD];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)qrow * a.ld + hh * kWinD);
+#pragma unroll
+    for (int i = 0; i < kWinD / 4; ++i) {
+      const float4 t = __ldg(qp + i);
+      q[4 * i] = t.x * a.scale, q[4 * i + 1] = t.y * a.scale, q[4 * i + 2] = t.z * a.scale, q[4 * i + 3] = t.w * a.scale;
+    }
+  }
+  auto score = [&](int j) {
+    const float4* kp = reinterpret_cast<const float4*>(Ks + j * kWinD);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWinD / 4; ++i) {
+      const float4 k = kp[i];
+      s0 = fmaf(q[4 * i], k.x, s0), s1 = fmaf(q[4 * i + 1], k.y, s1), s2 = fmaf(q[4 * i + 2], k.z, s2), s3 = fmaf(q[4 * i + 3], k.w, s3);
+    }
+    float sc = (s0 + s1) + (s2 + s3);
+    if (bias) sc += __ldg(bias + j);
+    if (mask) sc += __ldg(mask + j);
+    return sc;
+  };
+  float m = -INFINITY;
+  for (int j = 0; j < S; ++j) {
+    const float sc = score(j);
+    if (KEEP) my[j] = sc;
+    m = fmaxf(m, sc);
+  }
+  float acc[kWinD];
+#pragma unroll
+  for (int i = 0; i < kWinD; ++i) acc[i] = 0.f;
+  float l = 0.f;
+  for (int j = 0; j < S; ++j) {
+    const float p = expf((KEEP ? my[j] : score(j)) - m);
+    l += p;
+    const float4* vp = reinterpret_cast<const float4*>(Vs + j * kWinD);
+#pragma unroll
+    for (int i = 0; i < kWinD / 4; ++i) {
+      const float4 v = vp[i];
+      acc[4 * i] = fmaf(p, v.x, acc[4 * i]), acc[4 * i + 1] = fmaf(p, v.y, acc[4 * i + 1]);
+      acc[4 * i + 2] = fmaf(p, v.z, acc[4 * i + 2]), acc[4 * i + 3] = fmaf(p, v.w, acc[4 * i + 3]);
+    }
+  }
+  if (ok) {
+    const int64_t o = ((int64_t)seq * S + qi) * a.ldh + hh * kWinD;
+#pragma unroll
+    for (int i = 0; i < kWinD / 8; ++i) {   // 8 outputs = 16 bytes of hi, 16 bytes of lo
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_half(__fdiv_rn(acc[8 * i + 2 * e], l), h0, l0);
+        split_half(__fdiv_rn(acc[8 * i + 2 * e + 1], l), h1, l1);
+        const __half2 hp = __halves2half2(h0, h1), lp = __halves2half2(l0, l1);
+        ph[e] = *reinterpret_cast<const uint32_t*>(&hp), pl[e] = *reinterpret_cast<const uint32_t*>(&lp);
+      }
+      *reinterpret_cast<uint4*>(a.out_hi + o + 8 * i) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (a.out_lo) *reinterpret_cast<uint4*>(a.out_lo + o + 8 * i) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+}
+
 int attention(oryon_handle* h, const AttnArgs& a, cudaStream_t st) {
   ORYON_REQUIRE(a.d == 32 || a.d == 64, "attention: head dim %d unsupported", a.d);
   ORYON_REQUIRE(a.S > 0 && a.S <= 1024, "attention: S=%d unsupported", a.S);
+  static const bool generic_only = getenv("ORYON_ATTN_GENERIC") != nullptr;   // A/B switch
+  auto al = [](const void* p, size_t n) { return (reinterpret_cast<uintptr_t>(p) % n) == 0; };
+  if (!generic_only && a.d == kWinD && !a.causal && a.S <= 160 && a.ld % 4 == 0 && a.off_k % 4 == 0 && a.off_v % 4 == 0 && a.ldh % 8 == 0 &&
+      al(a.qkv, 16) && al(a.out_hi, 16) && (!a.out_lo || al(a.out_lo, 16))) {
+    const int warps = (a.S + 31) / 32;                                               // <= 5
+    const bool keep = a.S <= 64;
+    const int s_ld = a.S | 1;                                                        // odd row stride: conflict-free per-lane rows
+    const size_t smem = (size_t)(2 * a.S * kWinD + (keep ? warps * 32 * s_ld : 0)) * sizeof(float);
+    h->span_begin(KID_ATTN, st);
+    if (keep) {
+      ORYON_CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      window_attention_kernel<true><<<dim3(a.n_seq, a.heads), 32 * warps, smem, st>>>(a, s_ld);
+    } else {
+      ORYON_CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      window_attention_kernel<false><<<dim3(a.n_seq, a.heads), 32 * warps, smem, st>>>(a, s_ld);
+    }
+    h->span_end(st);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    return ORYON_OK;
+  }
   const size_t smem = (size_t)(a.d * kQS + kKC * (a.d + 1) + a.S * kQS) * sizeof(float);
   const dim3 grid((a.S + kQT - 1) / kQT, a.heads, a.n_seq);
   h->span_begin(KID_ATTN, st);

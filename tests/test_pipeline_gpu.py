@@ -209,3 +209,46 @@ def test_test_step_feeds_evaluator(system):
         assert ev.metrics["ADD(S)-0.1d"][i] == float(ref[2] <= ev.add_diams[batch["cls_id"][i]] * 0.1)
         assert ev.metrics["MSSD"][i] == (ref[4] < ev.mssd_rec * obj["diams"][batch["cls_id"][i]]).mean()
     assert ev.metrics["R error"][2] == 0.0 and ev.metrics["MSSD"][2] == 0.0
+
+
+def test_decoded_frames_to_metrics_end_to_end(system, tmp_path):
+    """The whole widened path in one piece: decoded uint8 frames -> GpuCollate (N1: staging on the GPU) -> test_step
+    (network, masks, matching, lifting, PointDSC) -> prediction CSV (N3) -> Evaluator on the CUDA backend (N2), and the CSV
+    read back by dict_from_preds carries the poses the evaluator saw."""
+    from oryon_b200.datasets import GpuCollate
+    from oryon_b200.utils.evaluator import Evaluator, dict_from_preds
+    import stage_oracle
+    model, solver, _ = system
+    B = 3
+    frames = synth.raw_frames(11, 2 * B)
+    pairs = [synth.synthetic_rgbd_pair(900 + i) for i in range(B)]
+    K = np.asarray(synth.NOCS_INTRINSICS).reshape(3, 3)
+    tokens = sb.synthetic_tokens(7, 1)
+
+    def item(f, depth, tag, i):
+        return dict(rgb=f["rgb"], mask=f["mask"], depth=depth.numpy(), camera=K, instance_id=f"scene{i} {tag}{i} mug",
+                    metadata=dict(mask_ids=[f["mask_id"]], poses=[np.eye(4)]))
+
+    data = [(item(frames[2 * i], pairs[i]["depth_a"], 1, i), item(frames[2 * i + 1], pairs[i]["depth_q"], 2, i), ["mug"] * 81,
+             np.eye(4), 1 + i % 3, f"pair{i}", True) for i in range(B)]
+    batch = GpuCollate((224, 224), "cuda:0")(data)
+    assert torch.equal(batch["anchor"]["rgb"][1].cpu(), stage_oracle.stage_rgb(frames[2]["rgb"], (224, 224)))
+    batch["prompt_tokens"] = tokens.expand(B, -1, -1).contiguous()
+    obj = synth.eval_objects(0)
+    ev = Evaluator("e2e", compute_vsd=False, compute_iou=True, device="cuda:0")
+    ev.add_object_info(obj["models"], obj["diams"], obj["syms"])
+    ev.init_test()
+    args = dict(ARGS, test=dict(ARGS["test"], mask="oracle"))
+    pipe = FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver, evaluator=ev)
+    csv = tmp_path / "pred.csv"
+    pipe.on_test_start(str(csv))
+    rows = pipe.test_step(batch, 0)
+    pipe.on_test_end()
+    assert len(rows) == B and all(r["status"] in ("ok", "no_corrs", "invalid_mask") for r in rows)
+    assert len(ev.metrics["R error"]) == B and ev.metrics["instance_id"] == [f"pair{i}" for i in range(B)]
+    preds, ia, iq, present = dict_from_preds(str(csv))
+    assert present and len(preds) == B
+    for i, r in enumerate(rows):
+        key = f"scene{i}_1{i}_scene{i}_2{i}_mug"
+        np.testing.assert_array_equal(preds[key].astype(np.float32), r["pred_pose_rel"].numpy()[:3])
+        assert np.float32(ia[key]) == np.float32(r["iou_a"])
