@@ -201,6 +201,30 @@ def full_path_measure(pairs, local, peaks, precision=3):
                      "frac_tensor_pipe": (passes * tf / peak_tf if tf else None)}}
 
 
+def cpu_full_path_sample(threads):
+    """The reference's whole test step for ONE pair on the host cores, through the oracle (backbone_oracle.oryon_forward restates
+    net.py:142-167 -- including the prompt encoding the reference repeats on every step, net.py:147 -- and
+    oryon_oracle.post_network_step restates pipeline.py:311-355).  Same synthetic weights / inputs as `full_path`."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import backbone_oracle as bo
+    import oryon_oracle as oracle
+    from oryon_b200 import synth, synth_backbone as sb
+    torch.set_num_threads(threads)
+    w = sb.oryon_state_dict(11)
+    batch = synth.synthetic_batch(5, 1)
+    swin = bo.guidance_backbone(w)
+    t0 = time.perf_counter()
+    out = bo.oryon_forward(w, batch["anchor"]["rgb"], batch["query"]["rgb"], batch["prompt_tokens"], swin=swin)
+    t1 = time.perf_counter()
+    torch.manual_seed(1)
+    rows = oracle.post_network_step({k: out[k] for k in ("featmap_a", "featmap_q", "mask_a", "mask_q")}, batch, synth.pointdsc_state_dict(300),
+                                    synth.POINTDSC_DEFAULT_CFG, mask_mode="oracle")
+    t2 = time.perf_counter()
+    return {"network_s_per_pair": t1 - t0, "post_network_s_per_pair": t2 - t1, "pairs_per_s": 1.0 / (t2 - t0), "cores": threads,
+            "kind": "port", "status": rows[0]["status"],
+            "sample": "1 pair, one pass, no warm-up; float32 CPU PyTorch; the prompt set is re-encoded as the reference does on every step"}
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference matcher, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -386,6 +410,11 @@ def main():
                     line["full_path_medium_precision"] = full_path_measure(args.full_pairs, local, peaks, precision=1)
             except Exception as e:  # the contract line must still be printed
                 line["full_path"] = {"error": repr(e)}
+        if not args.no_cpu_baseline and world == 1 and isinstance(line.get("full_path"), dict) and "error" not in line["full_path"]:
+            try:
+                line["full_path"]["cpu_oracle"] = cpu_full_path_sample(os.cpu_count() or 1)
+            except Exception as e:
+                line["full_path"]["cpu_oracle"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             cpu_port_sample(32, threads)
