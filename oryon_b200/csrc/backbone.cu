@@ -582,10 +582,27 @@ void swin_block(Ctx& c, float* x, int N, const Stage& S, const SwinBlock& B, boo
   c.ar.off = mark;
 }
 
-// 3x3 / 7x7 convolution as im2col + GEMM; returns fp32 NHWC [n*H*W][cout]
+// 3x3 / 7x7 convolution; returns fp32 NHWC [n*H*W][cout].  Implicit GEMM: the A operand is gathered from the activations by
+// producer warps inside the GEMM kernel (gemm::ConvGather); the im2col matrix (up to 1.5 GB per layer at 192x192) is neither
+// written nor read.  ORYON_CONV_IM2COL=1 (A/B switch) or channel counts that are not multiples of 8 take im2col + GEMM.
 float* conv_nhwc(Ctx& c, const Im2colArgs& src, const SplitW& W, const float* bias, int act) {
   const size_t rows = (size_t)src.n * src.H * src.W;
   float* out = c.ar.take<float>(rows * W.N);
+  static const bool force_im2col = getenv("ORYON_CONV_IM2COL") != nullptr;
+  if (!force_im2col && src.C0 % 8 == 0 && src.C1 % 8 == 0 && W.K == src.k * src.k * (src.C0 + src.C1)) {
+    if (!c.dry && !c.rc) {
+      gemm::ConvGather g;
+      g.src0 = src.src0, g.C0 = src.C0, g.shuffle0 = src.shuffle0, g.src1 = src.src1, g.C1 = src.C1;
+      g.n = src.n, g.H = src.H, g.W = src.W, g.k = src.k;
+      gemm::Problem p;
+      p.M = (int)rows, p.N = W.N, p.K = W.K, p.precision = c.prec;
+      p.W.hi = W.hi, p.W.lo = W.lo, p.W.ld = W.ld;
+      p.ep = ep_f32(out, W.N, bias, act);
+      p.gather = &g;
+      c.rc = gemm::launch(c.h, p, c.st);
+    }
+    return out;
+  }
   const size_t mark = c.ar.off;
   SplitA A = c.split(rows, W.ld);
   if (!c.dry && !c.rc) {

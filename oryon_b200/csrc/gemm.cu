@@ -39,7 +39,8 @@ struct Cfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarBytes = (8 * (2 * kStages + 4) + 16 + 15) / 16 * 16;
   static constexpr int kEpiBytes = 8 * kEpiWarpFloats * 4;
-  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes + kEpiBytes;
+  static constexpr int kRowInfoBytes = 256 * 2 * 4;                  // gather kernels: (y | x << 16, n) per tile row
+  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes + kEpiBytes + kRowInfoBytes;
   static constexpr int kTmemCols = 2 * kRowBlocks * TN;               // 512 / 256 / 128
   static_assert(kStages >= 2, "pipeline depth");
 };
@@ -48,7 +49,11 @@ struct KArgs {
   int M, N, KB;          // KB = number of 64-deep K blocks
   int nb0, nb1, tiles_m, tiles_n;
   Epilogue ep;
+  ConvGather g;          // GATHER kernels only
+  int K;                 // logical depth (GATHER: columns >= K are zero)
 };
+
+constexpr int kGatherThreads = 256;   // one producer thread per row of the 256-row CTA tile
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -73,10 +78,13 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
-template <int TN, int NPASS>
-__global__ void __launch_bounds__(kThreads, 1)
+// GATHER = true: implicit-GEMM convolution.  The A tile of every stage is written by 8 extra producer warps (thread <-> row of
+// the CTA tile) straight from the fp32 NHWC activations -- split into fp16 hi / lo on the way and stored in the 128-byte-swizzled
+// K-major layout TMA would have produced -- instead of being materialised in HBM by an im2col pass and read back.
+template <int TN, int NPASS, bool GATHER>
+__global__ void __launch_bounds__(kThreads + (GATHER ? kGatherThreads : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, KArgs args) {
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const __grid_constant__ KArgs args) {
   using L = Cfg<TN, NPASS>;
   constexpr int STAGES = L::kStages;
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kTileM, TN, /*fp16*/ 0);
@@ -92,10 +100,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tm_a_hi);
+    if (!GATHER) ptx::prefetch_tensormap(&tm_a_hi);
     ptx::prefetch_tensormap(&tm_w_hi);
-    if (NPASS == 3) ptx::prefetch_tensormap(&tm_a_lo), ptx::prefetch_tensormap(&tm_w_lo);
-    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    if (NPASS == 3) {
+      if (!GATHER) ptx::prefetch_tensormap(&tm_a_lo);
+      ptx::prefetch_tensormap(&tm_w_lo);
+    }
+    // full: the TMA thread's arrive.expect_tx (+ one arrival per gather warp once its rows are in shared memory)
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], GATHER ? 1 + kGatherThreads / 32 : 1), ptx::mbar_init(&empty[s], 1);
     for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 8);
     ptx::fence_barrier_init();
   }
@@ -119,14 +131,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
         for (int kb = 0; kb < args.KB; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], L::kStage);
+          ptx::mbar_arrive_expect_tx(&full[stage], GATHER ? L::kWBytes : L::kStage);
           uint8_t* sa = smem + stage * L::kStage;
           uint8_t* sw = sa + L::kABytes;
+          if (!GATHER) {
 #pragma unroll
-          for (int r = 0; r < kRowBlocks; ++r) {
-            tma_load_4d(sa + r * L::kABlock, &tm_a_hi, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
-            if (NPASS == 3)
-              tma_load_4d(sa + (kRowBlocks + r) * L::kABlock, &tm_a_lo, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
+            for (int r = 0; r < kRowBlocks; ++r) {
+              tma_load_4d(sa + r * L::kABlock, &tm_a_hi, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
+              if (NPASS == 3)
+                tma_load_4d(sa + (kRowBlocks + r) * L::kABlock, &tm_a_lo, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
+            }
           }
           tma_load_4d(sw, &tm_w_hi, &full[stage], kb * kKB, nt * TN, b0, b1);
           if (NPASS == 3) tma_load_4d(sw + L::kWBlock, &tm_w_lo, &full[stage], kb * kKB, nt * TN, b0, b1);
@@ -141,7 +155,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       for (int kb = 0; kb < args.KB; ++kb) {
-        ptx::mbar_wait(&full[stage], phase);
+        if (GATHER) ptx::mbar_wait_relaxed(&full[stage], phase);
+        else ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
         {
           // every lane computes the (warp-uniform) descriptors, one elected lane issues: the UTCHMMAs of a stage go out back
@@ -175,6 +190,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
       ++tile_iter;
     }
+  } else if (GATHER && warp >= 10) {
+    // ============================ A gather (8 producer warps) ============================
+    // Warp w owns rows 32w .. 32w+31 of the CTA tile.  Per stage a lane always handles the same 4 consecutive columns of the
+    // 64-deep K block (e = 4 * (lane & 15): one tap, 4 channels), so its tap / channel arithmetic is done once per stage; the
+    // two half-warps take two rows per step, 16 lanes covering the 256 contiguous bytes of one (pixel, tap) -- fully used
+    // sectors, 4 L1 wavefronts per load instead of 32 for a thread-per-row mapping.  Row coordinates come from a small
+    // shared-memory table written once per tile.
+    const ConvGather& g = args.g;
+    const int pw = warp - 10;                         // 0..7
+    const int t = threadIdx.x - kThreads;             // 0..255
+    int32_t* rowinfo = reinterpret_cast<int32_t*>(smem + L::kStage * STAGES + L::kBarBytes + L::kEpiBytes);   // [256][2]: y | x << 16, pixel base
+    const int gH = g.H, gW = g.W, gC0 = g.C0, gC1 = g.C1, shuffle0 = g.shuffle0;
+    const int Ct = g.C0 + g.C1, half_k = g.k / 2;
+    const int e = 4 * (lane & 15), hrow = lane >> 4;
+    const uint32_t chunk = (lane & 15) >> 1, sub8 = (lane & 1) * 8;
+    uint32_t stage = 0, phase = 0;
+    for (int tk = blockIdx.x; tk < total_tasks; tk += gridDim.x) {
+      const int mt = (tk / args.tiles_n) % args.tiles_m;
+      {
+        const int row = mt * kCtaRows + t;
+        int yx = -1, pix = 0;
+        if (row < args.M) {
+          const int x = row % gW, y = (row / gW) % gH, n = row / (gW * gH);
+          yx = y | (x << 16);
+          pix = shuffle0 ? n * (gH >> 1) * (gW >> 1) : row;   // base of the image in the pixel-shuffle view / linear pixel index
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // the previous tile's readers are done with the table
+        rowinfo[2 * t] = yx, rowinfo[2 * t + 1] = pix;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      for (int kb = 0; kb < args.KB; ++kb) {
+        const int k0 = kb * kKB + e;
+        const bool k_ok = k0 < args.K;
+        const int tap = k_ok ? k0 / Ct : 0, c = k0 - tap * Ct;
+        const int dy = tap / g.k - half_k, dx = tap % g.k - half_k;
+        const bool from0 = c < g.C0;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int r = pw * 32 + it * 2 + hrow;
+          const int yx = rowinfo[2 * r], pix = rowinfo[2 * r + 1];   // pix: linear pixel index n*H*W + y*W + x (shuffle view: see below)
+          v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k_ok && yx >= 0) {
+            const int yy = (yx & 0xffff) + dy, xx = (yx >> 16) + dx;
+            if (yy >= 0 && yy < gH && xx >= 0 && xx < gW) {
+              // 32-bit element offsets (largest activation: 1.2 M pixels x 128 channels), one 64-bit add for the pointer
+              const float* src;
+              if (from0) {
+                if (shuffle0) {   // [n][H/2][W/2][2][2][C0]: pix holds n * (H/2) * (W/2)
+                  const int pp = pix + (yy >> 1) * (gW >> 1) + (xx >> 1);
+                  src = g.src0 + (unsigned)((pp * 4 + (yy & 1) * 2 + (xx & 1)) * gC0 + c);
+                } else {
+                  src = g.src0 + (unsigned)((pix + dy * gW + dx) * gC0 + c);
+                }
+              } else {
+                src = g.src1 + (unsigned)((shuffle0 ? pix * 4 + yy * gW + xx : pix + dy * gW + dx) * gC1 + (c - gC0));
+              }
+              v[it] = __ldg(reinterpret_cast<const float4*>(src));
+            }
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int r = pw * 32 + it * 2 + hrow, rr = r & 127;
+          __half h0, l0, h1, l1, h2, l2, h3, l3;
+          split_half(v[it].x, h0, l0), split_half(v[it].y, h1, l1), split_half(v[it].z, h2, l2), split_half(v[it].w, h3, l3);
+          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+          const uint32_t dst = sa + (r >> 7) * L::kABlock + (rr >> 3) * 1024 + (rr & 7) * 128 + ((chunk ^ (rr & 7)) << 4) + sub8;
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&ha)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&hb))
+                       : "memory");
+          if (NPASS == 3)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kRowBlocks * L::kABlock), "r"(*reinterpret_cast<const uint32_t*>(&la)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&lb))
+                         : "memory");
+        }
+        ptx::fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&full[stage]);
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
   } else {
     // ============================ epilogue (8 warps) ============================
     // A warp owns 32 rows of one 128-row block (TMEM lane quarter = warp % 4).  Per 16-column chunk: tcgen05.ld
@@ -205,7 +304,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::st_shared_f1(bias_s + (j * 32 + lane) * 4, (ep.bias && col < args.N) ? __ldg(ep.bias + col) : 0.f);
       }
       __syncwarp();
-      ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+      if (GATHER) ptx::mbar_wait_relaxed(&t_full[buf], (tile_iter >> 1) & 1);   // long waits behind the gather: do not spin hot
+      else ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * TN) + rblk * TN;
 #pragma unroll 1
@@ -334,22 +434,25 @@ static int make_map(oryon_handle* h, CUtensorMap* tm, const __half* base, int kp
   return ORYON_OK;
 }
 
-template <int TN, int NPASS>
+template <int TN, int NPASS, bool GATHER = false>
 static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
   using L = Cfg<TN, NPASS>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
   const int kpad = round_up(p.K, kKB);
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   int rc;
-  if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
   if ((rc = make_map(h, &tw_hi, p.W.hi, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
-  if (NPASS == 3) {
-    if ((rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
-    if ((rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
-  } else {
-    ta_lo = ta_hi, tw_lo = tw_hi;
+  tw_lo = tw_hi;
+  if (NPASS == 3 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
+  ta_hi = tw_hi, ta_lo = tw_lo;   // GATHER: the A maps are never touched
+  if (!GATHER) {
+    if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+    ta_lo = ta_hi;
+    if (NPASS == 3 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
   }
   KArgs ka;
+  ka.K = p.K;
+  if (GATHER) ka.g = *p.gather;
   ka.M = p.M, ka.N = p.N, ka.KB = kpad / kKB;
   ka.nb0 = p.nb0, ka.nb1 = p.nb1;
   ka.tiles_m = (p.M + kCtaRows - 1) / kCtaRows;
@@ -357,7 +460,7 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
   ka.ep = p.ep;
   const long long tasks = (long long)ka.tiles_m * ka.tiles_n * p.nb0 * p.nb1;
   const int grid = (int)std::min<long long>(h->sm_count, tasks);
-  auto kern = gemm_tc_kernel<TN, NPASS>;
+  auto kern = gemm_tc_kernel<TN, NPASS, GATHER>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -367,15 +470,15 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (log_shapes) cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventRecord(e0, st);
   h->span_begin(KID_GEMM, st);
-  kern<<<grid, kThreads, L::kTotal, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, ka);
+  kern<<<grid, kThreads + (GATHER ? kGatherThreads : 0), L::kTotal, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, ka);
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
   if (log_shapes) {
     cudaEventRecord(e1, st), cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    fprintf(stderr, "gemm M=%d N=%d K=%d batch=%dx%d TN=%d npass=%d tasks=%lld  %.1f us  %.0f TFLOP/s (algorithmic)\n", p.M, p.N, p.K, p.nb0,
-            p.nb1, TN, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
+    fprintf(stderr, "gemm%s M=%d N=%d K=%d batch=%dx%d TN=%d npass=%d tasks=%lld  %.1f us  %.0f TFLOP/s (algorithmic)\n", GATHER ? "+gather" : "",
+            p.M, p.N, p.K, p.nb0, p.nb1, TN, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
   ++h->gemm_launches;
@@ -386,13 +489,36 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
 int launch(oryon_handle* h, const Problem& p, cudaStream_t st) {
   ORYON_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.nb0 > 0 && p.nb1 > 0, "gemm: empty problem (M=%d N=%d K=%d)", p.M, p.N, p.K);
   ORYON_REQUIRE(p.precision == 1 || p.precision == 3, "gemm: precision must be 1 or 3");
+  const int tn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+  if (p.gather) {
+    const ConvGather& g = *p.gather;
+    ORYON_REQUIRE(p.W.hi && (p.precision == 1 || p.W.lo) && (p.W.ld % 8) == 0, "gemm+gather: missing / misaligned weights");
+    ORYON_REQUIRE(p.nb0 == 1 && p.nb1 == 1 && !p.ep.row_map, "gemm+gather: unbatched problems only");
+    ORYON_REQUIRE(g.src0 && g.C0 > 0 && g.C0 % 8 == 0 && g.C1 % 8 == 0 && (g.C1 == 0 || g.src1) && (g.k & 1) && g.k <= 7,
+                  "gemm+gather: channel counts must be multiples of 8 and the kernel odd (C0=%d C1=%d k=%d)", g.C0, g.C1, g.k);
+    ORYON_REQUIRE(p.K == g.k * g.k * (g.C0 + g.C1) && (long long)p.M == (long long)g.n * g.H * g.W, "gemm+gather: shape mismatch");
+    ORYON_REQUIRE(!g.shuffle0 || ((g.H | g.W) & 1) == 0, "gemm+gather: the pixel-shuffle view needs even H and W");
+    ORYON_REQUIRE((reinterpret_cast<uintptr_t>(g.src0) % 16) == 0 && (reinterpret_cast<uintptr_t>(g.src1) % 16) == 0,
+                  "gemm+gather: activations must be 16-byte aligned");
+    if (p.precision == 3) {
+      switch (tn) {
+        case 32: return launch_t<32, 3, true>(h, p, st);
+        case 64: return launch_t<64, 3, true>(h, p, st);
+        default: return launch_t<128, 3, true>(h, p, st);
+      }
+    }
+    switch (tn) {
+      case 32: return launch_t<32, 1, true>(h, p, st);
+      case 64: return launch_t<64, 1, true>(h, p, st);
+      default: return launch_t<128, 1, true>(h, p, st);
+    }
+  }
   ORYON_REQUIRE(p.A.hi && p.W.hi && (p.precision == 1 || (p.A.lo && p.W.lo)), "gemm: missing operand");
   ORYON_REQUIRE((p.A.ld % 8) == 0 && (p.W.ld % 8) == 0 && (p.A.stride_b0 % 8) == 0 && (p.A.stride_b1 % 8) == 0 &&
                     (p.W.stride_b0 % 8) == 0 && (p.W.stride_b1 % 8) == 0,
                 "gemm: operand strides must be multiples of 8 elements (16 bytes)");
   ORYON_REQUIRE(p.A.ld >= round_up(p.K, kKB) || p.A.ld >= p.K, "gemm: A row stride shorter than K");
   ORYON_REQUIRE(!p.ep.row_map || (p.nb0 == 1 && p.nb1 == 1), "gemm: row_map needs an unbatched problem");
-  const int tn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
   if (p.precision == 3) {
     switch (tn) {
       case 32: return launch_t<32, 3>(h, p, st);

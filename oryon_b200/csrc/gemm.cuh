@@ -41,12 +41,25 @@ struct Epilogue {
   int transpose_h = 0;                // write out_hi/out_lo transposed: element (m, n) at n * ldh + m
 };
 
+// Implicit-GEMM A operand of a k x k convolution (stride 1, zero padding k / 2) over NHWC fp32 activations: row m is output
+// pixel (n, y, x), column (tap * (C0 + C1) + c) is input channel c of tap (ty, tx) -- the column order of the im2col matrix
+// and of the packed conv weights.  Channels come from src0 ([n][H][W][C0], or through a pixel-shuffle view of a
+// ConvTranspose(k=2, s=2) GEMM output [n][H/2][W/2][2][2][C0] when shuffle0) followed by src1 ([n][H][W][C1], may be null).
+struct ConvGather {
+  const float* src0 = nullptr;
+  int C0 = 0, shuffle0 = 0;
+  const float* src1 = nullptr;
+  int C1 = 0;
+  int n = 0, H = 0, W = 0, k = 3;
+};
+
 struct Problem {
   int M = 0, N = 0, K = 0;      // K = logical depth; operands are readable up to Kpad = round_up(K, 64)
   int nb0 = 1, nb1 = 1;         // batch extents
   int precision = 3;            // 1 or 3
   Operand A, W;
   Epilogue ep;
+  const ConvGather* gather = nullptr;   // when set, A is produced on the fly from the activations (A.hi / A.lo unused); unbatched
 };
 
 // Enqueues the GEMM on `st`.  Returns an oryon_status.

@@ -84,6 +84,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait with back-off for warps that expect to wait long (e.g. an epilogue behind a slow producer): after a few failed polls the
+// warp sleeps between polls instead of competing for issue slots with the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (int i = 0; i < 8; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (clock64() - t0 > (1ll << 31)) {
+      printf("oryon: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
