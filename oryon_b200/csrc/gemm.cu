@@ -220,53 +220,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         rowinfo[2 * t] = yx, rowinfo[2 * t + 1] = pix;
         asm volatile("bar.sync 2, 256;" ::: "memory");
       }
+      // this lane's 16 rows (two per step) stay in registers for all K blocks of the tile
+      int ry[16], rp[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int r = pw * 32 + it * 2 + hrow;
+        ry[it] = rowinfo[2 * r], rp[it] = rowinfo[2 * r + 1];
+      }
       for (int kb = 0; kb < args.KB; ++kb) {
         const int k0 = kb * kKB + e;
         const bool k_ok = k0 < args.K;
         const int tap = k_ok ? k0 / Ct : 0, c = k0 - tap * Ct;
         const int dy = tap / g.k - half_k, dx = tap % g.k - half_k;
-        const bool from0 = c < g.C0;
+        const bool from0 = !k_ok || c < gC0;   // padded K columns: any valid base (they are zeroed)
+        // per-stage constants of the address: element offset = pixel * C + delta
+        const float* sbase = from0 ? g.src0 : g.src1;
+        const int Csel = from0 ? gC0 : gC1, csel = from0 ? c : c - gC0;
+        const int delta = (dy * gW + dx) * Csel + csel;
+        const bool shuf = from0 && shuffle0;
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
-        float4 v[16];
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int r = pw * 32 + it * 2 + hrow;
-          const int yx = rowinfo[2 * r], pix = rowinfo[2 * r + 1];   // pix: linear pixel index n*H*W + y*W + x (shuffle view: see below)
-          v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k_ok && yx >= 0) {
-            const int yy = (yx & 0xffff) + dy, xx = (yx >> 16) + dx;
-            if (yy >= 0 && yy < gH && xx >= 0 && xx < gW) {
-              // 32-bit element offsets (largest activation: 1.2 M pixels x 128 channels), one 64-bit add for the pointer
-              const float* src;
-              if (from0) {
-                if (shuffle0) {   // [n][H/2][W/2][2][2][C0]: pix holds n * (H/2) * (W/2)
-                  const int pp = pix + (yy >> 1) * (gW >> 1) + (xx >> 1);
-                  src = g.src0 + (unsigned)((pp * 4 + (yy & 1) * 2 + (xx & 1)) * gC0 + c);
-                } else {
-                  src = g.src0 + (unsigned)((pix + dy * gW + dx) * gC0 + c);
-                }
-              } else {
-                src = g.src1 + (unsigned)((shuffle0 ? pix * 4 + yy * gW + xx : pix + dy * gW + dx) * gC1 + (c - gC0));
-              }
-              v[it] = __ldg(reinterpret_cast<const float4*>(src));
-            }
+        for (int half16 = 0; half16 < 2; ++half16) {   // two batches of 8 rows: 8 loads in flight per lane
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int it = half16 * 8 + j;
+            const int yy = (ry[it] & 0xffff) + dy, xx = (ry[it] >> 16) + dx;
+            // branch-free: out-of-image taps / padding rows / padded K columns read a valid dummy address and are zeroed
+            const bool ok = k_ok && ry[it] >= 0 && (unsigned)yy < (unsigned)gH && (unsigned)xx < (unsigned)gW;
+            int off;
+            if (shuf) off = ((rp[it] + (yy >> 1) * (gW >> 1) + (xx >> 1)) * 4 + (yy & 1) * 2 + (xx & 1)) * gC0 + c;   // [n][H/2][W/2][2][2][C0]
+            else if (shuffle0) off = (rp[it] * 4 + yy * gW + xx) * Csel + csel;                                      // src1 next to a shuffled src0
+            else off = rp[it] * Csel + delta;
+            const float4 ld = __ldg(reinterpret_cast<const float4*>(sbase + (ok ? (unsigned)off : 0u)));
+            v[j] = ok ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        }
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int r = pw * 32 + it * 2 + hrow, rr = r & 127;
-          __half h0, l0, h1, l1, h2, l2, h3, l3;
-          split_half(v[it].x, h0, l0), split_half(v[it].y, h1, l1), split_half(v[it].z, h2, l2), split_half(v[it].w, h3, l3);
-          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
-          const uint32_t dst = sa + (r >> 7) * L::kABlock + (rr >> 3) * 1024 + (rr & 7) * 128 + ((chunk ^ (rr & 7)) << 4) + sub8;
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&ha)),
-                       "r"(*reinterpret_cast<const uint32_t*>(&hb))
-                       : "memory");
-          if (NPASS == 3)
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kRowBlocks * L::kABlock), "r"(*reinterpret_cast<const uint32_t*>(&la)),
-                         "r"(*reinterpret_cast<const uint32_t*>(&lb))
+          for (int j = 0; j < 8; ++j) {
+            const int it = half16 * 8 + j;
+            const int r = pw * 32 + it * 2 + hrow, rr = r & 127;
+            __half h0, l0, h1, l1, h2, l2, h3, l3;
+            split_half(v[j].x, h0, l0), split_half(v[j].y, h1, l1), split_half(v[j].z, h2, l2), split_half(v[j].w, h3, l3);
+            const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+            const uint32_t dst = sa + (r >> 7) * L::kABlock + (rr >> 3) * 1024 + (rr & 7) * 128 + ((chunk ^ (rr & 7)) << 4) + sub8;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&ha)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&hb))
                          : "memory");
+            if (NPASS == 3)
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kRowBlocks * L::kABlock), "r"(*reinterpret_cast<const uint32_t*>(&la)),
+                           "r"(*reinterpret_cast<const uint32_t*>(&lb))
+                           : "memory");
+          }
         }
         ptx::fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
         __syncwarp();
