@@ -238,14 +238,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int Csel = from0 ? gC0 : gC1, csel = from0 ? c : c - gC0;
         const int delta = (dy * gW + dx) * Csel + csel;
         const bool shuf = from0 && shuffle0;
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
+        auto load4 = [&](float4 (&v)[4], int b) {
 #pragma unroll
-        for (int half16 = 0; half16 < 2; ++half16) {   // two batches of 8 rows: 8 loads in flight per lane
-          float4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int it = half16 * 8 + j;
+          for (int j = 0; j < 4; ++j) {
+            const int it = b * 4 + j;
             const int yy = (ry[it] & 0xffff) + dy, xx = (ry[it] >> 16) + dx;
             // branch-free: out-of-image taps / padding rows / padded K columns read a valid dummy address and are zeroed
             const bool ok = k_ok && ry[it] >= 0 && (unsigned)yy < (unsigned)gH && (unsigned)xx < (unsigned)gW;
@@ -256,9 +253,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const float4 ld = __ldg(reinterpret_cast<const float4*>(sbase + (ok ? (unsigned)off : 0u)));
             v[j] = ok ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        };
+        auto store4 = [&](const float4 (&v)[4], int b) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int it = half16 * 8 + j;
+          for (int j = 0; j < 4; ++j) {
+            const int it = b * 4 + j;
             const int r = pw * 32 + it * 2 + hrow, rr = r & 127;
             __half h0, l0, h1, l1, h2, l2, h3, l3;
             split_half(v[j].x, h0, l0), split_half(v[j].y, h1, l1), split_half(v[j].z, h2, l2), split_half(v[j].w, h3, l3);
@@ -272,7 +271,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                            "r"(*reinterpret_cast<const uint32_t*>(&lb))
                            : "memory");
           }
-        }
+        };
+        // software pipeline over four batches of four rows: eight loads in flight, and the first eight are issued before the
+        // wait for the shared-memory slot (global loads do not need it)
+        float4 va[4], vb[4];
+        load4(va, 0);
+        load4(vb, 1);
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        store4(va, 0);
+        load4(va, 2);
+        store4(vb, 1);
+        load4(vb, 3);
+        store4(va, 2);
+        store4(vb, 3);
         ptx::fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&full[stage]);
