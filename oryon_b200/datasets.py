@@ -56,6 +56,7 @@ class GpuCollate:
         self.img_size = tuple(int(v) for v in img_size)
         self.device = device
         self._pinned: Dict[tuple, Tensor] = {}
+        self._uploaded: Dict[str, torch.cuda.Event] = {}   # per view: the H2D copies that last read the pinned buffers
 
     def _pin(self, key: str, shape, dtype) -> Tensor:
         k = (key, tuple(shape), dtype)
@@ -68,6 +69,8 @@ class GpuCollate:
         H, W = items[0]["mask"].shape
         if any(it["mask"].shape != (H, W) for it in items):
             raise ValueError("GpuCollate: frames of one batch must share a size")
+        if tag in self._uploaded:      # the previous batch's asynchronous uploads must have left the pinned buffers
+            self._uploaded[tag].synchronize()
         rgb = self._pin(tag + "rgb", (B, H, W, 3), torch.uint8)
         mask = self._pin(tag + "mask", (B, H, W), torch.uint8 if np.asarray(items[0]["mask"]).dtype == np.uint8 else torch.int32)
         depth_dtype = {np.dtype(np.uint16): torch.int32, np.dtype(np.int64): torch.int32}.get(np.asarray(items[0]["depth"]).dtype, None)
@@ -80,7 +83,11 @@ class GpuCollate:
         ids = torch.tensor([int(it["metadata"]["mask_ids"][0]) for it in items], dtype=torch.int32)
         dev = self.device
         rgb_f, mask_u8 = stage_inputs(rgb, mask, ids, self.img_size, dev)
-        return dict(rgb=rgb_f, mask=mask_u8, orig_depth=as_device(depth, rgb_f.device), eval_depth=depth,
+        depth_dev = as_device(depth, rgb_f.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(rgb_f.device))
+        self._uploaded[tag] = ev
+        return dict(rgb=rgb_f, mask=mask_u8, orig_depth=depth_dev, eval_depth=depth.clone(),
                     camera=torch.stack([torch.as_tensor(np.asarray(it["camera"], dtype=np.float64)).reshape(3, 3) for it in items]),
                     pose=torch.stack([torch.as_tensor(np.asarray(it["metadata"]["poses"][0], dtype=np.float64)) for it in items]),
                     sizes=torch.tensor([[H, W]] * B), instance_id=[it["instance_id"] for it in items])
