@@ -42,6 +42,7 @@ struct SwinBlock {
   const float *n1_g, *n1_b, *n2_g, *n2_b, *qkv_b, *proj_b, *fc1_b, *fc2_b;
   SplitW qkv, proj, fc1, fc2;
   const float* bias = nullptr;  // [heads][S][S] relative position bias (guidance backbone only)
+  const float* bias_t = nullptr;  // the same table with the two token indices swapped (query index contiguous)
 };
 struct Stage {  // one resolution of a (guidance or fusion) Swin stack
   int H, W, ws, shift, heads, dim;
@@ -340,6 +341,11 @@ int finalize(oryon_handle* h, const oryon_backbone_config* cfg, cudaStream_t st)
               for (int hd = 0; hd < heads; ++hd) bias[((size_t)hd * 49 + i) * 49 + j] = (*tab)[(size_t)(dy * 13 + dx) * heads + hd];
             }
           B.bias = L.f32(bias);
+          std::vector<float> bias_t(bias.size());
+          for (int hd = 0; hd < heads; ++hd)
+            for (int i = 0; i < 49; ++i)
+              for (int j = 0; j < 49; ++j) bias_t[((size_t)hd * 49 + j) * 49 + i] = bias[((size_t)hd * 49 + i) * 49 + j];
+          B.bias_t = L.f32(bias_t);
         }
       }
       const std::string mg = p + "." + std::to_string(feat + 1);
@@ -568,7 +574,7 @@ void swin_block(Ctx& c, float* x, int N, const Stage& S, const SwinBlock& B, boo
   c.gemm(a_in, Mw, B.qkv, ep_f32(qkv, 3 * dim, B.qkv_b));
   AttnArgs a;
   a.qkv = qkv, a.ld = 3 * dim, a.off_k = dim, a.off_v = 2 * dim, a.n_seq = N * S.nW, a.S = ws2, a.heads = S.heads, a.d = dim / S.heads;
-  a.scale = 1.f / sqrtf((float)(dim / S.heads)), a.bias = B.bias, a.mask = shifted ? S.mask : nullptr, a.n_win = S.nW;
+  a.scale = 1.f / sqrtf((float)(dim / S.heads)), a.bias = B.bias, a.bias_t = B.bias_t, a.mask = shifted ? S.mask : nullptr, a.n_win = S.nW;
   a.out_hi = att.hi, a.out_lo = att.lo, a.ldh = dim;
   c.attn(a);
   c.gemm(att, Mw, B.proj, ep_f32(x, dim, B.proj_b, gemm::ACT_NONE, x, map));

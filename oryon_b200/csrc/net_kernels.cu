@@ -418,8 +418,12 @@ __global__ void __launch_bounds__(160) window_attention_kernel(AttnArgs a, int s
   const int qi = w * 32 + lane;
   const bool ok = qi < S;
   const int qrow = ok ? qi : 0;
-  const float* bias = a.bias ? a.bias + ((int64_t)hh * S + qrow) * S : nullptr;
-  const float* mask = a.mask ? a.mask + ((int64_t)(seq % a.n_win) * S + qrow) * S : nullptr;
+  // bias / mask are read with the QUERY index contiguous across lanes (one 128-byte line per instruction instead of 32 scattered
+  // sectors): the transposed bias table when the caller has one, and the shift mask through its symmetry mask[i][j] == mask[j][i]
+  const bool bt = a.bias_t != nullptr;
+  const float* bias = bt ? a.bias_t + (int64_t)hh * S * S + qrow : (a.bias ? a.bias + ((int64_t)hh * S + qrow) * S : nullptr);
+  const int bstride = bt ? S : 1;
+  const float* mask = a.mask ? a.mask + (int64_t)(seq % a.n_win) * S * S + qrow : nullptr;
   float* my = Sc + (size_t)(w * 32 + lane) * s_ld;
   float q[kWinD];
   {
@@ -439,8 +443,8 @@ __global__ void __launch_bounds__(160) window_attention_kernel(AttnArgs a, int s
       s0 = fmaf(q[4 * i], k.x, s0), s1 = fmaf(q[4 * i + 1], k.y, s1), s2 = fmaf(q[4 * i + 2], k.z, s2), s3 = fmaf(q[4 * i + 3], k.w, s3);
     }
     float sc = (s0 + s1) + (s2 + s3);
-    if (bias) sc += __ldg(bias + j);
-    if (mask) sc += __ldg(mask + j);
+    if (bias) sc += __ldg(bias + j * bstride);
+    if (mask) sc += __ldg(mask + j * S);
     return sc;
   };
   float m = -INFINITY;

@@ -44,7 +44,8 @@ struct AttnArgs {
   float scale = 1.f;              // q * scale before the dot product
   int causal = 0;                 // CLIP text tower (upper-triangular -inf mask)
   const float* bias = nullptr;    // [heads][S][S] relative-position bias (torchvision swin)
-  const float* mask = nullptr;    // [n_win][S][S] shifted-window mask, window = seq % n_win
+  const float* bias_t = nullptr;  // optional: bias with the token indices swapped, [heads][key][query] (coalesced for a query per lane)
+  const float* mask = nullptr;    // [n_win][S][S] shifted-window mask, window = seq % n_win; symmetric in the two token indices
   int n_win = 1;
   __half* out_hi = nullptr;       // [n_seq*S][ldh] heads concatenated
   __half* out_lo = nullptr;
