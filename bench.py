@@ -250,10 +250,33 @@ def run_reference(args):
             "cpu_baseline": {"value": pairs_per_s, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": pairs_per_s, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version from C code when a
+    communicator is created), so file descriptor 1 is pointed at stderr for the whole run and the line is written to the
+    saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -422,7 +445,7 @@ def main():
             line["cpu_baseline"] = {"value": (args.cpu_rows / n) / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_rows} of {n} anchor rows of one pair x all {n} query positions, D={D}; "
                                               f"{sec:.1f} s measured, scaled by {n / args.cpu_rows:.1f}"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
