@@ -103,6 +103,19 @@ int oryon_match_nn(oryon_handle* h, const float* feat_a, const float* feat_q, in
  *   stats[2] rows that overflowed to the exact fallback   stats[3] kernels launched by the call */
 int oryon_match_last_stats(oryon_handle* h, int64_t stats[4], void* stream);
 
+/* HOST-ONLY diagnostic (no device work, no handle): the work decomposition oryon_match_nn uses for its tensor-core pass on
+ * a device with `sm_count` SMs.  The units (pair, 256-row anchor block, 128-column query tile) of the batch are distributed
+ * over the CTAs of the persistent kernel as lists of segments: whole row blocks round robin for the full waves, the rest cut
+ * into per-CTA tile quotas that level the finishing times (kind 0, the default; 1 = one contiguous range per CTA, 2 = whole
+ * row blocks only; the environment variable ORYON_MATCH_PLAN=contiguous|whole selects 1 / 2 inside oryon_match_nn).
+ *   n_a, n_q   HOST int32 [B] list lengths          seg_cap   capacity of segs_out in segments (0: only count)
+ *   segs_out   HOST int32 [seg_cap][5]: pair, row block, first tile, end tile, candidate-list slot of the row block
+ *   begin_out  HOST int32 [sm_count + 1]: first segment of CTA c in [c], total in [grid]
+ *   info_out   HOST int32 [3]: grid, candidate lists per row (max slot + 1), number of segments
+ * Returns 0, or ORYON_ERR_INVALID_ARGUMENT when seg_cap is too small (info_out is still filled). */
+int oryon_match_plan(const int32_t* n_a, const int32_t* n_q, int B, int sm_count, int kind, int32_t* segs_out, int seg_cap,
+                     int32_t* begin_out, int32_t info_out[3]);
+
 /* Row-major compaction of a [B][HW] mask into pixel-id lists: ids of elements equal to `value`
  * in ascending order == torch.nonzero(mask == value) (reference utils/pcd.py:184-185).
  *   mask    DEVICE int32 [B][HW]      roi_out DEVICE int32 [B][HW]      n_out DEVICE int32 [B] */

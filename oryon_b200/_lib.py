@@ -59,6 +59,8 @@ SIGNATURES = {
     "oryon_match_nn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "oryon_match_last_stats": (c_int, [c_void_p, POINTER(c_int64), c_void_p]),
+    "oryon_match_plan": (c_int, [POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
+                                 POINTER(c_int32)]),
     "oryon_mask_to_roi": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "oryon_corrs_to_pcd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -52,6 +52,7 @@ int run_match(oryon_handle*, const float*, const float*, int, int, int, int, con
               const int32_t*, int, int, int, int32_t*, float*, cudaStream_t);
 int run_mask_to_roi(oryon_handle*, const int32_t*, int, int, int, int32_t*, int32_t*, cudaStream_t);
 int read_stats(oryon_handle*, int64_t*, cudaStream_t);
+int plan_debug(const int32_t*, const int32_t*, int, int, int, int32_t*, int, int32_t*, int32_t*);
 }  // namespace match
 namespace stage {
 int run(oryon_handle*, const uint8_t*, const void*, int, const int32_t*, int, int, int, int, int, float*, uint8_t*, cudaStream_t);
@@ -118,7 +119,7 @@ void oryon_handle::span_end(cudaStream_t st) {
 
 int64_t oryon_handle::workspace_bytes() const {
   return (int64_t)(rows16_a.bytes + rows16_q.bytes + rows32_a.bytes + rows32_q.bytes + cand.bytes + counters.bytes +
-                   overflow_rows.bytes + pair_meta.bytes + lift_scratch.bytes + pdsc_ws.bytes + gemm_scratch.bytes);
+                   overflow_rows.bytes + pair_meta.bytes + match_plan.bytes + lift_scratch.bytes + pdsc_ws.bytes + gemm_scratch.bytes);
 }
 
 extern "C" {
@@ -164,7 +165,7 @@ int oryon_destroy(oryon_handle* h) {
   h->rows16_a.release(), h->rows16_q.release(), h->rows32_a.release(), h->rows32_q.release();
   for (auto& s : h->spans) cudaEventDestroy(s.a), cudaEventDestroy(s.b);
   for (auto e : h->free_events) cudaEventDestroy(e);
-  h->cand.release(), h->counters.release(), h->overflow_rows.release(), h->pair_meta.release(), h->lift_scratch.release();
+  h->cand.release(), h->counters.release(), h->overflow_rows.release(), h->pair_meta.release(), h->match_plan.release(), h->lift_scratch.release();
   oryon::pdsc::destroy_model(h);
   oryon::net::destroy_backbone(h);
   oryon::eval::destroy_state(h);
@@ -205,6 +206,11 @@ int oryon_match_nn(oryon_handle* h, const float* feat_a, const float* feat_q, in
 
 int oryon_match_last_stats(oryon_handle* h, int64_t stats[4], void* stream) {
   return oryon::match::read_stats(h, stats, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_match_plan(const int32_t* n_a, const int32_t* n_q, int B, int sm_count, int kind, int32_t* segs_out, int seg_cap,
+                     int32_t* begin_out, int32_t info_out[3]) {
+  return oryon::match::plan_debug(n_a, n_q, B, sm_count, kind, segs_out, seg_cap, begin_out, info_out);
 }
 
 int oryon_mask_to_roi(oryon_handle* h, const int32_t* mask, int B, int HW, int value, int32_t* roi_out, int32_t* n_out, void* stream) {

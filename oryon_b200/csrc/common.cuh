@@ -84,6 +84,7 @@ struct oryon_handle {
   oryon::DeviceBuffer counters;             // small counter block (work queue, stats, overflow list size)
   oryon::DeviceBuffer overflow_rows;        // rows that need the exact fallback
   oryon::DeviceBuffer pair_meta;            // per-pair {n_a, n_q} on device
+  oryon::DeviceBuffer match_plan;           // segment table of the tensor-core pass (match.cu: Seg)
   int64_t last_launches = 0;
 
   // ---- lift workspace ----

@@ -14,6 +14,8 @@
 // zero padded).  Candidate lists: cand_m / cand_cnt [B][S][Npad_a], cand_chunk [B][S][Npad_a][CAND_CAP].
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -145,6 +147,81 @@ __global__ void __launch_bounds__(256) prep_dense_kernel(PrepArgs a) {
   }
 }
 
+// Dense path, second version (D in {32, 64, 128, 256}): the transposition happens in registers.  A thread loads the same pixel
+// pair of four consecutive channels (float2 each, 256 contiguous bytes per warp instruction, every load of the thread issued
+// before the first use) and stores the two pixels' channel quads as float4 into a PIXEL-major tile.  After the only barrier
+// a warp owns a pixel: one float4 per lane (conflict free), squared norm by warp shuffles, and the unit row leaves as one
+// 16-byte fp32 store and one 8-byte fp16 store per lane (512 / 256 contiguous bytes per instruction) instead of 4- and
+// 2-byte stores after two more barriers.  Same arithmetic as prep_dense_kernel up to the summation order of the norm.
+template <int NIT>   // D = 32 * NIT channels: NIT channel quads per warp
+__global__ void __launch_bounds__(256) prep_dense2_kernel(PrepArgs a) {
+  extern __shared__ __align__(16) float tile4[];  // [kPrepPix][LD]
+  float* tile = tile4;
+  constexpr int D = 32 * NIT, LD = D + 4;         // LD / 4 odd: float4 stores of consecutive pixels fall into distinct bank quads
+  const int side = blockIdx.z, b = blockIdx.y, r0 = blockIdx.x * kPrepPix;
+  const int hw = a.hw[side];
+  if (r0 >= hw) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = a.feat[side] + (size_t)b * D * hw + r0;
+  const int npix = min(kPrepPix, hw - r0);
+  const bool in0 = 2 * lane < npix, in1 = 2 * lane + 1 < npix;
+  float2 v[NIT][4];
+  if (npix == kPrepPix) {   // whole tile (CTA-uniform): straight-line loads
+#pragma unroll
+    for (int i = 0; i < NIT; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)   // hw even, r0 even: 8-byte aligned
+        v[i][c] = __ldg(reinterpret_cast<const float2*>(src + (size_t)(4 * (warp + 8 * i) + c) * hw) + lane);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NIT; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* ch = src + (size_t)(4 * (warp + 8 * i) + c) * hw;
+        v[i][c] = make_float2(0.f, 0.f);
+        if (in1) v[i][c] = __ldg(reinterpret_cast<const float2*>(ch) + lane);
+        else if (in0) v[i][c].x = __ldg(ch + 2 * lane);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int d = 4 * (warp + 8 * i);
+    *reinterpret_cast<float4*>(&tile[(2 * lane) * LD + d]) = make_float4(v[i][0].x, v[i][1].x, v[i][2].x, v[i][3].x);
+    *reinterpret_cast<float4*>(&tile[(2 * lane + 1) * LD + d]) = make_float4(v[i][0].y, v[i][1].y, v[i][2].y, v[i][3].y);
+  }
+  __syncthreads();
+  float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;   // D4 == D here
+  __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
+  constexpr int Q = (D + 127) / 128;   // float4 quads per lane (1 up to D = 128, 2 at D = 256)
+#pragma unroll 4
+  for (int row = warp; row < npix; row += 8) {
+    float4 x[Q];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int d = 4 * (lane + 32 * q);
+      x[q] = d < D ? *reinterpret_cast<const float4*>(&tile[row * LD + d]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss = fmaf(x[q].x, x[q].x, ss), ss = fmaf(x[q].y, x[q].y, ss), ss = fmaf(x[q].z, x[q].z, ss), ss = fmaf(x[q].w, x[q].w, ss);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    // x / max(|x|, eps) as x * (1 / max(|x|, eps)), as in prep_dense_kernel
+    const float inv = __fdiv_rn(1.f, fmaxf(sqrtf(ss), 1e-8f));
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int d = 4 * (lane + 32 * q);
+      const float4 u = make_float4(x[q].x * inv, x[q].y * inv, x[q].z * inv, x[q].w * inv);
+      if (d < D) *reinterpret_cast<float4*>(d32 + (size_t)row * D + d) = u;
+      if (d < a.Dpad) {   // columns D .. Dpad - 1 (D = 32 with a 64-wide swizzle atom never occurs: Dpad == D for these D)
+        const __half2 lo = __floats2half2_rn(u.x, u.y), hi = __floats2half2_rn(u.z, u.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo), pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(d16 + (size_t)row * a.Dpad + d) = pk;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // exact fp32 rows (mode ORYON_MATCH_EXACT_FP32 and overflow fallback)
 // ------------------------------------------------------------------------------------------------
@@ -264,8 +341,23 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(ExactArgs a) {
 // ------------------------------------------------------------------------------------------------
 // tcgen05 similarity + running-max / candidate-chunk epilogue
 // ------------------------------------------------------------------------------------------------
+// Work decomposition ("stream-K" over query tiles).  The unit of work is one 128-column query tile of one 256-row anchor
+// block; all units of the batch, in (pair, row block, tile) order, are cut into gridDim.x contiguous ranges of equal length
+// (+-1), so every CTA of the persistent kernel finishes at the same time whatever the task count (2 400 row blocks on 148 SMs
+// are 16.2 waves: whole-task round robin idles 116 SMs during a 17th).  A range is a list of segments = (row block, tile
+// range); a row block cut by a range boundary is scanned by two (at most `splits`) CTAs, each with its own candidate list
+// (slot), merged by the refine pass.  The table is built on the host (list lengths are host-side arguments of the C ABI).
+struct Seg {
+  int32_t b_slot;   // pair | slot << 24
+  int32_t rb;       // 256-row anchor block within the pair
+  int32_t j0, j1;   // query tiles [j0, j1)
+};
+static_assert(sizeof(Seg) == 16, "Seg is loaded as one 16-byte word");
+
 struct TcArgs {
   const PairMeta* meta;
+  const Seg* segs;
+  const int32_t* seg_begin;   // [gridDim.x + 1]
   int B, npad_a, npad_q, splits;
   float* cand_m;
   int32_t* cand_cnt;
@@ -332,20 +424,15 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  const int rb_per_pair = args.npad_a / kCtaRows;
-  const int total_tasks = args.B * rb_per_pair * args.splits;
+  const int seg_lo = args.seg_begin[blockIdx.x], seg_hi = args.seg_begin[blockIdx.x + 1];
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, task_iter = 0;
-      for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-        const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
-        const PairMeta pm = args.meta[b];
-        if (rb * kCtaRows >= pm.n_a || pm.n_q <= 0) continue;
-        const int tiles = (pm.n_q + kTileN - 1) / kTileN;
-        const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
-        if (j0 >= j1) continue;
+      for (int si = seg_lo; si < seg_hi; ++si) {
+        const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);
+        const int b = sg.x & 0xFFFFFF, rb = sg.y, j0 = sg.z, j1 = sg.w;
         ptx::mbar_wait(a_empty, (task_iter & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, L::kABytes);
 #pragma unroll
@@ -370,13 +457,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // Every lane runs the (warp-uniform) control flow; one elected lane issues.  Descriptors are built once per stage /
     // row block and advanced by adding 2 (= 32 bytes >> 4) per 16-element K step.
     uint32_t stage = 0, phase = 0, task_iter = 0, tile_iter = 0;
-    for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-      const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
-      const int n_a = __shfl_sync(0xffffffffu, args.meta[b].n_a, 0), n_q = __shfl_sync(0xffffffffu, args.meta[b].n_q, 0);
-      if (rb * kCtaRows >= n_a || n_q <= 0) continue;
-      const int tiles = (n_q + kTileN - 1) / kTileN;
-      const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
-      if (j0 >= j1) continue;
+    for (int si = seg_lo; si < seg_hi; ++si) {
+      const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);   // same address in every lane
+      const int j0 = __shfl_sync(0xffffffffu, sg.z, 0), j1 = __shfl_sync(0xffffffffu, sg.w, 0);
       ptx::mbar_wait(a_full, task_iter & 1);
       for (int j = j0; j < j1; ++j) {
         const uint32_t buf = tile_iter & 1;
@@ -420,20 +503,13 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
     const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
     uint32_t tile_iter = 0;
-    for (int t = blockIdx.x; t < total_tasks; t += gridDim.x) {
-      const int s = t % args.splits, rb = (t / args.splits) % rb_per_pair, b = t / (args.splits * rb_per_pair);
+    for (int si = seg_lo; si < seg_hi; ++si) {
+      const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);
+      const int b = sg.x & 0xFFFFFF, s = sg.x >> 24, rb = sg.y, j0 = sg.z, j1 = sg.w;
       const PairMeta pm = args.meta[b];
-      if (rb * kCtaRows >= pm.n_a || pm.n_q <= 0) continue;
-      const int tiles = (pm.n_q + kTileN - 1) / kTileN;
-      const int j0 = (int)((long long)tiles * s / args.splits), j1 = (int)((long long)tiles * (s + 1) / args.splits);
       const int row = rb * kCtaRows + row_in_cta;
       const bool row_ok = row < pm.n_a;
       const size_t slot = (((size_t)b * args.splits + s) * kEpiSets + set) * args.npad_a + row;
-      if (j0 >= j1) {
-        // this split owns no tile (more splits than tiles): publish an empty list
-        if (row_ok) args.cand_m[slot] = -INFINITY, args.cand_cnt[slot] = 0;
-        continue;
-      }
       uint32_t* my_list = args.cand_chunk + slot * kCandCap;
       float m_run = -INFINITY;
       float thr = row_ok ? -INFINITY : INFINITY;  // rows beyond n_a never record anything
@@ -523,6 +599,7 @@ struct RefineArgs {
   const float* cand_m;
   const int32_t* cand_cnt;
   const uint32_t* cand_chunk;
+  const uint8_t* nseg;         // [B][npad_a / kCtaRows] candidate lists (segments) per anchor row block
   int B, npad_a, npad_q, D4, splits, cap_a;
   float ambiguity;
   int32_t* out_idx;
@@ -549,9 +626,10 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
       if (lane == 0) a.out_idx[o] = -1, a.out_dist[o] = INFINITY;
       continue;
     }
+    const int lists = a.nseg[b * (a.npad_a / kCtaRows) + r / kCtaRows] * kEpiSets;
     float m_all = -INFINITY;
     bool overflow = false;
-    for (int s = 0; s < a.splits; ++s) {
+    for (int s = 0; s < lists; ++s) {
       const size_t slot = ((size_t)b * a.splits + s) * a.npad_a + r;
       m_all = fmaxf(m_all, a.cand_m[slot]);
       overflow |= a.cand_cnt[slot] > kCandCap;
@@ -565,7 +643,7 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
     const float4* arow = reinterpret_cast<const float4*>(a.rows32_a + ((size_t)b * a.npad_a + r) * a.D4);
     float best = -INFINITY;
     int best_j = 0x7fffffff;
-    for (int s = 0; s < a.splits; ++s) {
+    for (int s = 0; s < lists; ++s) {
       const size_t slot = ((size_t)b * a.splits + s) * a.npad_a + r;
       if (a.cand_m[slot] < m_all - a.ambiguity) continue;  // nothing in this split can win
       const int cnt = a.cand_cnt[slot];
@@ -599,6 +677,86 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
     }
   }
   if (lane == 0 && a.stats) {
+    if (n_rows) atomicAdd(a.stats + 0, n_rows);
+    if (n_chunks) atomicAdd(a.stats + 1, n_chunks);
+    if (n_over) atomicAdd(a.stats + 2, n_over);
+  }
+}
+
+// Second version: eight lanes per anchor row, four rows per warp.  The work per row is a chain of dependent loads (list
+// length -> list entry -> query row) followed by a 128-element dot product; with a whole warp per row only one such chain
+// per warp is in flight and the dot product is a single float4 per lane.  Eight lanes per row keep four chains in flight per
+// warp and still read 128 contiguous bytes per row and instruction.  Groups diverge only when their list lengths differ.
+// Same arithmetic as refine_rows_kernel up to the summation order of the dot product (8 partial sums of 16 instead of 32 of 4).
+__global__ void __launch_bounds__(256) refine_rows4_kernel(RefineArgs a) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const unsigned gmask = 0xffu << (grp * 8);
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nvec = a.D4 >> 2;
+  const int total = a.B * a.npad_a;
+  unsigned long long n_rows = 0, n_chunks = 0, n_over = 0;
+  for (int item0 = wid * 4; item0 < total; item0 += nwarps * 4) {
+    const int item = item0 + grp;
+    if (item >= total) continue;
+    const int b = item / a.npad_a, r = item - b * a.npad_a;
+    const PairMeta pm = a.meta[b];
+    if (r >= pm.n_a) continue;
+    const size_t o = (size_t)b * a.cap_a + r;
+    if (pm.n_q <= 0) {
+      if (sub == 0) a.out_idx[o] = -1, a.out_dist[o] = INFINITY;
+      continue;
+    }
+    const int lists = a.nseg[b * (a.npad_a / kCtaRows) + r / kCtaRows] * kEpiSets;
+    float m_all = -INFINITY;
+    bool overflow = false;
+    for (int s = 0; s < lists; ++s) {
+      const size_t slot = ((size_t)b * a.splits + s) * a.npad_a + r;
+      m_all = fmaxf(m_all, a.cand_m[slot]);
+      overflow |= a.cand_cnt[slot] > kCandCap;
+    }
+    if (overflow) {
+      if (sub == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = item, ++n_over;
+      continue;
+    }
+    if (sub == 0) ++n_rows;
+    const float4* arow = reinterpret_cast<const float4*>(a.rows32_a + ((size_t)b * a.npad_a + r) * a.D4);
+    float best = -INFINITY;
+    int best_j = 0x7fffffff;
+    for (int s = 0; s < lists; ++s) {
+      const size_t slot = ((size_t)b * a.splits + s) * a.npad_a + r;
+      if (a.cand_m[slot] < m_all - a.ambiguity) continue;  // nothing in this list can win
+      const int cnt = a.cand_cnt[slot];
+      for (int e = 0; e < cnt; ++e) {
+        const uint32_t ent = a.cand_chunk[slot * kCandCap + e];
+        const int col0 = (int)(ent & 0xFFFFFFu) * kChunk;
+        uint32_t bits = ent >> 24;
+        while (bits) {
+          const int col = col0 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (col >= pm.n_q) continue;
+          const float4* qrow = reinterpret_cast<const float4*>(a.rows32_q + ((size_t)b * a.npad_q + col) * a.D4);
+          float acc = 0.f;
+          for (int i = sub; i < nvec; i += 8) {
+            const float4 x = __ldg(arow + i), y = __ldg(qrow + i);
+            acc = fmaf(x.x, y.x, acc);
+            acc = fmaf(x.y, y.y, acc);
+            acc = fmaf(x.z, y.z, acc);
+            acc = fmaf(x.w, y.w, acc);
+          }
+#pragma unroll
+          for (int off = 4; off >= 1; off >>= 1) acc += __shfl_xor_sync(gmask, acc, off);
+          if (acc > best || (acc == best && col < best_j)) best = acc, best_j = col;
+        }
+        if (sub == 0) ++n_chunks;
+      }
+    }
+    if (sub == 0) {
+      a.out_idx[o] = best_j;
+      a.out_dist[o] = 0.5f * (-1.f * best + 1.f);
+    }
+  }
+  if (sub == 0 && a.stats) {
     if (n_rows) atomicAdd(a.stats + 0, n_rows);
     if (n_chunks) atomicAdd(a.stats + 1, n_chunks);
     if (n_over) atomicAdd(a.stats + 2, n_over);
@@ -677,12 +835,111 @@ static int launch_tc(oryon_handle* h, const CUtensorMap& tma, const CUtensorMap&
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+struct TcPlan {
+  std::vector<Seg> segs;
+  std::vector<int32_t> begin;   // [grid + 1] first segment of every CTA
+  std::vector<uint8_t> nseg;    // [B][rb_per_pair] segments (candidate lists) of a row block
+  int grid = 0, splits = 0;
+};
+
+// Distributes the (pair, row block, query tile) units of a batch over the CTAs of the persistent kernel (see Seg).
+//   kPlanHybrid      whole row blocks round robin for as many full waves as there are (CTAs that run at the same time then sweep
+//                    neighbouring row blocks of the same pair, so the query tiles they stream are shared through L2), and the
+//                    remaining row blocks cut into per-CTA quotas of query tiles that level the finishing times (water filling
+//                    over the bulk loads, which differ when the pairs are ragged).
+//   kPlanContiguous  every CTA gets one contiguous range of units.  Equally balanced, but at config 2 the 148 CTAs then sweep 148
+//                    different row blocks spread over all 32 pairs: the query rows in flight (157 MB) no longer fit L2 and the
+//                    kernel becomes HBM-bound (measured 2.69 ms against 2.44 ms for whole-task round robin).  Kept for A/B.
+//   kPlanWholeTasks  round robin of whole row blocks whenever there are at least as many as CTAs (no cutting: the tail wave is
+//                    partly idle); the first version's behaviour, kept for A/B.
+// A quota is either 0 or >= tiles_max / (kMaxSplits - 1), so no row block is shared by more than kMaxSplits CTAs.
+enum PlanKind { kPlanHybrid = 0, kPlanContiguous = 1, kPlanWholeTasks = 2 };
+
+static void build_tc_plan(const std::vector<PairMeta>& meta, int rb_per_pair, int sm_count, int kind, TcPlan* plan) {
+  struct Task {
+    int b, rb, tiles;
+  };
+  const int B = (int)meta.size();
+  plan->nseg.assign((size_t)B * rb_per_pair, 0);
+  std::vector<Task> tasks;
+  long long units = 0;
+  int tiles_max = 0;
+  for (int b = 0; b < B; ++b) {
+    const PairMeta& pm = meta[b];
+    if (pm.n_a <= 0 || pm.n_q <= 0) continue;
+    const int tiles = (pm.n_q + kTileN - 1) / kTileN, rbs = (pm.n_a + kCtaRows - 1) / kCtaRows;
+    for (int rb = 0; rb < rbs; ++rb) tasks.push_back(Task{b, rb, tiles});
+    units += (long long)rbs * tiles;
+    tiles_max = std::max(tiles_max, tiles);
+  }
+  if (units == 0) {
+    plan->begin.assign(1, 0);
+    return;
+  }
+  const int G = sm_count;
+  const long long min_share = (tiles_max + kMaxSplits - 2) / (kMaxSplits - 1);
+  size_t n_bulk = tasks.size() / G * G;
+  if (kind == kPlanContiguous) n_bulk = 0;
+  if (kind == kPlanWholeTasks && tasks.size() >= (size_t)G) n_bulk = tasks.size();
+  std::vector<std::vector<Seg>> lists(G);
+  std::vector<long long> load(G, 0), quota(G, 0);
+  for (size_t t = 0; t < n_bulk; ++t) {
+    const Task& k = tasks[t];
+    lists[t % G].push_back(Seg{k.b, k.rb, 0, k.tiles});
+    load[t % G] += k.tiles;
+    plan->nseg[(size_t)k.b * rb_per_pair + k.rb] = 1;
+    plan->splits = std::max(plan->splits, 1);
+  }
+  long long rem = 0;
+  for (size_t t = n_bulk; t < tasks.size(); ++t) rem += tasks[t].tiles;
+  if (rem > 0) {
+    // water filling over the k least loaded CTAs, with the largest k that leaves every participant a quota >= min_share
+    std::vector<int> order(G);
+    for (int c = 0; c < G; ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return load[x] < load[y]; });
+    std::vector<long long> pre(G + 1, 0);
+    for (int i = 0; i < G; ++i) pre[i + 1] = pre[i] + load[order[i]];
+    int k = G;
+    long long level = 0;
+    for (; k >= 1; --k) {
+      level = (rem + pre[k]) / k;
+      if (k == 1 || level - load[order[k - 1]] >= min_share) break;
+    }
+    long long left = rem - (level * k - pre[k]);   // < k
+    std::vector<int> part(order.begin(), order.begin() + k);
+    std::sort(part.begin(), part.end());
+    for (int c : part) quota[c] = level - load[c] + (left > 0 ? 1 : 0), left -= left > 0 ? 1 : 0;
+    int c = 0;
+    long long room = quota[0];
+    for (size_t t = n_bulk; t < tasks.size(); ++t) {
+      const Task& tk = tasks[t];
+      int j = 0, slot = 0;
+      while (j < tk.tiles) {
+        while (room == 0 && c + 1 < G) room = quota[++c];
+        const int take = (int)std::min<long long>(tk.tiles - j, room > 0 ? room : tk.tiles - j);
+        lists[c].push_back(Seg{tk.b | (slot << 24), tk.rb, j, j + take});
+        j += take, room -= std::min<long long>(room, take), ++slot;
+      }
+      plan->nseg[(size_t)tk.b * rb_per_pair + tk.rb] = (uint8_t)slot;
+      plan->splits = std::max(plan->splits, slot);
+    }
+  }
+  plan->begin.assign(1, 0);
+  for (int c = 0; c < G; ++c) {
+    if (lists[c].empty()) continue;   // fewer units than CTAs x min_share: idle CTAs are not launched
+    plan->segs.insert(plan->segs.end(), lists[c].begin(), lists[c].end());
+    plan->begin.push_back((int32_t)plan->segs.size());
+  }
+  plan->grid = (int)plan->begin.size() - 1;
+}
+
 int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, int D, int HW_a, int HW_q, const int32_t* roi_a,
               const int32_t* roi_q, const int32_t* n_a, const int32_t* n_q, int cap_a, int cap_q, int mode, int32_t* out_idx,
               float* out_dist, cudaStream_t st) {
   ORYON_REQUIRE(h && feat_a && feat_q && out_idx && out_dist, "oryon_match_nn: null argument");
   ORYON_REQUIRE(B > 0 && D > 0 && HW_a > 0 && HW_q > 0, "oryon_match_nn: B, D, HW must be positive");
   ORYON_REQUIRE(D <= 256, "oryon_match_nn: D=%d not supported (max 256)", D);
+  ORYON_REQUIRE(B < (1 << 24), "oryon_match_nn: B=%d pairs per call not supported", B);
   ORYON_REQUIRE((roi_a == nullptr) == (n_a == nullptr) && (roi_q == nullptr) == (n_q == nullptr),
                 "oryon_match_nn: roi_x and n_x must both be given or both be NULL");
   ORYON_REQUIRE(mode == ORYON_MATCH_TC_REFINED || mode == ORYON_MATCH_EXACT_FP32, "oryon_match_nn: unknown mode %d", mode);
@@ -744,7 +1001,20 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     pa.meta = d_meta;
     pa.D = D, pa.D4 = D4, pa.Dpad = Dpad;
     h->span_begin(KID_PREP, st);
-    if (!roi_a && !roi_q && (HW_a % 2) == 0 && (HW_q % 2) == 0) {
+    static const bool prep_v1 = std::getenv("ORYON_PREP_V1") != nullptr;   // A/B switch: the first dense kernel
+    const bool dense = !roi_a && !roi_q && (HW_a % 2) == 0 && (HW_q % 2) == 0;
+    if (dense && !prep_v1 && (D == 32 || D == 64 || D == 128 || D == 256) && Dpad == D) {
+      const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, B, 2);
+      const size_t smem = (size_t)kPrepPix * (D + 4) * sizeof(float);
+      auto launch = [&](auto kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) kern<<<grid, 256, smem, st>>>(pa);
+        return e;
+      };
+      cudaError_t e = D == 32 ? launch(prep_dense2_kernel<1>) : D == 64 ? launch(prep_dense2_kernel<2>)
+                    : D == 128 ? launch(prep_dense2_kernel<4>) : launch(prep_dense2_kernel<8>);
+      ORYON_CUDA_CHECK(e);
+    } else if (dense) {
       const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, B, 2);
       const size_t smem = (size_t)D * (kPrepPix + 1) * sizeof(float);
       ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -779,16 +1049,30 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
 
   // ---- tensor-core pass ----
   const int rb_per_pair = npad_a / kCtaRows;
-  const int tiles_max = npad_q / tile_n;
-  const int halves = kEpiSets;   // candidate lists per (row, split): one per epilogue warp set
-  int splits = 1;
-  if (B * rb_per_pair < h->sm_count) splits = std::min({kMaxSplits, tiles_max, (h->sm_count + B * rb_per_pair - 1) / (B * rb_per_pair)});
-  splits = std::max(splits, 1);
+  const int halves = kEpiSets;   // candidate lists per (row, segment): one per epilogue warp set
+  static const int plan_kind = [] {
+    const char* e = std::getenv("ORYON_MATCH_PLAN");   // A/B switch: "contiguous" | "whole" (default: hybrid)
+    return !e ? kPlanHybrid : !strcmp(e, "contiguous") ? kPlanContiguous : !strcmp(e, "whole") ? kPlanWholeTasks : kPlanHybrid;
+  }();
+  TcPlan plan;
+  build_tc_plan(meta, rb_per_pair, h->sm_count, plan_kind, &plan);
+  const int splits = std::max(plan.splits, 1);
   const size_t slots = (size_t)B * splits * halves * npad_a;
   if ((rc = h->cand.reserve(slots * (4 + 4 + 4 * kCandCap), st))) return rc;
   if ((rc = h->overflow_rows.reserve((size_t)B * npad_a * 4, st))) return rc;
+  // one upload: [seg_begin (grid + 1) | segments | segments per row block]
+  const size_t off_segs = (sizeof(int32_t) * plan.begin.size() + 15) & ~size_t(15);
+  const size_t off_nseg = off_segs + sizeof(Seg) * plan.segs.size();
+  std::vector<uint8_t> blob(off_nseg + plan.nseg.size());
+  memcpy(blob.data(), plan.begin.data(), sizeof(int32_t) * plan.begin.size());
+  if (!plan.segs.empty()) memcpy(blob.data() + off_segs, plan.segs.data(), sizeof(Seg) * plan.segs.size());
+  memcpy(blob.data() + off_nseg, plan.nseg.data(), plan.nseg.size());
+  if ((rc = h->match_plan.reserve(blob.size(), st))) return rc;
+  ORYON_CUDA_CHECK(cudaMemcpyAsync(h->match_plan.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
   TcArgs ta;
   ta.meta = d_meta;
+  ta.seg_begin = h->match_plan.as<int32_t>();
+  ta.segs = reinterpret_cast<const Seg*>(h->match_plan.as<char>() + off_segs);
   ta.B = B, ta.npad_a = npad_a, ta.npad_q = npad_q, ta.splits = splits;
   ta.cand_m = h->cand.as<float>();
   ta.cand_cnt = reinterpret_cast<int32_t*>(ta.cand_m + slots);
@@ -798,8 +1082,11 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   CUtensorMap tma, tmq;
   if ((rc = make_rows_tensor_map(h, &tma, h->rows16_a.ptr, B * npad_a, Dpad, kb_elems, kTileM))) return rc;
   if ((rc = make_rows_tensor_map(h, &tmq, h->rows16_q.ptr, B * npad_q, Dpad, kb_elems, tile_n))) return rc;
-  const int grid = std::min(h->sm_count, B * rb_per_pair * splits);
-  if (sw64) {
+  const int grid = plan.grid;
+  if (grid == 0) {
+    // no (row block, query tile) unit at all: every pair has an empty side, the refine pass writes (-1, inf)
+    rc = ORYON_OK;
+  } else if (sw64) {
     rc = launch_tc<32, 1, 8>(h, tma, tmq, ta, grid, st);
   } else {
     switch (num_kb) {
@@ -810,12 +1097,13 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     }
   }
   if (rc) return rc;
-  ++h->last_launches;
+  if (grid) ++h->last_launches;
 
   RefineArgs ra;
   ra.rows32_a = ea.rows32_a, ra.rows32_q = ea.rows32_q;
   ra.meta = d_meta;
   ra.cand_m = ta.cand_m, ra.cand_cnt = ta.cand_cnt, ra.cand_chunk = ta.cand_chunk;
+  ra.nseg = reinterpret_cast<const uint8_t*>(h->match_plan.as<char>() + off_nseg);
   ra.B = B, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = splits * halves, ra.cap_a = cap_a;
   ra.ambiguity = kAmbiguity;
   ra.out_idx = out_idx, ra.out_dist = out_dist;
@@ -823,10 +1111,12 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   ra.overflow_count = d_overflow_count;
   ra.stats = d_stats;
   {
-    const int warps_needed = B * npad_a;
+    static const bool refine_v1 = std::getenv("ORYON_REFINE_V1") != nullptr;   // A/B switch: one warp per row
+    const int warps_needed = refine_v1 ? B * npad_a : (B * npad_a + 3) / 4;
     const int blocks = std::min((warps_needed + 7) / 8, h->sm_count * 16);
     h->span_begin(KID_REFINE, st);
-    refine_rows_kernel<<<blocks, 256, 0, st>>>(ra);
+    if (refine_v1) refine_rows_kernel<<<blocks, 256, 0, st>>>(ra);
+    else refine_rows4_kernel<<<blocks, 256, 0, st>>>(ra);
     h->span_end(st);
     ORYON_CUDA_CHECK(cudaGetLastError());
     ++h->last_launches;
@@ -839,6 +1129,28 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     ORYON_CUDA_CHECK(cudaGetLastError());
     ++h->last_launches;
   }
+  return ORYON_OK;
+}
+
+int plan_debug(const int32_t* n_a, const int32_t* n_q, int B, int sm_count, int kind, int32_t* segs_out, int seg_cap,
+               int32_t* begin_out, int32_t* info_out) {
+  ORYON_REQUIRE(n_a && n_q && B > 0 && B < (1 << 24) && sm_count > 0 && begin_out && info_out && (segs_out || seg_cap == 0) &&
+                    kind >= kPlanHybrid && kind <= kPlanWholeTasks,
+                "oryon_match_plan: bad argument");
+  std::vector<PairMeta> meta(B);
+  int max_a = 0;
+  for (int b = 0; b < B; ++b) meta[b].n_a = n_a[b], meta[b].n_q = n_q[b], max_a = std::max(max_a, n_a[b]);
+  TcPlan plan;
+  build_tc_plan(meta, std::max(1, round_up(max_a, kCtaRows) / kCtaRows), sm_count, kind, &plan);
+  info_out[0] = plan.grid, info_out[1] = plan.splits, info_out[2] = (int32_t)plan.segs.size();
+  for (int c = 0; c <= plan.grid; ++c) begin_out[c] = plan.begin[c];
+  ORYON_REQUIRE((int)plan.segs.size() <= seg_cap || seg_cap == 0, "oryon_match_plan: %zu segments, capacity %d", plan.segs.size(), seg_cap);
+  if (seg_cap)
+    for (size_t i = 0; i < plan.segs.size(); ++i) {
+      const Seg& g = plan.segs[i];
+      int32_t* o = segs_out + 5 * i;
+      o[0] = g.b_slot & 0xFFFFFF, o[1] = g.rb, o[2] = g.j0, o[3] = g.j1, o[4] = g.b_slot >> 24;
+    }
   return ORYON_OK;
 }
 

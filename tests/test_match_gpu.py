@@ -105,7 +105,7 @@ def test_host_tensors_are_accepted_and_result_returns_to_host():
 
 
 @pytest.mark.parametrize("D,h,w,B", [(128, 40, 40, 3), (256, 24, 24, 2), (17, 20, 30, 2), (1, 16, 16, 1), (64, 33, 17, 2), (96, 31, 9, 1),
-                                     (200, 16, 16, 1)])
+                                     (200, 16, 16, 1), (32, 24, 26, 2), (64, 30, 34, 2)])
 def test_dense_batched_vs_oracle(D, h, w, B):
     need_gpu()
     fa, fq, perm = synth.permuted_feature_batch(7 + D, B, D, h, w, noise=0.3)
