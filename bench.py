@@ -399,9 +399,12 @@ def main():
             "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         flops, bytes_ = algorithmic_work(B, D, n, n)
         cfg_name = {(128, 120, 160): "config2", (256, 240, 320): "config5"}.get((D, H, W), "custom")
+        # the library may cut the batch into chunks (one match_tc launch each, pipelined against prep / refine on side streams):
+        # a launch processes flops / launches_per_step, so achieved = flops of a step / summed launch durations of a step
         tc_ms, tc_n = prof.get("match_tc", (0.0, 0))
+        tc_per_step = max(tc_n // max(args.steps, 1), 1)
         tc_avg = tc_ms / max(tc_n, 1)
-        achieved_tf = flops / (tc_avg * 1e-3) / 1e12 if tc_avg > 0 else None
+        achieved_tf = flops / (tc_avg * tc_per_step * 1e-3) / 1e12 if tc_avg > 0 else None
         hbm_peak = peaks.get("hbm_gbs") or 6650.0
         line = {
             "metric": "image-pairs/sec", "value": world * B * args.steps / (ms_max * 1e-3), "unit": "pairs/s", "n_gpus": world,
@@ -421,7 +424,7 @@ def main():
                          "frac": (achieved_tf / peak_tf if achieved_tf else None), "traffic": NCU_TRAFFIC_BYTES if (B, D, n) == (32, 128, 19200) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch "
                                            "(profiles/r01_match_tc_ncu_v4.md)", "peak_source": peak_src,
-                         "algorithmic_flops_per_launch": flops, "launch_ms": tc_avg,
+                         "algorithmic_flops_per_launch": flops / tc_per_step, "launch_ms": tc_avg, "launches_per_step": tc_per_step,
                          "hbm": {"algorithmic_bytes_per_step": bytes_, "achieved_gbs": bytes_ / (ms_max / args.steps * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": bytes_ / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak}},
         }

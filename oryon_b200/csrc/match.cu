@@ -601,6 +601,7 @@ struct RefineArgs {
   const uint32_t* cand_chunk;
   const uint8_t* nseg;         // [B][npad_a / kCtaRows] candidate lists (segments) per anchor row block
   int B, npad_a, npad_q, D4, splits, cap_a;
+  int item_base;               // first pair of this launch * npad_a (overflow rows are packed with batch-wide pair indices)
   float ambiguity;
   int32_t* out_idx;
   float* out_dist;
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
       overflow |= a.cand_cnt[slot] > kCandCap;
     }
     if (overflow) {
-      if (lane == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = item;
+      if (lane == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = a.item_base + item;
       ++n_over;
       continue;
     }
@@ -716,7 +717,7 @@ __global__ void __launch_bounds__(256) refine_rows4_kernel(RefineArgs a) {
       overflow |= a.cand_cnt[slot] > kCandCap;
     }
     if (overflow) {
-      if (sub == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = item, ++n_over;
+      if (sub == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = a.item_base + item, ++n_over;
       continue;
     }
     if (sub == 0) ++n_rows;
@@ -981,54 +982,55 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   const int kb_elems = sw64 ? 32 : 64;
   const int Dpad = round_up(D, kb_elems);
   const int num_kb = Dpad / kb_elems;
-  const int tile_n = kTileN;
-  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), tile_n);
+  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), kTileN);
 
   if ((rc = h->rows16_a.reserve((size_t)B * npad_a * Dpad * 2, st))) return rc;
   if ((rc = h->rows16_q.reserve((size_t)B * npad_q * Dpad * 2, st))) return rc;
   if ((rc = h->rows32_a.reserve((size_t)B * npad_a * D4 * 4, st))) return rc;
   if ((rc = h->rows32_q.reserve((size_t)B * npad_q * D4 * 4, st))) return rc;
 
-  {
+  // ---- prep of pairs [b0, b0 + nb) on `stream` ----
+  auto launch_prep = [&](int b0, int nb, cudaStream_t stream) -> int {
     PrepArgs pa;
-    pa.feat[0] = feat_a, pa.feat[1] = feat_q;
-    pa.roi[0] = roi_a, pa.roi[1] = roi_q;
+    pa.feat[0] = feat_a + (size_t)b0 * D * HW_a, pa.feat[1] = feat_q + (size_t)b0 * D * HW_q;
+    pa.roi[0] = roi_a ? roi_a + (size_t)b0 * cap_a : nullptr, pa.roi[1] = roi_q ? roi_q + (size_t)b0 * cap_q : nullptr;
     pa.hw[0] = HW_a, pa.hw[1] = HW_q;
     pa.cap[0] = cap_a, pa.cap[1] = cap_q;
     pa.npad[0] = npad_a, pa.npad[1] = npad_q;
-    pa.rows16[0] = h->rows16_a.as<__half>(), pa.rows16[1] = h->rows16_q.as<__half>();
-    pa.rows32[0] = h->rows32_a.as<float>(), pa.rows32[1] = h->rows32_q.as<float>();
-    pa.meta = d_meta;
+    pa.rows16[0] = h->rows16_a.as<__half>() + (size_t)b0 * npad_a * Dpad, pa.rows16[1] = h->rows16_q.as<__half>() + (size_t)b0 * npad_q * Dpad;
+    pa.rows32[0] = h->rows32_a.as<float>() + (size_t)b0 * npad_a * D4, pa.rows32[1] = h->rows32_q.as<float>() + (size_t)b0 * npad_q * D4;
+    pa.meta = d_meta + b0;
     pa.D = D, pa.D4 = D4, pa.Dpad = Dpad;
-    h->span_begin(KID_PREP, st);
+    h->span_begin(KID_PREP, stream);
     static const bool prep_v1 = std::getenv("ORYON_PREP_V1") != nullptr;   // A/B switch: the first dense kernel
     const bool dense = !roi_a && !roi_q && (HW_a % 2) == 0 && (HW_q % 2) == 0;
     if (dense && !prep_v1 && (D == 32 || D == 64 || D == 128 || D == 256) && Dpad == D) {
-      const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, B, 2);
+      const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, nb, 2);
       const size_t smem = (size_t)kPrepPix * (D + 4) * sizeof(float);
       auto launch = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) kern<<<grid, 256, smem, st>>>(pa);
+        if (e == cudaSuccess) kern<<<grid, 256, smem, stream>>>(pa);
         return e;
       };
       cudaError_t e = D == 32 ? launch(prep_dense2_kernel<1>) : D == 64 ? launch(prep_dense2_kernel<2>)
                     : D == 128 ? launch(prep_dense2_kernel<4>) : launch(prep_dense2_kernel<8>);
       ORYON_CUDA_CHECK(e);
     } else if (dense) {
-      const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, B, 2);
+      const dim3 grid((std::max(max_a, max_q) + kPrepPix - 1) / kPrepPix, nb, 2);
       const size_t smem = (size_t)D * (kPrepPix + 1) * sizeof(float);
       ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prep_dense_kernel<<<grid, 256, smem, st>>>(pa);
+      prep_dense_kernel<<<grid, 256, smem, stream>>>(pa);
     } else {
-      const dim3 grid((std::max(max_a, max_q) + 31) / 32, B, 2);
+      const dim3 grid((std::max(max_a, max_q) + 31) / 32, nb, 2);
       const size_t smem = (size_t)D * 33 * sizeof(float);
       ORYON_CUDA_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prep_rows_kernel<<<grid, 256, smem, st>>>(pa);
+      prep_rows_kernel<<<grid, 256, smem, stream>>>(pa);
     }
-    h->span_end(st);
+    h->span_end(stream);
     ORYON_CUDA_CHECK(cudaGetLastError());
     ++h->last_launches;
-  }
+    return ORYON_OK;
+  };
 
   ExactArgs ea;
   ea.rows32_a = h->rows32_a.as<float>(), ea.rows32_q = h->rows32_q.as<float>();
@@ -1037,6 +1039,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   ea.out_idx = out_idx, ea.out_dist = out_dist;
 
   if (mode == ORYON_MATCH_EXACT_FP32 || max_q == 0) {
+    if ((rc = launch_prep(0, B, st))) return rc;
     ea.row_list = nullptr, ea.n_items_dev = nullptr, ea.n_items_host = B * npad_a;
     const int blocks = std::min((B * npad_a + 63) / 64, h->sm_count * 8);
     h->span_begin(KID_EXACT, st);
@@ -1048,81 +1051,100 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   }
 
   // ---- tensor-core pass ----
-  const int rb_per_pair = npad_a / kCtaRows;
-  const int halves = kEpiSets;   // candidate lists per (row, segment): one per epilogue warp set
+  // (Tried and measured, profiles/r01_match_pipelining_experiment_run35.json: cutting the batch into chunks of pairs and running
+  // the prep of the next chunk / the refine of the previous one on side streams next to the persistent tensor-core CTAs does not
+  // shorten the step -- match_tc slows down by what the co-runners hide.  The three launchers below still take a pair range.)
   static const int plan_kind = [] {
     const char* e = std::getenv("ORYON_MATCH_PLAN");   // A/B switch: "contiguous" | "whole" (default: hybrid)
     return !e ? kPlanHybrid : !strcmp(e, "contiguous") ? kPlanContiguous : !strcmp(e, "whole") ? kPlanWholeTasks : kPlanHybrid;
   }();
-  TcPlan plan;
-  build_tc_plan(meta, rb_per_pair, h->sm_count, plan_kind, &plan);
-  const int splits = std::max(plan.splits, 1);
-  const size_t slots = (size_t)B * splits * halves * npad_a;
-  if ((rc = h->cand.reserve(slots * (4 + 4 + 4 * kCandCap), st))) return rc;
+  const int rb_per_pair = npad_a / kCtaRows;
+  const int halves = kEpiSets;   // candidate lists per (row, segment): one per epilogue warp set
+  struct Chunk {   // a range of pairs with its work decomposition and its slice of the candidate / plan buffers
+    int b0, nb, splits;
+    TcPlan plan;
+    size_t slot_base, slots, off_begin, off_segs, off_nseg;
+  };
+  Chunk all;
+  all.b0 = 0, all.nb = B;
+  build_tc_plan(meta, rb_per_pair, h->sm_count, plan_kind, &all.plan);
+  all.splits = std::max(all.plan.splits, 1);
+  all.slot_base = 0, all.slots = (size_t)B * all.splits * halves * npad_a;
+  all.off_begin = 0;
+  all.off_segs = (sizeof(int32_t) * all.plan.begin.size() + 15) & ~size_t(15);
+  all.off_nseg = all.off_segs + sizeof(Seg) * all.plan.segs.size();
+  const size_t slots_total = all.slots;
+  if ((rc = h->cand.reserve(slots_total * (4 + 4 + 4 * kCandCap), st))) return rc;
   if ((rc = h->overflow_rows.reserve((size_t)B * npad_a * 4, st))) return rc;
-  // one upload: [seg_begin (grid + 1) | segments | segments per row block]
-  const size_t off_segs = (sizeof(int32_t) * plan.begin.size() + 15) & ~size_t(15);
-  const size_t off_nseg = off_segs + sizeof(Seg) * plan.segs.size();
-  std::vector<uint8_t> blob(off_nseg + plan.nseg.size());
-  memcpy(blob.data(), plan.begin.data(), sizeof(int32_t) * plan.begin.size());
-  if (!plan.segs.empty()) memcpy(blob.data() + off_segs, plan.segs.data(), sizeof(Seg) * plan.segs.size());
-  memcpy(blob.data() + off_nseg, plan.nseg.data(), plan.nseg.size());
+  // one upload: [first segment of every CTA | segments | candidate lists per row block]
+  std::vector<uint8_t> blob(all.off_nseg + all.plan.nseg.size());
+  memcpy(blob.data() + all.off_begin, all.plan.begin.data(), sizeof(int32_t) * all.plan.begin.size());
+  if (!all.plan.segs.empty()) memcpy(blob.data() + all.off_segs, all.plan.segs.data(), sizeof(Seg) * all.plan.segs.size());
+  memcpy(blob.data() + all.off_nseg, all.plan.nseg.data(), all.plan.nseg.size());
   if ((rc = h->match_plan.reserve(blob.size(), st))) return rc;
   ORYON_CUDA_CHECK(cudaMemcpyAsync(h->match_plan.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
-  TcArgs ta;
-  ta.meta = d_meta;
-  ta.seg_begin = h->match_plan.as<int32_t>();
-  ta.segs = reinterpret_cast<const Seg*>(h->match_plan.as<char>() + off_segs);
-  ta.B = B, ta.npad_a = npad_a, ta.npad_q = npad_q, ta.splits = splits;
-  ta.cand_m = h->cand.as<float>();
-  ta.cand_cnt = reinterpret_cast<int32_t*>(ta.cand_m + slots);
-  ta.cand_chunk = reinterpret_cast<uint32_t*>(ta.cand_cnt + slots);
-  ta.ambiguity = kAmbiguity;
+  float* cand_m = h->cand.as<float>();
+  int32_t* cand_cnt = reinterpret_cast<int32_t*>(cand_m + slots_total);
+  uint32_t* cand_chunk = reinterpret_cast<uint32_t*>(cand_cnt + slots_total);
 
-  CUtensorMap tma, tmq;
-  if ((rc = make_rows_tensor_map(h, &tma, h->rows16_a.ptr, B * npad_a, Dpad, kb_elems, kTileM))) return rc;
-  if ((rc = make_rows_tensor_map(h, &tmq, h->rows16_q.ptr, B * npad_q, Dpad, kb_elems, tile_n))) return rc;
-  const int grid = plan.grid;
-  if (grid == 0) {
-    // no (row block, query tile) unit at all: every pair has an empty side, the refine pass writes (-1, inf)
-    rc = ORYON_OK;
-  } else if (sw64) {
-    rc = launch_tc<32, 1, 8>(h, tma, tmq, ta, grid, st);
-  } else {
-    switch (num_kb) {
-      case 1: rc = launch_tc<64, 1, 8>(h, tma, tmq, ta, grid, st); break;
-      case 2: rc = launch_tc<64, 2, 8>(h, tma, tmq, ta, grid, st); break;
-      case 3: rc = launch_tc<64, 3, 6>(h, tma, tmq, ta, grid, st); break;
-      default: rc = launch_tc<64, 4, 5>(h, tma, tmq, ta, grid, st); break;
+  auto launch_match = [&](const Chunk& k, cudaStream_t stream) -> int {
+    if (k.plan.grid == 0) return ORYON_OK;   // no (row block, query tile) unit: the refine pass writes (-1, inf)
+    TcArgs ta;
+    ta.meta = d_meta + k.b0;
+    ta.seg_begin = reinterpret_cast<const int32_t*>(h->match_plan.as<char>() + k.off_begin);
+    ta.segs = reinterpret_cast<const Seg*>(h->match_plan.as<char>() + k.off_segs);
+    ta.B = k.nb, ta.npad_a = npad_a, ta.npad_q = npad_q, ta.splits = k.splits;
+    ta.cand_m = cand_m + k.slot_base, ta.cand_cnt = cand_cnt + k.slot_base, ta.cand_chunk = cand_chunk + k.slot_base * kCandCap;
+    ta.ambiguity = kAmbiguity;
+    CUtensorMap tma, tmq;
+    int r;
+    if ((r = make_rows_tensor_map(h, &tma, h->rows16_a.as<__half>() + (size_t)k.b0 * npad_a * Dpad, k.nb * npad_a, Dpad, kb_elems, kTileM))) return r;
+    if ((r = make_rows_tensor_map(h, &tmq, h->rows16_q.as<__half>() + (size_t)k.b0 * npad_q * Dpad, k.nb * npad_q, Dpad, kb_elems, kTileN))) return r;
+    if (sw64) {
+      r = launch_tc<32, 1, 8>(h, tma, tmq, ta, k.plan.grid, stream);
+    } else {
+      switch (num_kb) {
+        case 1: r = launch_tc<64, 1, 8>(h, tma, tmq, ta, k.plan.grid, stream); break;
+        case 2: r = launch_tc<64, 2, 8>(h, tma, tmq, ta, k.plan.grid, stream); break;
+        case 3: r = launch_tc<64, 3, 6>(h, tma, tmq, ta, k.plan.grid, stream); break;
+        default: r = launch_tc<64, 4, 5>(h, tma, tmq, ta, k.plan.grid, stream); break;
+      }
     }
-  }
-  if (rc) return rc;
-  if (grid) ++h->last_launches;
+    if (r) return r;
+    ++h->last_launches;
+    return ORYON_OK;
+  };
 
-  RefineArgs ra;
-  ra.rows32_a = ea.rows32_a, ra.rows32_q = ea.rows32_q;
-  ra.meta = d_meta;
-  ra.cand_m = ta.cand_m, ra.cand_cnt = ta.cand_cnt, ra.cand_chunk = ta.cand_chunk;
-  ra.nseg = reinterpret_cast<const uint8_t*>(h->match_plan.as<char>() + off_nseg);
-  ra.B = B, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = splits * halves, ra.cap_a = cap_a;
-  ra.ambiguity = kAmbiguity;
-  ra.out_idx = out_idx, ra.out_dist = out_dist;
-  ra.overflow_rows = h->overflow_rows.as<int32_t>();
-  ra.overflow_count = d_overflow_count;
-  ra.stats = d_stats;
-  {
+  auto launch_refine = [&](const Chunk& k, cudaStream_t stream) -> int {
+    RefineArgs ra;
+    ra.rows32_a = h->rows32_a.as<float>() + (size_t)k.b0 * npad_a * D4, ra.rows32_q = h->rows32_q.as<float>() + (size_t)k.b0 * npad_q * D4;
+    ra.meta = d_meta + k.b0;
+    ra.cand_m = cand_m + k.slot_base, ra.cand_cnt = cand_cnt + k.slot_base, ra.cand_chunk = cand_chunk + k.slot_base * kCandCap;
+    ra.nseg = reinterpret_cast<const uint8_t*>(h->match_plan.as<char>() + k.off_nseg);
+    ra.B = k.nb, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = k.splits * halves, ra.cap_a = cap_a;
+    ra.item_base = k.b0 * npad_a;
+    ra.ambiguity = kAmbiguity;
+    ra.out_idx = out_idx + (size_t)k.b0 * cap_a, ra.out_dist = out_dist + (size_t)k.b0 * cap_a;
+    ra.overflow_rows = h->overflow_rows.as<int32_t>();
+    ra.overflow_count = d_overflow_count;
+    ra.stats = d_stats;
     static const bool refine_v1 = std::getenv("ORYON_REFINE_V1") != nullptr;   // A/B switch: one warp per row
-    const int warps_needed = refine_v1 ? B * npad_a : (B * npad_a + 3) / 4;
+    const int warps_needed = refine_v1 ? k.nb * npad_a : (k.nb * npad_a + 3) / 4;
     const int blocks = std::min((warps_needed + 7) / 8, h->sm_count * 16);
-    h->span_begin(KID_REFINE, st);
-    if (refine_v1) refine_rows_kernel<<<blocks, 256, 0, st>>>(ra);
-    else refine_rows4_kernel<<<blocks, 256, 0, st>>>(ra);
-    h->span_end(st);
+    h->span_begin(KID_REFINE, stream);
+    if (refine_v1) refine_rows_kernel<<<blocks, 256, 0, stream>>>(ra);
+    else refine_rows4_kernel<<<blocks, 256, 0, stream>>>(ra);
+    h->span_end(stream);
     ORYON_CUDA_CHECK(cudaGetLastError());
     ++h->last_launches;
-  }
+    return ORYON_OK;
+  };
+
+  if ((rc = launch_prep(0, B, st))) return rc;
+  if ((rc = launch_match(all, st))) return rc;
+  if ((rc = launch_refine(all, st))) return rc;
   {
-    ea.row_list = ra.overflow_rows, ea.n_items_dev = d_overflow_count, ea.n_items_host = 0;
+    ea.row_list = h->overflow_rows.as<int32_t>(), ea.n_items_dev = d_overflow_count, ea.n_items_host = 0;
     h->span_begin(KID_EXACT, st);
     exact_rows_kernel<<<h->sm_count * 2, 256, 0, st>>>(ea);
     h->span_end(st);
