@@ -118,7 +118,7 @@ def cpu_port_sample(rows, threads, D=WORKLOAD["D"], n=WORKLOAD["H"] * WORKLOAD["
     return best
 
 
-NCU_TRAFFIC_BYTES = 330.893056e6 + 27.174656e6   # profiles/r01_match_tc_ncu_v4.md (config 2, one launch)
+NCU_TRAFFIC_BYTES = 331.953664e6 + 25.663232e6   # profiles/r01_match_kernels_ncu_run38.md (config 2, one launch)
 
 
 def full_path_measure(pairs, local, peaks, precision=3):
@@ -423,7 +423,7 @@ def main():
             "roofline": {"kernel": "match_tc_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (achieved_tf / peak_tf if achieved_tf else None), "traffic": NCU_TRAFFIC_BYTES if (B, D, n) == (32, 128, 19200) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch "
-                                           "(profiles/r01_match_tc_ncu_v4.md)", "peak_source": peak_src,
+                                           "(profiles/r01_match_kernels_ncu_run38.md)", "peak_source": peak_src,
                          "algorithmic_flops_per_launch": flops / tc_per_step, "launch_ms": tc_avg, "launches_per_step": tc_per_step,
                          "hbm": {"algorithmic_bytes_per_step": bytes_, "achieved_gbs": bytes_ / (ms_max / args.steps * 1e-3) / 1e9,
                                  "peak_gbs": hbm_peak, "frac": bytes_ / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak}},

@@ -65,6 +65,13 @@ def mask_postproc(logits: Optional[Tensor], gt: Optional[Tensor], size: Tuple[in
     return out
 
 
+def format_pred_line(id_a: str, id_q: str, mask_a_iou, mask_q_iou, pred_pose: np.ndarray) -> str:
+    """The prediction-CSV wire format of the reference (pipeline.py:490-497): ``str()`` of the numpy scalars as they are
+    (float32 poses and IoUs print their shortest float32 representation)."""
+    pose = " ".join([str(n) for n in pred_pose[:3, :].flatten()])
+    return ",".join([id_a, id_q, pose, str(mask_a_iou), str(mask_q_iou)]) + "\n"
+
+
 class FPM_Pipeline:
     def __init__(self, args, test_model: bool = False, *, model: Optional[Oryon] = None, pointdsc_solver=None, evaluator=None):
         self.args = args
@@ -173,8 +180,7 @@ class FPM_Pipeline:
     def add_pred_pose(self, id_a: str, id_q: str, mask_a_iou, mask_q_iou, pred_pose: np.ndarray):
         """One CSV line ``id_a,id_q,<12 floats>,iou_a,iou_q`` (pipeline.py:490-497; read back by
         scripts/evaluation/compute_metrics.py:14-49)."""
-        pose = " ".join([str(n) for n in pred_pose[:3, :].flatten()])
-        line = ",".join([id_a, id_q, pose, str(mask_a_iou), str(mask_q_iou)]) + "\n"
+        line = format_pred_line(id_a, id_q, mask_a_iou, mask_q_iou, pred_pose)
         if self.pred_file is not None:
             self.pred_file.write(line)
         return line

@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Test-loop entry point: the B200 counterpart of the reference's ``run_test.py`` (:12-42) without hydra / Lightning.
+
+    python run_test.py --pairs 2000 --batch 32 --out predictions.csv
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 run_test.py --pairs 2000
+
+What the reference does in one process -- ``Trainer.test(system, test_data)``: ``on_test_start``, ``test_step`` per batch,
+``on_test_end`` (pipeline.py:296-370) -- is done here on every rank for its own contiguous share of the pair list
+(``sharding.shard_pairs``: no padding, no duplicates), with no collective on the data path; at the end ONE ``all_gather`` of
+16-float result rows (``sharding.gather_rows``; NCCL over NVLink on GPUs) brings every pair's pose / IoUs / status to all
+ranks and rank 0 writes the single prediction CSV in pair order, in the reference's wire format
+(``pipeline.format_pred_line``; scripts/evaluation/compute_metrics.py:14-49 reads it back).  The reference itself has no
+such gather: under several GPUs it would leave one partial CSV per process.
+
+No dataset, checkpoint or BPE vocabulary exists offline, so the pairs are synthetic (``synth.synthetic_batch``: 224x224 RGB,
+480x640 depth related by a planted rigid motion, NOCS intrinsics) and the weights seeded random ones of the reference's
+architecture; with real data the same loop runs over ``GpuCollate`` batches.  Prints one JSON line
+(rank 0): pairs, pairs/s (barrier + synchronize on both sides, max over ranks), status counts.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from typing import Callable, Dict, List, Optional, Sequence
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from oryon_b200 import sharding  # noqa: E402
+
+
+def pair_ids(pair_index: int) -> tuple:
+    """Instance ids ``'scene image object'`` of a synthetic pair, in the form the offline scorer splits
+    (scripts/evaluation/compute_metrics.py:30-33; the reference's ids come from instance_list.txt, datasets.py:421-442)."""
+    return f"0001 {pair_index:06d} 1", f"0002 {pair_index:06d} 1"
+
+
+def run_sharded(n_pairs: int, batch_size: int, step_fn: Callable[[Sequence[int]], List[dict]], *, out_path: Optional[str] = None,
+                device: Optional[torch.device] = None, sync: Optional[Callable[[], None]] = None) -> Dict:
+    """The sharded test loop.  ``step_fn(pair_indices)`` returns one record per pair with the keys ``status``, ``iou_a``,
+    ``iou_q``, ``pred_pose_rel`` (``FPM_Pipeline.test_step``'s records).  Returns, on every rank, the gathered table in pair
+    order, the status counts and the loop time (max over ranks); rank 0 also writes ``out_path``."""
+    from oryon_b200.pipeline import format_pred_line
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    mine = sharding.shard_pairs(n_pairs, rank, world)
+
+    def barrier():
+        if sync is not None:
+            sync()
+        if world > 1:
+            dist.barrier()
+
+    local = []
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(mine.start, mine.stop, batch_size):
+        idx = list(range(s, min(s + batch_size, mine.stop)))
+        rows = step_fn(idx)
+        if len(rows) != len(idx):
+            raise RuntimeError(f"step_fn returned {len(rows)} records for {len(idx)} pairs")
+        local.append(sharding.encode_rows(idx, rows))
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+    local_t = torch.cat(local) if local else torch.zeros(0, sharding.ROW_FLOATS, dtype=torch.float64)
+    if device is not None:
+        local_t, dt = local_t.to(device), dt.to(device)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    table = sharding.gather_rows(local_t, n_pairs).cpu()       # the only collective that carries results
+    records = sharding.decode_rows(table)
+    if rank == 0 and out_path is not None:
+        with open(out_path, "w") as fh:
+            for r in records:
+                id_a, id_q = pair_ids(r["pair_index"])
+                fh.write(format_pred_line(id_a, id_q, np.float32(r["iou_a"]), np.float32(r["iou_q"]), r["pred_pose_rel"].numpy()))
+    counts = {k: sum(r["status"] == k for r in records) for k in sharding.STATUS}
+    return dict(table=table, records=records, status=counts, seconds=float(dt.item()), world=world, rank=rank)
+
+
+def build_pipeline(local_rank: int, precision: int):
+    """``FPM_Pipeline(args, test_model=True)`` (run_test.py:15) on seeded random weights of the reference's architecture."""
+    from oryon_b200 import synth, synth_backbone as sb
+    from oryon_b200.net import Oryon
+    from oryon_b200.pipeline import FPM_Pipeline
+    from oryon_b200.utils.pointdsc.init import PointDSCSolver
+    cfg = synth.POINTDSC_DEFAULT_CFG
+    dev = f"cuda:{local_rank}"
+    model = Oryon(None, dev, state_dict=sb.oryon_state_dict(11), precision=precision)
+    solver = PointDSCSolver(synth.pointdsc_state_dict(300), in_dim=cfg["in_dim"], num_layers=cfg["num_layers"],
+                            num_channels=cfg["num_channels"], num_iterations=cfg["num_iterations"], ratio=cfg["ratio"],
+                            sigma_d=cfg["sigma_d"], k=cfg["k"], nms_radius=cfg["inlier_threshold"], device=dev)
+    args = dict(device=dev, corrs_device="cpu", dataset=dict(img_size=[224, 224], max_corrs=500),
+                model=dict(image_encoder=dict(img_size=[192, 192])),
+                test=dict(mask="oracle", src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
+    return FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver), model
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("--pairs", type=int, default=2000, help="size of the test split (NOCS / TOYL: 2000 pairs)")
+    ap.add_argument("--batch", type=int, default=32, help="configs/config.yaml:17")
+    ap.add_argument("--out", default=None, help="prediction CSV written by rank 0")
+    ap.add_argument("--precision", type=int, default=3, choices=[1, 3], help="GEMM products per algorithmic product (3 = float32-equivalent)")
+    ap.add_argument("--distinct-batches", type=int, default=4, help="synthetic batches generated up front and cycled")
+    ap.add_argument("--seed", type=int, default=1, help="on_test_start seed (utils/misc.py:186-196)")
+    args = ap.parse_args(argv)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("run_test.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oryon_b200 import synth
+    pipe, model = build_pipeline(local, args.precision)
+    batches = []
+    for k in range(args.distinct_batches):
+        b = synth.synthetic_batch(100 + k, args.batch)
+        emb = model.encode_tokens(b.pop("prompt_tokens")[0].cuda())[None]      # one prompt set per batch: cached as the benchmark allows
+        for key in ("anchor", "query"):
+            b[key]["rgb"] = b[key]["rgb"].pin_memory()
+            b[key]["orig_depth"] = torch.stack(b[key]["orig_depth"]).pin_memory()
+        b["prompt_emb_one"] = emb
+        batches.append(b)
+
+    def take(b: dict, n: int) -> dict:
+        """The first n pairs of a generated batch (the last batch of a shard may be short)."""
+        out = dict(prompt_emb=b["prompt_emb_one"].expand(n, -1, -1).contiguous(), instance_id=b["instance_id"][:n], cls_id=b["cls_id"][:n])
+        for key in ("anchor", "query"):
+            out[key] = {k: v[:n] for k, v in b[key].items()}
+        return out
+
+    def step(idx: Sequence[int]) -> List[dict]:
+        b = take(batches[(idx[0] // args.batch) % len(batches)], len(idx))
+        return pipe.test_step(b, idx[0] // args.batch)
+
+    pipe.on_test_start(seed=args.seed + rank)       # per-rank draw sequences; one rank = the reference's order
+    step(list(range(min(args.batch, args.pairs))))  # warm-up: workspaces, arena, clocks
+    pipe.on_test_start(seed=args.seed + rank)
+    res = run_sharded(args.pairs, args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize)
+    pipe.on_test_end()
+    if rank == 0:
+        print(json.dumps({"metric": "image-pairs/sec (whole test loop)", "value": args.pairs / res["seconds"], "unit": "pairs/s",
+                          "n_gpus": world, "pairs": args.pairs, "batch": args.batch, "seconds": res["seconds"], "status": res["status"],
+                          "gemm_precision": args.precision, "data": "synthetic", "csv": args.out,
+                          "config": {"workload": f"{args.pairs} synthetic pairs: 224x224 RGB -> CLIP ViT-L/14@336 + swin_b + fusion + decoder -> "
+                                                 "matching -> lift -> PointDSC; pairs sharded over ranks, one all_gather of result rows"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,22 +1,18 @@
 #!/bin/bash
-# One GPU call: matcher parity with the current defaults, then A/B bench lines: chunk pipelining (ORYON_MATCH_CHUNKS),
-# TMA ring depth (ORYON_MATCH_STAGES8), work decomposition (ORYON_MATCH_PLAN), kernel versions (ORYON_PREP_V1, ORYON_REFINE_V1).
+# One GPU call: matcher parity with the current defaults, then A/B bench lines of the refine kernel variants
+# (ORYON_REFINE_OCC3, ORYON_REFINE_V1), the work decomposition (ORYON_MATCH_PLAN) and the first prep kernel (ORYON_PREP_V1).
 mkdir -p gpurun_out
 B="python bench.py --steps 20 --no-full-path --no-cpu-baseline"
 timeout 300 python -m pytest tests/test_match_gpu.py -x -q -m gpu > gpurun_out/exp_pytest.log 2>&1; echo "pytest default rc=$?" | tee -a gpurun_out/exp_pytest.log
 tail -3 gpurun_out/exp_pytest.log
-timeout 120 $B > gpurun_out/exp_bench_default.json 2> gpurun_out/exp_bench_default.err
-ORYON_MATCH_CHUNKS=1 timeout 120 $B --no-e2e > gpurun_out/exp_bench_chunks1.json 2>/dev/null
-ORYON_MATCH_CHUNKS=1 ORYON_MATCH_STAGES8=1 timeout 120 $B --no-e2e > gpurun_out/exp_bench_chunks1_s8.json 2>/dev/null
-ORYON_MATCH_CHUNKS=2 timeout 120 $B --no-e2e > gpurun_out/exp_bench_chunks2.json 2>/dev/null
-ORYON_MATCH_CHUNKS=8 timeout 120 $B --no-e2e > gpurun_out/exp_bench_chunks8.json 2>/dev/null
-ORYON_MATCH_STAGES8=1 timeout 120 $B --no-e2e > gpurun_out/exp_bench_chunks4_s8.json 2>/dev/null
+timeout 120 $B --no-e2e > gpurun_out/exp_bench_default.json 2> gpurun_out/exp_bench_default.err
+ORYON_REFINE_OCC3=1 timeout 120 $B --no-e2e > gpurun_out/exp_bench_occ3.json 2>/dev/null
+ORYON_REFINE_V1=1 timeout 120 $B --no-e2e > gpurun_out/exp_bench_refv1.json 2>/dev/null
 timeout 120 $B --no-e2e > gpurun_out/exp_bench_default2.json 2>/dev/null
 timeout 120 $B --no-e2e --D 256 --H 240 --W 320 --B 8 --steps 10 > gpurun_out/exp_bench_c5.json 2>/dev/null
-ORYON_MATCH_CHUNKS=1 timeout 120 $B --no-e2e --D 256 --H 240 --W 320 --B 8 --steps 10 > gpurun_out/exp_bench_c5chunks1.json 2>/dev/null
 python - <<'PY'
 import json
-for n in ("default", "chunks1", "chunks1_s8", "chunks2", "chunks8", "chunks4_s8", "default2", "c5", "c5chunks1"):
+for n in ("default", "occ3", "refv1", "default2", "c5"):
     try:
         l = json.loads(open(f"gpurun_out/exp_bench_{n}.json").read().strip().splitlines()[-1])
         print(n, round(l["value"], 1), round(l["ms_per_step"], 4), "ok" if l["results_ok"] else "BAD", {k: round(v, 4) for k, v in l["kernels_ms_per_step"].items()},
