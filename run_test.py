@@ -104,6 +104,10 @@ def build_pipeline(local_rank: int, precision: int):
 
 
 def main(argv=None):
+    # one JSON line on stdout: library banners (NCCL prints its version from C code) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--pairs", type=int, default=2000, help="size of the test split (NOCS / TOYL: 2000 pairs)")
     ap.add_argument("--batch", type=int, default=32, help="configs/config.yaml:17")
@@ -152,11 +156,13 @@ def main(argv=None):
     res = run_sharded(args.pairs, args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize)
     pipe.on_test_end()
     if rank == 0:
-        print(json.dumps({"metric": "image-pairs/sec (whole test loop)", "value": args.pairs / res["seconds"], "unit": "pairs/s",
+        line = json.dumps({"metric": "image-pairs/sec (whole test loop)", "value": args.pairs / res["seconds"], "unit": "pairs/s",
                           "n_gpus": world, "pairs": args.pairs, "batch": args.batch, "seconds": res["seconds"], "status": res["status"],
                           "gemm_precision": args.precision, "data": "synthetic", "csv": args.out,
                           "config": {"workload": f"{args.pairs} synthetic pairs: 224x224 RGB -> CLIP ViT-L/14@336 + swin_b + fusion + decoder -> "
-                                                 "matching -> lift -> PointDSC; pairs sharded over ranks, one all_gather of result rows"}}))
+                                                 "matching -> lift -> PointDSC; pairs sharded over ranks, one all_gather of result rows"}})
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
