@@ -57,6 +57,11 @@ struct PrepArgs {
   int D, D4, Dpad;
 };
 
+// a.X[side] with a run-time `side` makes the compiler copy the whole argument struct to local memory (112 bytes of stack per
+// thread; the dead stack lines are later written back to DRAM: ncu showed 999 MB written for 786 MB of output).  A select
+// between the two parameter words keeps the arguments in the constant bank.
+#define SIDE(arr) (side == 0 ? (arr)[0] : (arr)[1])
+
 __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
   extern __shared__ float tile[];  // [D][33]
   __shared__ float red[8][32];
@@ -66,10 +71,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
   if (r0 >= n) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = r0 + lane;
-  const int hw = a.hw[side];
+  const int hw = SIDE(a.hw);
   int pix = 0;
-  if (r < n) pix = a.roi[side] ? a.roi[side][(size_t)b * a.cap[side] + r] : r;
-  const float* src = a.feat[side] + (size_t)b * a.D * hw + pix;
+  if (r < n) pix = SIDE(a.roi) ? SIDE(a.roi)[(size_t)b * SIDE(a.cap) + r] : r;
+  const float* src = SIDE(a.feat) + (size_t)b * a.D * hw + pix;
   float ss = 0.f;
   for (int d = warp; d < a.D; d += 8) {
     const float v = (r < n) ? __ldg(src + (size_t)d * hw) : 0.f;
@@ -86,12 +91,12 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
     inv_norm[lane] = fmaxf(sqrtf(s), 1e-8f);
   }
   __syncthreads();
-  float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;
+  float* d32 = SIDE(a.rows32) + ((size_t)b * SIDE(a.npad) + r0) * a.D4;
   for (int i = threadIdx.x; i < 32 * a.D4; i += 256) {
     const int row = i / a.D4, d = i - row * a.D4;
     d32[i] = d < a.D ? __fdiv_rn(tile[d * 33 + row], inv_norm[row]) : 0.f;
   }
-  __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
+  __half* d16 = SIDE(a.rows16) + ((size_t)b * SIDE(a.npad) + r0) * a.Dpad;
   for (int i = threadIdx.x; i < 32 * a.Dpad; i += 256) {
     const int row = i / a.Dpad, d = i - row * a.Dpad;
     d16[i] = __float2half_rn(d < a.D ? __fdiv_rn(tile[d * 33 + row], inv_norm[row]) : 0.f);
@@ -109,10 +114,10 @@ __global__ void __launch_bounds__(256) prep_dense_kernel(PrepArgs a) {
   __shared__ float nrm[kPrepPix];
   constexpr int LD = kPrepPix + 1;
   const int side = blockIdx.z, b = blockIdx.y, r0 = blockIdx.x * kPrepPix;
-  const int hw = a.hw[side];
+  const int hw = SIDE(a.hw);
   if (r0 >= hw) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* src = a.feat[side] + (size_t)b * a.D * hw + r0;
+  const float* src = SIDE(a.feat) + (size_t)b * a.D * hw + r0;
   const int npix = min(kPrepPix, hw - r0);
   for (int d = warp; d < a.D; d += 8) {
     float2 v = make_float2(0.f, 0.f);
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(256) prep_dense_kernel(PrepArgs a) {
     nrm[p] = __fdiv_rn(1.f, fmaxf(sqrtf(red[0][p] + red[1][p] + red[2][p] + red[3][p]), 1e-8f));
   }
   __syncthreads();
-  float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;
-  __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
+  float* d32 = SIDE(a.rows32) + ((size_t)b * SIDE(a.npad) + r0) * a.D4;
+  __half* d16 = SIDE(a.rows16) + ((size_t)b * SIDE(a.npad) + r0) * a.Dpad;
   for (int row = warp; row < npix; row += 8) {
     const float inv = nrm[row];
     for (int d = lane; d < a.Dpad || d < a.D4; d += 32) {
@@ -159,10 +164,10 @@ __global__ void __launch_bounds__(256) prep_dense2_kernel(PrepArgs a) {
   float* tile = tile4;
   constexpr int D = 32 * NIT, LD = D + 4;         // LD / 4 odd: float4 stores of consecutive pixels fall into distinct bank quads
   const int side = blockIdx.z, b = blockIdx.y, r0 = blockIdx.x * kPrepPix;
-  const int hw = a.hw[side];
+  const int hw = SIDE(a.hw);
   if (r0 >= hw) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* src = a.feat[side] + (size_t)b * D * hw + r0;
+  const float* src = SIDE(a.feat) + (size_t)b * D * hw + r0;
   const int npix = min(kPrepPix, hw - r0);
   const bool in0 = 2 * lane < npix, in1 = 2 * lane + 1 < npix;
   float2 v[NIT][4];
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(256) prep_dense2_kernel(PrepArgs a) {
     *reinterpret_cast<float4*>(&tile[(2 * lane + 1) * LD + d]) = make_float4(v[i][0].y, v[i][1].y, v[i][2].y, v[i][3].y);
   }
   __syncthreads();
-  float* d32 = a.rows32[side] + ((size_t)b * a.npad[side] + r0) * a.D4;   // D4 == D here
-  __half* d16 = a.rows16[side] + ((size_t)b * a.npad[side] + r0) * a.Dpad;
+  float* d32 = SIDE(a.rows32) + ((size_t)b * SIDE(a.npad) + r0) * a.D4;   // D4 == D here
+  __half* d16 = SIDE(a.rows16) + ((size_t)b * SIDE(a.npad) + r0) * a.Dpad;
   constexpr int Q = (D + 127) / 128;   // float4 quads per lane (1 up to D = 128, 2 at D = 256)
 #pragma unroll 4
   for (int row = warp; row < npix; row += 8) {
@@ -221,6 +226,8 @@ __global__ void __launch_bounds__(256) prep_dense2_kernel(PrepArgs a) {
     }
   }
 }
+
+#undef SIDE
 
 // ------------------------------------------------------------------------------------------------
 // exact fp32 rows (mode ORYON_MATCH_EXACT_FP32 and overflow fallback)

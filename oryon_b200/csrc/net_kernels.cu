@@ -101,7 +101,10 @@ __global__ void __launch_bounds__(256) resize_patch_kernel(ResizeArgs a) {
         }
         acc = fmaf(wy[i], r, acc);
       }
-      val = __fdiv_rn(acc - a.mean[c], a.stdv[c]);
+      // selects, not a.mean[c]: a run-time index would copy the argument struct to local memory
+      const float mean = c == 0 ? a.mean[0] : c == 1 ? a.mean[1] : a.mean[2];
+      const float stdv = c == 0 ? a.stdv[0] : c == 1 ? a.stdv[1] : a.stdv[2];
+      val = __fdiv_rn(acc - mean, stdv);
     }
     __half hh, ll;
     split_half(val, hh, ll);
