@@ -4,7 +4,7 @@
  *
  * The reference (jcorsetti/oryon) has no FFI: its boundary for this path is a set of Python
  * functions.  Each entry point below names the reference function (file:line under the reference
- * tree) whose arithmetic it replaces; oryon_b200/*.py are the Python mirrors that keep the
+ * tree) whose arithmetic it replaces; the oryon_b200 Python modules are the mirrors that keep the
  * reference signatures and call these through ctypes (INTEGRATION.md shows the binding a reference
  * maintainer would add).
  *
