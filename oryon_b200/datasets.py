@@ -12,6 +12,9 @@ Training-only entries (``corrs``, ``all_corrs``, resized ``depth``, ``box``, ``o
 """
 from __future__ import annotations
 
+import json
+import os
+import pickle
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -104,3 +107,130 @@ class GpuCollate:
         if poses:
             out["pose"] = torch.tensor(np.stack(poses, axis=0))
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dataset reader (test time): the reference's NOCSDataset (datasets.py:369-543) producing GpuCollate samples
+# ------------------------------------------------------------------------------------------------
+def _cfg(obj, path: str, default=None):
+    """``args.a.b`` on attribute- or mapping-style configs (hydra's DictConfig in the reference, plain dicts here)."""
+    cur = obj
+    for key in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(key) if isinstance(cur, dict) else getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+def get_mask_type(mask: str, eval: bool) -> str:
+    """Which mask FILE a sample carries (datasets.py:27-45): when the mask is predicted by the network the oracle mask
+    is loaded as ground truth; outside evaluation always the oracle."""
+    if eval:
+        return "oracle" if mask == "predicted" else mask
+    return "oracle"
+
+
+def nearest_resized_mask_nonempty(mask01: np.ndarray, size: Sequence[int]) -> bool:
+    """``check_validity`` (utils/data/common.py:104-111) of the mask AFTER the test-time nearest resize
+    (utils/augmentations.py:138): whether any sampled source pixel ``floor(dst * float32(in / out))`` is set."""
+    H, W = mask01.shape
+    ys = np.minimum(np.floor(np.arange(size[0], dtype=np.float32) * np.float32(H / size[0])).astype(np.int64), H - 1)
+    xs = np.minimum(np.floor(np.arange(size[1], dtype=np.float32) * np.float32(W / size[1])).astype(np.int64), W - 1)
+    return bool(mask01[np.ix_(ys, xs)].any())
+
+
+class NOCSDataset:
+    """Test-time reader of the NOCS (REAL275) pair split in the reference's on-disk layout (datasets.py:369-457).
+
+    ``dataset[i]`` is the ``GpuCollate`` sample ``(item_a, item_q, prompt, pose, obj_id, instance_id, valid)``: the two
+    decoded frames as ``utils.data.nocs.get_item_data`` returns them plus the NOCS intrinsics, the 1 + len(templates)
+    prompt strings (datasets.py:515-532), the relative ground-truth pose with its translation in metres (:441-443), the
+    object name, ``'<scene_a>_<img_a>_<scene_q>_<img_q>_<object>'`` and the validity flag (:492-497: both resized masks
+    non-empty and ground-truth correspondences present).  What the reference does next on the DataLoader workers
+    (``preprocess_item``, resize, ``CollateWrapper``) is ``GpuCollate``'s job, on the GPU.  Training-only products
+    (sampled correspondences, augmentations) are not produced."""
+
+    def __init__(self, args, eval: bool = True):
+        from .utils.data import nocs
+        self._nocs = nocs
+        self.eval = eval
+        self.root = _cfg(args, "dataset.root")
+        self.max_corrs = int(_cfg(args, "dataset.max_corrs", 500))
+        self.img_size = tuple(_cfg(args, "dataset.img_size", (224, 224)))
+        self.mask_type = _cfg(args, "test.mask", "oracle")
+        self.add_description = _cfg(args, "test.add_description", "yes")
+        part = "test" if eval else "train"
+        self.name = _cfg(args, f"dataset.{part}.name")
+        self.split = _cfg(args, f"dataset.{part}.split")
+        self.obj = str(_cfg(args, f"dataset.{part}.obj"))
+        self.K = nocs.get_camera()
+        base = os.path.join(self.root, self.name)
+        with open(os.path.join(base, "templates.json")) as f:
+            self.prompt_templates = json.load(f)
+        with open(os.path.join(base, "object_splits.json")) as f:
+            self.obj_ids = [int(cat) for cat in json.load(f)[self.obj]]
+        self.abs_poses = nocs.get_part_data(base)
+        self.obj_names = nocs.get_obj_names(base)
+        self.path_split = os.path.join(base, "fixed_split", self.split)
+        self._obj_data = None
+        with open(os.path.join(self.path_split, "instance_list.txt")) as f:
+            lines = f.readlines()
+        with open(os.path.join(self.path_split, "annots.pkl"), "rb") as f:
+            annots = pickle.load(f)
+        self.instances, self.poses, self.corrs = [], [], []
+        for line in lines:
+            split, scene_a, img_a, scene_q, img_q, cat_id, obj_name = nocs.parse_pair_line(line)
+            if cat_id in self.obj_ids:
+                key = "_".join(str(e) for e in (scene_a, img_a, scene_q, img_q, cat_id, obj_name))
+                pose = np.array(annots[key]["gt"], dtype=np.float64, copy=True)
+                pose[:3, 3] = pose[:3, 3] / 1000.
+                self.poses.append(pose)
+                self.corrs.append(annots[key]["corrs"])
+                self.instances.append((split, scene_a, img_a, scene_q, img_q, cat_id, obj_name))
+        self.tracked_instances = []
+        tracked = os.path.join(self.path_split, "tracked.txt")
+        if os.path.exists(tracked):
+            with open(tracked) as f:
+                for line in f.readlines():
+                    _, scene_a, img_a, scene_q, img_q, _, obj_name = nocs.parse_pair_line(line)
+                    self.tracked_instances.append(f"{scene_a}_{img_a}_{scene_q}_{img_q}_{obj_name}")
+        self.collate = GpuCollate(self.img_size, _cfg(args, "device"))
+
+    def __len__(self) -> int:
+        return len(self.instances)
+
+    def get_item(self, scene_id: int, img_id: int, obj_id: str, mask_type: str = "oracle") -> dict:
+        return self._nocs.get_item_data(os.path.join(self.root, self.name), scene_id, img_id, self.abs_poses, self.obj_names, obj_id, mask_type)
+
+    def get_item_prompt(self, item: dict) -> List[str]:
+        name = item["metadata"]["cls_names"][0]
+        if self.add_description == "yes":
+            name = f"{item['metadata']['cls_descs'][0][0]} {name}"
+        elif self.add_description == "wrong":
+            name = f"{item['metadata']['cls_descs'][0][1]} {name}"
+        elif self.add_description == "desconly":
+            name = f"{item['metadata']['cls_descs'][0][0]} object"
+        return [name] + [template.format(name) for template in self.prompt_templates]
+
+    def __getitem__(self, index: int):
+        _, scene_a, img_a, scene_q, img_q, _, obj_id = self.instances[index]
+        instance_id = f"{scene_a}_{img_a}_{scene_q}_{img_q}_{obj_id}"
+        mask = get_mask_type(self.mask_type, self.eval)
+        item_a, item_q = self.get_item(scene_a, img_a, obj_id, mask), self.get_item(scene_q, img_q, obj_id, mask)
+        valid = len(self.corrs[index]) > 0
+        for item in (item_a, item_q):
+            if len(item["metadata"]["mask_ids"]) != 1:      # the assertion of preprocess_item (utils/data/common.py:45)
+                raise AssertionError(f" Problem with instance {item['instance_id']}: no objects found. Check cls_id!")
+            item["camera"] = self.K
+            valid = valid and nearest_resized_mask_nonempty(np.asarray(item["mask"]) == item["metadata"]["mask_ids"][0], self.img_size)
+        return item_a, item_q, self.get_item_prompt(item_a), self.poses[index], obj_id, instance_id, valid
+
+    def get_object_info(self):
+        """``(models, diameters, symmetries)`` of all objects, for ``Evaluator.add_object_info`` (datasets.py:509-513)."""
+        if self._obj_data is None:
+            self._obj_data = self._nocs.get_obj_data(os.path.join(self.root, self.name))
+        return self._obj_data
+
+    def get_obj_info(self, obj_id):
+        models, diams, symms = self.get_object_info()
+        return models[obj_id], diams[obj_id], symms[obj_id]

@@ -414,3 +414,106 @@ def eval_scene_depth(models: Dict, cls_id: int, gt_pose: np.ndarray, K: np.ndarr
         scene[max(0, yc - 4):yc + 5, :] = np.minimum(scene[max(0, yc - 4):yc + 5, :], float(d[d > 0].min()) - 60.0)   # occluder
         scene[:, max(0, xc + 6):xc + 12] = 0.0                                                                          # missing depth
     return np.round(scene).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# a tiny dataset tree in the on-disk layout of the reference's NOCS (REAL275) test split
+# (datasets.py:369-457, utils/data/nocs.py): input of the reader tests and of oracle/make_golden_nocs.py
+# ------------------------------------------------------------------------------------------------
+NOCS_TREE_OBJECTS = {"mug_synth_a": (6, ["mug", "white", "red"]), "bowl_synth_b": (2, ["bowl", "blue", "green"]),
+                     "can_synth_c": (3, ["can", "metal", "paper"])}   # object name -> (category id, [class name, descriptions...])
+
+
+def write_nocs_tree(root: str, seed: int = 0, name: str = "nocs", split: str = "cross_scene_test", hw: Tuple[int, int] = (48, 64),
+                    n_scenes: int = 2, n_imgs: int = 3) -> Dict:
+    """Writes ``<root>/<name>/...`` with ``n_scenes x n_imgs`` frames (colour / label mask / 16-bit depth PNGs, meta and
+    detection text files, per-frame pose pickles), three object models (one with a continuous, one with a discrete
+    symmetry), the prompt templates, the object split and a fixed pair split (instance list, annotations, tracked list).
+    Deterministic in ``seed``.  One frame lacks the third object, one object is a single pixel, one pair has no ground-truth
+    correspondences (an invalid sample in the reference's sense)."""
+    import json
+    import os
+    import pickle
+    from PIL import Image
+
+    g = np.random.default_rng(seed)
+    base = os.path.join(root, name)
+    H, W = hw
+    names = list(NOCS_TREE_OBJECTS)
+    for d in ("gts/real_test", "obj_models/real_test", f"fixed_split/{split}", "split/real_test"):
+        os.makedirs(os.path.join(base, d), exist_ok=True)
+    with open(os.path.join(base, "templates.json"), "w") as f:
+        json.dump(["a photo of a {}.", "a bad photo of the {}.", "a close-up photo of a {}.", "itap of a {}.", "a {} in a scene."], f)
+    with open(os.path.join(base, "object_splits.json"), "w") as f:
+        json.dump({"all": ["6", "2", "3"], "mugs": ["6"]}, f)
+    with open(os.path.join(base, "obj_names.json"), "w") as f:
+        json.dump({k: v[1] + ["norm"] for k, v in NOCS_TREE_OBJECTS.items()}, f)
+
+    # object models: vertices in metres (the reader scales to mm), normals, OBJ faces (1-based, v/vt/vn triplets)
+    info = {}
+    for i, obj in enumerate(names):
+        nv = 12 + 4 * i
+        v = g.normal(size=(nv, 3)) * 0.05
+        nrm = v / np.linalg.norm(v, axis=1, keepdims=True)
+        faces = np.stack([np.arange(nv - 2), np.arange(1, nv - 1), np.arange(2, nv)], 1) + 1
+        p = os.path.join(base, "obj_models/real_test", obj)
+        np.savetxt(p + "_vertices.txt", v, fmt="%.6f")
+        np.savetxt(p + "_normals.txt", nrm, fmt="%.6f")
+        with open(p + ".obj", "w") as f:
+            f.write("# synthetic\n" + "".join(f"v {a:.6f} {b:.6f} {c:.6f}\n" for a, b, c in v))
+            f.write("".join(f"f {a}/{a}/{a} {b}/{b}/{b} {c}/{c}/{c}\n" for a, b, c in faces))
+        info[obj] = {"diameter": float(np.ptp(v, axis=0).max() * 1000.0)}
+    info[names[1]]["symmetries_continuous"] = [{"axis": [0, 0, 1], "offset": [0, 0, 0]}]
+    info[names[2]]["symmetries_discrete"] = [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]
+    with open(os.path.join(base, "obj_models/real_test/models_info.json"), "w") as f:
+        json.dump(info, f)
+
+    frames = []
+    for s in range(1, n_scenes + 1):
+        os.makedirs(os.path.join(base, f"split/real_test/scene_{s}"), exist_ok=True)
+        for im in range(n_imgs):
+            present = names if not (s == 1 and im == 1) else names[:2]          # one frame without the third object
+            rgb = g.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+            depth = g.integers(400, 1600, size=(H, W)).astype(np.uint16)
+            mask = np.full((H, W), 255, np.uint8)
+            meta, det, poses = [], [], []
+            for k, obj in enumerate(present):
+                mask_id = k + 1
+                y0, x0 = 4 + 12 * k, 5 + 14 * k
+                hh, ww = (10, 12) if not (s == 2 and im == 2 and k == 0) else (1, 1)   # one single-pixel object
+                mask[y0:y0 + hh, x0:x0 + ww] = mask_id
+                meta.append(f"{mask_id} {NOCS_TREE_OBJECTS[obj][0]} {obj}\n")
+                det.append(f"{mask_id} {x0} {y0} {ww - 1} {hh - 1}\n")
+                T = np.eye(4)
+                T[:3, :3] = _axis_rotation(g.normal(size=3), float(g.uniform(0.1, 2.0))) * float(g.uniform(0.2, 0.4))   # NOCS poses carry a scale
+                T[:3, 3] = g.normal(size=3) * 0.1 + np.array([0.0, 0.0, 1.0])
+                poses.append(T)
+            stem = os.path.join(base, f"split/real_test/scene_{s}/{im:04d}")
+            Image.fromarray(rgb).save(stem + "_color.png")
+            Image.fromarray(mask).save(stem + "_mask.png")
+            Image.fromarray(depth).save(stem + "_depth.png")
+            open(stem + "_meta.txt", "w").writelines(meta)
+            open(stem + "_detection.txt", "w").writelines(det)
+            with open(os.path.join(base, f"gts/real_test/results_real_test_scene_{s}_{im:04d}.pkl"), "wb") as f:
+                pickle.dump({"gt_RTs": np.stack(poses)}, f)
+            frames.append((s, im, present))
+
+    # fixed pair split: anchors in scene 1, queries in scene 2 (plus one same-scene pair), objects present in both frames
+    lines, annots = [], {}
+    pairs = [(1, 0, 2, 0, names[0]), (1, 0, 2, 1, names[1]), (1, 2, 2, 2, names[2]), (1, 1, 2, 0, names[1]), (1, 2, 2, 2, names[0]),
+             (2, 1, 2, 0, names[0])]
+    for sa, ia, sq, iq, obj in pairs:
+        cat = NOCS_TREE_OBJECTS[obj][0]
+        lines.append(f"real_test, {sa} {ia}, {sq} {iq}, {cat} {obj}\n")
+        gt = np.eye(4)
+        gt[:3, :3] = _axis_rotation(g.normal(size=3), float(g.uniform(0.1, 1.0)))
+        gt[:3, 3] = g.normal(size=3) * 100.0                                   # millimetres on disk
+        n_c = int(g.integers(0, 30)) if (sa, ia, sq, iq, obj) != pairs[3] else 0   # one pair without ground-truth correspondences
+        corrs = np.stack([g.integers(0, H, n_c), g.integers(0, W, n_c), g.integers(0, H, n_c), g.integers(0, W, n_c)], 1).astype(np.int64)
+        annots[f"{sa}_{ia}_{sq}_{iq}_{cat}_{obj}"] = {"gt": gt, "corrs": corrs}
+    sp = os.path.join(base, f"fixed_split/{split}")
+    open(os.path.join(sp, "instance_list.txt"), "w").writelines(lines)
+    open(os.path.join(sp, "tracked.txt"), "w").writelines(lines[:2])
+    with open(os.path.join(sp, "annots.pkl"), "wb") as f:
+        pickle.dump(annots, f)
+    return dict(base=base, name=name, split=split, pairs=pairs, frames=frames)

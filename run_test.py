@@ -43,10 +43,12 @@ def pair_ids(pair_index: int) -> tuple:
 
 
 def run_sharded(n_pairs: int, batch_size: int, step_fn: Callable[[Sequence[int]], List[dict]], *, out_path: Optional[str] = None,
-                device: Optional[torch.device] = None, sync: Optional[Callable[[], None]] = None) -> Dict:
+                device: Optional[torch.device] = None, sync: Optional[Callable[[], None]] = None,
+                id_fn: Callable[[int], tuple] = None) -> Dict:
     """The sharded test loop.  ``step_fn(pair_indices)`` returns one record per pair with the keys ``status``, ``iou_a``,
     ``iou_q``, ``pred_pose_rel`` (``FPM_Pipeline.test_step``'s records).  Returns, on every rank, the gathered table in pair
-    order, the status counts and the loop time (max over ranks); rank 0 also writes ``out_path``."""
+    order, the status counts and the loop time (max over ranks); rank 0 also writes ``out_path`` (``id_fn(pair_index)`` gives
+    the two ``'scene image object'`` ids of a CSV line; default: synthetic ids)."""
     from oryon_b200.pipeline import format_pred_line
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -79,28 +81,86 @@ def run_sharded(n_pairs: int, batch_size: int, step_fn: Callable[[Sequence[int]]
     if rank == 0 and out_path is not None:
         with open(out_path, "w") as fh:
             for r in records:
-                id_a, id_q = pair_ids(r["pair_index"])
+                id_a, id_q = (id_fn or pair_ids)(r["pair_index"])
                 fh.write(format_pred_line(id_a, id_q, np.float32(r["iou_a"]), np.float32(r["iou_q"]), r["pred_pose_rel"].numpy()))
     counts = {k: sum(r["status"] == k for r in records) for k in sharding.STATUS}
     return dict(table=table, records=records, status=counts, seconds=float(dt.item()), world=world, rank=rank)
 
 
-def build_pipeline(local_rank: int, precision: int):
-    """``FPM_Pipeline(args, test_model=True)`` (run_test.py:15) on seeded random weights of the reference's architecture."""
-    from oryon_b200 import synth, synth_backbone as sb
+def build_pipeline(local_rank: int, precision: int, opts=None, evaluator=None):
+    """``FPM_Pipeline(args, test_model=True)`` (run_test.py:15).  Weights: the files named on the command line (the reference's
+    ``pretrained_models/`` set and its Lightning checkpoint, run_test.py:42, assembled in the reference's load order by
+    ``oryon_b200.checkpoint``), otherwise seeded random weights of the reference's architecture."""
+    from oryon_b200 import checkpoint as ck, synth, synth_backbone as sb
     from oryon_b200.net import Oryon
     from oryon_b200.pipeline import FPM_Pipeline
-    from oryon_b200.utils.pointdsc.init import PointDSCSolver
+    from oryon_b200.utils.pointdsc.init import PointDSCSolver, get_pointdsc_solver
     cfg = synth.POINTDSC_DEFAULT_CFG
     dev = f"cuda:{local_rank}"
-    model = Oryon(None, dev, state_dict=sb.oryon_state_dict(11), precision=precision)
-    solver = PointDSCSolver(synth.pointdsc_state_dict(300), in_dim=cfg["in_dim"], num_layers=cfg["num_layers"],
-                            num_channels=cfg["num_channels"], num_iterations=cfg["num_iterations"], ratio=cfg["ratio"],
-                            sigma_d=cfg["sigma_d"], k=cfg["k"], nms_radius=cfg["inlier_threshold"], device=dev)
+    tokenizer = None
+    if opts is not None and opts.bpe:
+        from oryon_b200.models.tokenizer import SimpleTokenizer
+        tokenizer = SimpleTokenizer(opts.bpe)
+    if opts is not None and (opts.clip or opts.ckpt):
+        sd = ck.assemble_state_dict(ck.clip_state_dict(opts.clip) if opts.clip else None, ck.swin_state_dict(opts.swin) if opts.swin else None,
+                                    torch.load(opts.catseg, map_location="cpu")["model"] if opts.catseg else None,
+                                    ck.lightning_model_state_dict(opts.ckpt) if opts.ckpt else None)
+    else:
+        sd = sb.oryon_state_dict(11)
+    model = Oryon(None, dev, state_dict=sd, precision=precision, tokenizer=tokenizer)
+    if opts is not None and opts.pointdsc:
+        solver = get_pointdsc_solver(opts.pointdsc, dev)
+    else:
+        solver = PointDSCSolver(synth.pointdsc_state_dict(300), in_dim=cfg["in_dim"], num_layers=cfg["num_layers"],
+                                num_channels=cfg["num_channels"], num_iterations=cfg["num_iterations"], ratio=cfg["ratio"],
+                                sigma_d=cfg["sigma_d"], k=cfg["k"], nms_radius=cfg["inlier_threshold"], device=dev)
+    mask = opts.mask if opts is not None else "oracle"
     args = dict(device=dev, corrs_device="cpu", dataset=dict(img_size=[224, 224], max_corrs=500),
                 model=dict(image_encoder=dict(img_size=[192, 192])),
-                test=dict(mask="oracle", src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
-    return FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver), model
+                test=dict(mask=mask, src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
+    return FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver, evaluator=evaluator), model
+
+
+def dataset_args(opts, device: str) -> dict:
+    """The keys of configs/config.yaml the test-time reader consumes (datasets.py:371-392)."""
+    return dict(device=device, dataset=dict(root=opts.root, max_corrs=500, img_size=[224, 224],
+                                            test=dict(name=opts.dataset, split=opts.split, obj=opts.obj)),
+                test=dict(mask=opts.mask, add_description=opts.add_description))
+
+
+def dataset_pair_ids(ds, pair_index: int) -> tuple:
+    """``'scene image object'`` ids of both frames of a pair, as ``get_item_data`` names them (utils/data/nocs.py:265)."""
+    _, scene_a, img_a, scene_q, img_q, _, obj = ds.instances[pair_index]
+    return f"{scene_a} {img_a} {obj}", f"{scene_q} {img_q} {obj}"
+
+
+def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real_stdout: int) -> None:
+    """The test loop over a mounted dataset in the reference's NOCS layout: ``NOCSDataset`` samples -> ``GpuCollate`` (decode on
+    the host, resize / normalise on the GPU) -> ``test_step``.  Rank 0 writes the prediction CSV; scoring it is the offline
+    scorer's job (``oryon_b200.utils.evaluator`` / the reference's scripts/evaluation/compute_metrics.py read it back)."""
+    from oryon_b200.datasets import NOCSDataset
+    ds = NOCSDataset(dataset_args(args, f"cuda:{local}"), eval=True)
+    if len(ds) == 0:
+        raise SystemExit(f"run_test.py: no pair of split {args.split!r} matches object split {args.obj!r}")
+    pipe, model = build_pipeline(local, args.precision, args)
+    if model.tokenizer is None:
+        raise SystemExit("run_test.py: text prompts need the CLIP BPE vocabulary (--bpe)")
+
+    def step(idx: Sequence[int]) -> List[dict]:
+        return pipe.test_step(ds.collate([ds[i] for i in idx]), idx[0] // args.batch)
+
+    pipe.on_test_start(seed=args.seed + rank)
+    res = run_sharded(len(ds), args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize,
+                      id_fn=lambda i: dataset_pair_ids(ds, i))
+    pipe.on_test_end()
+    if rank == 0:
+        line = json.dumps({"metric": "image-pairs/sec (whole test loop, decode included)", "value": len(ds) / res["seconds"], "unit": "pairs/s",
+                           "n_gpus": world, "pairs": len(ds), "batch": args.batch, "seconds": res["seconds"], "status": res["status"],
+                           "gemm_precision": args.precision, "data": f"{args.dataset}/{args.split}/{args.obj}", "csv": args.out})
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main(argv=None):
@@ -115,6 +175,19 @@ def main(argv=None):
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3], help="GEMM products per algorithmic product (3 = float32-equivalent)")
     ap.add_argument("--distinct-batches", type=int, default=4, help="synthetic batches generated up front and cycled")
     ap.add_argument("--seed", type=int, default=1, help="on_test_start seed (utils/misc.py:186-196)")
+    ap.add_argument("--dataset", default=None, help="name of a mounted dataset in the reference's NOCS layout (args.dataset.test.name), e.g. nocs; "
+                                                    "default: synthetic pairs")
+    ap.add_argument("--root", default="data", help="args.dataset.root")
+    ap.add_argument("--split", default="cross_scene_test", help="args.dataset.test.split (a directory under fixed_split/)")
+    ap.add_argument("--obj", default="all", help="args.dataset.test.obj (a key of object_splits.json)")
+    ap.add_argument("--mask", default="oracle", choices=["oracle", "predicted", "ovseg", "san", "oryon"], help="args.test.mask")
+    ap.add_argument("--add-description", default="yes", choices=["yes", "no", "wrong", "desconly"], help="args.test.add_description")
+    ap.add_argument("--bpe", default=None, help="CLIP BPE vocabulary (bpe_simple_vocab_16e6.txt.gz); needed for text prompts")
+    ap.add_argument("--clip", default=None, help="OpenAI CLIP ViT-L/14@336 TorchScript archive")
+    ap.add_argument("--swin", default=None, help="torchvision swin_b weights")
+    ap.add_argument("--catseg", default=None, help="CATSeg checkpoint (pretrained_models/catseg.pth)")
+    ap.add_argument("--ckpt", default=None, help="the reference's Lightning checkpoint (args.eval.ckpt)")
+    ap.add_argument("--pointdsc", default=None, help="PointDSC snapshot directory (args.pretrained.pointdsc)")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -128,6 +201,8 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=dev)
 
     from oryon_b200 import synth
+    if args.dataset is not None:
+        return run_dataset(args, world, rank, local, dev, real_stdout)
     pipe, model = build_pipeline(local, args.precision)
     batches = []
     for k in range(args.distinct_batches):

@@ -77,3 +77,23 @@ def test_csv_is_the_reference_wire_format(tmp_path):
     preds, ious_a, ious_q, iou_present = dict_from_preds(str(path))      # the offline scorer's reader (compute_metrics.py:14-49)
     assert iou_present and len(preds) == len(ious_a) == len(ious_q) == 6
     np.testing.assert_allclose(preds["0001_000003_0002_000003_1"], _fake_rows([3])[0]["pred_pose_rel"][:3].numpy(), rtol=1e-7)
+
+
+def test_dataset_mode_ids_and_config_from_a_nocs_tree(tmp_path):
+    """--dataset mode: the reader is configured from the command-line options and the CSV ids are the frames' own ids."""
+    import argparse
+    from oryon_b200 import synth
+    from oryon_b200.datasets import NOCSDataset
+    info = synth.write_nocs_tree(str(tmp_path), 0)
+    opts = argparse.Namespace(root=str(tmp_path), dataset=info["name"], split=info["split"], obj="all", mask="predicted", add_description="yes")
+    ds = NOCSDataset(run_test.dataset_args(opts, "cuda:0"), eval=True)
+    assert len(ds) == len(info["pairs"])
+    for i, (sa, ia, sq, iq, obj) in enumerate(info["pairs"]):
+        id_a, id_q = run_test.dataset_pair_ids(ds, i)
+        item_a, item_q, *_ = ds[i]
+        assert (id_a, id_q) == (item_a["instance_id"], item_q["instance_id"]) == (f"{sa} {ia} {obj}", f"{sq} {iq} {obj}")
+    path = tmp_path / "pred.csv"
+    run_test.run_sharded(len(ds), 4, _fake_rows, out_path=str(path), id_fn=lambda i: run_test.dataset_pair_ids(ds, i))
+    from oryon_b200.utils.evaluator import dict_from_preds
+    preds, *_ = dict_from_preds(str(path))
+    assert "1_0_2_0_mug_synth_a" in preds and len(preds) == len(ds)
