@@ -139,20 +139,18 @@ def nearest_resized_mask_nonempty(mask01: np.ndarray, size: Sequence[int]) -> bo
     return bool(mask01[np.ix_(ys, xs)].any())
 
 
-class NOCSDataset:
-    """Test-time reader of the NOCS (REAL275) pair split in the reference's on-disk layout (datasets.py:369-457).
+class _PairSplitDataset:
+    """Common part of the reference's test-time dataset classes (datasets.py:369-543 NOCS, :546-713 TOYL): a fixed split of
+    (anchor frame, query frame, object) pairs with relative ground-truth poses.
 
     ``dataset[i]`` is the ``GpuCollate`` sample ``(item_a, item_q, prompt, pose, obj_id, instance_id, valid)``: the two
-    decoded frames as ``utils.data.nocs.get_item_data`` returns them plus the NOCS intrinsics, the 1 + len(templates)
-    prompt strings (datasets.py:515-532), the relative ground-truth pose with its translation in metres (:441-443), the
-    object name, ``'<scene_a>_<img_a>_<scene_q>_<img_q>_<object>'`` and the validity flag (:492-497: both resized masks
-    non-empty and ground-truth correspondences present).  What the reference does next on the DataLoader workers
-    (``preprocess_item``, resize, ``CollateWrapper``) is ``GpuCollate``'s job, on the GPU.  Training-only products
-    (sampled correspondences, augmentations) are not produced."""
+    decoded frames as the dataset's ``get_item_data`` returns them plus the intrinsics, the 1 + len(templates) prompt strings
+    (:515-532 / :685-702), the relative ground-truth pose with its translation in metres (:441-443), the object key, the pair
+    id and the validity flag (:492-497: both resized masks non-empty and ground-truth correspondences present).  What the
+    reference does next on the DataLoader workers (``preprocess_item``, resize, ``CollateWrapper``) is ``GpuCollate``'s job,
+    on the GPU.  Training-only products (sampled correspondences, augmentations) are not produced."""
 
     def __init__(self, args, eval: bool = True):
-        from .utils.data import nocs
-        self._nocs = nocs
         self.eval = eval
         self.root = _cfg(args, "dataset.root")
         self.max_corrs = int(_cfg(args, "dataset.max_corrs", 500))
@@ -163,15 +161,15 @@ class NOCSDataset:
         self.name = _cfg(args, f"dataset.{part}.name")
         self.split = _cfg(args, f"dataset.{part}.split")
         self.obj = str(_cfg(args, f"dataset.{part}.obj"))
-        self.K = nocs.get_camera()
-        base = os.path.join(self.root, self.name)
-        with open(os.path.join(base, "templates.json")) as f:
+        self.K = self._reader.get_camera() if not hasattr(self, "K") else self.K
+        self.local_root = os.path.join(self.root, self.name)
+        with open(os.path.join(self.local_root, "templates.json")) as f:
             self.prompt_templates = json.load(f)
-        with open(os.path.join(base, "object_splits.json")) as f:
+        with open(os.path.join(self.local_root, "object_splits.json")) as f:
             self.obj_ids = [int(cat) for cat in json.load(f)[self.obj]]
-        self.abs_poses = nocs.get_part_data(base)
-        self.obj_names = nocs.get_obj_names(base)
-        self.path_split = os.path.join(base, "fixed_split", self.split)
+        self.part_data = self._reader.get_part_data(self.local_root)
+        self.obj_names = self._reader.get_obj_names(self.local_root)
+        self.path_split = os.path.join(self.local_root, "fixed_split", self.split)
         self._obj_data = None
         with open(os.path.join(self.path_split, "instance_list.txt")) as f:
             lines = f.readlines()
@@ -179,28 +177,33 @@ class NOCSDataset:
             annots = pickle.load(f)
         self.instances, self.poses, self.corrs = [], [], []
         for line in lines:
-            split, scene_a, img_a, scene_q, img_q, cat_id, obj_name = nocs.parse_pair_line(line)
-            if cat_id in self.obj_ids:
-                key = "_".join(str(e) for e in (scene_a, img_a, scene_q, img_q, cat_id, obj_name))
+            inst = self._reader.parse_pair_line(line)
+            if inst[5] in self.obj_ids:
+                key = "_".join(str(e) for e in inst[1:])
                 pose = np.array(annots[key]["gt"], dtype=np.float64, copy=True)
                 pose[:3, 3] = pose[:3, 3] / 1000.
                 self.poses.append(pose)
                 self.corrs.append(annots[key]["corrs"])
-                self.instances.append((split, scene_a, img_a, scene_q, img_q, cat_id, obj_name))
+                self.instances.append(inst)
         self.tracked_instances = []
         tracked = os.path.join(self.path_split, "tracked.txt")
         if os.path.exists(tracked):
             with open(tracked) as f:
                 for line in f.readlines():
-                    _, scene_a, img_a, scene_q, img_q, _, obj_name = nocs.parse_pair_line(line)
-                    self.tracked_instances.append(f"{scene_a}_{img_a}_{scene_q}_{img_q}_{obj_name}")
+                    inst = self._reader.parse_pair_line(line)
+                    self.tracked_instances.append("_".join(str(e) for e in inst[1:5] + (inst[-1],)))
         self.collate = GpuCollate(self.img_size, _cfg(args, "device"))
 
     def __len__(self) -> int:
         return len(self.instances)
 
-    def get_item(self, scene_id: int, img_id: int, obj_id: str, mask_type: str = "oracle") -> dict:
-        return self._nocs.get_item_data(os.path.join(self.root, self.name), scene_id, img_id, self.abs_poses, self.obj_names, obj_id, mask_type)
+    def get_item(self, scene_id: int, img_id: int, obj_id, mask_type: str = "oracle") -> dict:
+        return self._reader.get_item_data(self.local_root, scene_id, img_id, self.part_data, self.obj_names, obj_id, mask_type)
+
+    def frame_ids(self, index: int):
+        """``'scene image object'`` ids of the two frames of pair ``index`` (the ids of a prediction-CSV line)."""
+        inst = self.instances[index]
+        return f"{inst[1]} {inst[2]} {inst[-1]}", f"{inst[3]} {inst[4]} {inst[-1]}"
 
     def get_item_prompt(self, item: dict) -> List[str]:
         name = item["metadata"]["cls_names"][0]
@@ -213,7 +216,8 @@ class NOCSDataset:
         return [name] + [template.format(name) for template in self.prompt_templates]
 
     def __getitem__(self, index: int):
-        _, scene_a, img_a, scene_q, img_q, _, obj_id = self.instances[index]
+        inst = self.instances[index]
+        scene_a, img_a, scene_q, img_q, obj_id = inst[1], inst[2], inst[3], inst[4], inst[-1]
         instance_id = f"{scene_a}_{img_a}_{scene_q}_{img_q}_{obj_id}"
         mask = get_mask_type(self.mask_type, self.eval)
         item_a, item_q = self.get_item(scene_a, img_a, obj_id, mask), self.get_item(scene_q, img_q, obj_id, mask)
@@ -228,9 +232,31 @@ class NOCSDataset:
     def get_object_info(self):
         """``(models, diameters, symmetries)`` of all objects, for ``Evaluator.add_object_info`` (datasets.py:509-513)."""
         if self._obj_data is None:
-            self._obj_data = self._nocs.get_obj_data(os.path.join(self.root, self.name))
+            self._obj_data = self._reader.get_obj_data(self.local_root)
         return self._obj_data
+
+
+class NOCSDataset(_PairSplitDataset):
+    """Test-time reader of the NOCS (REAL275) pair split in the reference's on-disk layout (datasets.py:369-457): pairs are
+    ``(split, scene_a, img_a, scene_q, img_q, category id, object name)``, filtered by category id, keyed by object NAME."""
+    from .utils.data import nocs as _reader
+
+    @property
+    def abs_poses(self):
+        return self.part_data
 
     def get_obj_info(self, obj_id):
         models, diams, symms = self.get_object_info()
         return models[obj_id], diams[obj_id], symms[obj_id]
+
+
+class TOYLDataset(_PairSplitDataset):
+    """Test-time reader of the TOYL pair split in the reference's on-disk layout (datasets.py:546-630): pairs are
+    ``(split, scene_a, img_a, scene_q, img_q, object id)``, filtered and keyed by the integer object id; the intrinsics are
+    the ones the dataset class hard-codes (datasets.py:573), not ``utils.data.toyl.get_camera()``."""
+    from .utils.data import toyl as _reader
+    K = np.asarray([[572.4114, 0.0, 325.2611], [0.0, 573.5704, 242.0489], [0.0, 0.0, 1.0]])
+
+    def get_obj_info(self, obj_id):
+        models, diams, symms = self.get_object_info()
+        return models[int(obj_id)], diams[int(obj_id)], symms[int(obj_id)]

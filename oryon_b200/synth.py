@@ -517,3 +517,96 @@ def write_nocs_tree(root: str, seed: int = 0, name: str = "nocs", split: str = "
     with open(os.path.join(sp, "annots.pkl"), "wb") as f:
         pickle.dump(annots, f)
     return dict(base=base, name=name, split=split, pairs=pairs, frames=frames)
+
+
+def write_toyl_tree(root: str, seed: int = 0, name: str = "toyl", split: str = "cross_scene_test", hw: Tuple[int, int] = (48, 64),
+                    n_scenes: int = 2, n_imgs: int = 3) -> Dict:
+    """Writes ``<root>/<name>/...`` in the on-disk layout of the reference's TOYL data (datasets.py:546-630,
+    utils/data/toyl.py): BOP scene folders ``split/test/<scene:06d>/{rgb,depth,mask_visib}/<img:06d>.png`` with
+    ``scene_gt.json`` / ``scene_gt_info.json``, ``models_name.json``, ``models_bop/obj_<id:06d>.ply`` (one ASCII, the others
+    binary little endian) + ``models_info.json``, templates, object split and the fixed pair split.  Deterministic in ``seed``."""
+    import json
+    import os
+    import pickle
+    from PIL import Image
+
+    g = np.random.default_rng(1000 + seed)
+    base = os.path.join(root, name)
+    H, W = hw
+    objs = {1: ["duck", "yellow", "green"], 5: ["car", "red", "blue"], 12: ["robot", "grey", "pink"]}
+    for d in ("models_bop", f"fixed_split/{split}"):
+        os.makedirs(os.path.join(base, d), exist_ok=True)
+    with open(os.path.join(base, "templates.json"), "w") as f:
+        json.dump(["a photo of a {}.", "a blurry photo of the {}.", "a toy {}."], f)
+    with open(os.path.join(base, "object_splits.json"), "w") as f:
+        json.dump({"all": ["1", "5", "12"], "cars": ["5"]}, f)
+    with open(os.path.join(base, "models_name.json"), "w") as f:
+        json.dump({str(k): v for k, v in objs.items()}, f)
+
+    info = {}
+    for n, oid in enumerate(objs):
+        nv = 10 + 3 * n
+        v = (g.normal(size=(nv, 3)) * 40.0).astype(np.float32)
+        nrm = (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+        faces = np.stack([np.arange(nv - 2), np.arange(1, nv - 1), np.arange(2, nv)], 1).astype(np.int32)
+        header = (f"ply\nformat {'ascii' if n == 0 else 'binary_little_endian'} 1.0\ncomment synthetic\nelement vertex {nv}\n"
+                  "property float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n"
+                  f"element face {len(faces)}\nproperty list uchar int vertex_indices\nend_header\n")
+        with open(os.path.join(base, "models_bop", f"obj_{oid:06d}.ply"), "wb") as f:
+            f.write(header.encode())
+            if n == 0:
+                for a, b in zip(v, nrm):
+                    f.write((" ".join(repr(float(x)) for x in (*a, *b)) + "\n").encode())
+                for fc in faces:
+                    f.write(("3 " + " ".join(str(int(x)) for x in fc) + "\n").encode())
+            else:
+                f.write(np.concatenate([v, nrm], 1).astype("<f4").tobytes())
+                for fc in faces:
+                    f.write(b"\x03" + fc.astype("<i4").tobytes())
+        info[str(oid)] = {"diameter": float(np.ptp(v, axis=0).max())}
+    info["5"]["symmetries_discrete"] = [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]
+    info["12"]["symmetries_continuous"] = [{"axis": [0, 1, 0], "offset": [0, 0, 0]}]
+    with open(os.path.join(base, "models_bop", "models_info.json"), "w") as f:
+        json.dump(info, f)
+
+    ids = list(objs)
+    for s in range(1, n_scenes + 1):
+        sd = os.path.join(base, "split", "test", f"{s:06d}")
+        for d in ("rgb", "depth", "mask_visib"):
+            os.makedirs(os.path.join(sd, d), exist_ok=True)
+        gt, gt_info = {}, {}
+        for im in range(n_imgs):
+            present = ids if not (s == 2 and im == 1) else ids[1:]               # one frame without the first object
+            Image.fromarray(g.integers(0, 256, size=(H, W, 3), dtype=np.uint8)).save(os.path.join(sd, "rgb", f"{im:06d}.png"))
+            Image.fromarray(g.integers(300, 1400, size=(H, W)).astype(np.uint16)).save(os.path.join(sd, "depth", f"{im:06d}.png"))
+            mask = np.zeros((H, W), np.uint8)
+            gt[str(im)], gt_info[str(im)] = [], []
+            for k, oid in enumerate(present):
+                y0, x0 = 3 + 13 * k, 6 + 15 * k
+                mask[y0:y0 + 9, x0:x0 + 11] = k + 1
+                R = _axis_rotation(g.normal(size=3), float(g.uniform(0.1, 2.5)))
+                gt[str(im)].append({"cam_R_m2c": R.reshape(-1).tolist(), "cam_t_m2c": (g.normal(size=3) * 80.0 + np.array([0, 0, 900.0])).tolist(),
+                                    "obj_id": oid})
+                gt_info[str(im)].append({"bbox_visib": [x0, y0, 11, 9], "bbox_obj": [x0, y0, 11, 9], "px_count_visib": 99})
+            Image.fromarray(mask).save(os.path.join(sd, "mask_visib", f"{im:06d}.png"))
+        with open(os.path.join(sd, "scene_gt.json"), "w") as f:
+            json.dump(gt, f)
+        with open(os.path.join(sd, "scene_gt_info.json"), "w") as f:
+            json.dump(gt_info, f)
+
+    pairs = [(1, 0, 2, 0, 1), (1, 1, 2, 2, 5), (1, 2, 2, 1, 12), (1, 0, 2, 2, 5), (2, 0, 2, 2, 1)]
+    lines, annots = [], {}
+    for n, (sa, ia, sq, iq, oid) in enumerate(pairs):
+        lines.append(f"test, {sa} {ia}, {sq} {iq}, {oid}\n")
+        pose = np.eye(4)
+        pose[:3, :3] = _axis_rotation(g.normal(size=3), float(g.uniform(0.1, 1.0)))
+        pose[:3, 3] = g.normal(size=3) * 120.0
+        n_c = int(g.integers(1, 25)) if n != 3 else 0
+        corrs = np.stack([g.integers(0, H, n_c), g.integers(0, W, n_c), g.integers(0, H, n_c), g.integers(0, W, n_c)], 1).astype(np.int64)
+        annots[f"{sa}_{ia}_{sq}_{iq}_{oid}"] = {"gt": pose, "corrs": corrs}
+    sp = os.path.join(base, f"fixed_split/{split}")
+    open(os.path.join(sp, "instance_list.txt"), "w").writelines(lines)
+    open(os.path.join(sp, "tracked.txt"), "w").writelines(lines[1:3])
+    with open(os.path.join(sp, "annots.pkl"), "wb") as f:
+        pickle.dump(annots, f)
+    return dict(base=base, name=name, split=split, pairs=pairs)

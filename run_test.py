@@ -129,17 +129,18 @@ def dataset_args(opts, device: str) -> dict:
 
 
 def dataset_pair_ids(ds, pair_index: int) -> tuple:
-    """``'scene image object'`` ids of both frames of a pair, as ``get_item_data`` names them (utils/data/nocs.py:265)."""
-    _, scene_a, img_a, scene_q, img_q, _, obj = ds.instances[pair_index]
-    return f"{scene_a} {img_a} {obj}", f"{scene_q} {img_q} {obj}"
+    """``'scene image object'`` ids of both frames of a pair, as ``get_item_data`` names them (utils/data/nocs.py:265,
+    utils/data/toyl.py:202)."""
+    return ds.frame_ids(pair_index)
 
 
 def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real_stdout: int) -> None:
-    """The test loop over a mounted dataset in the reference's NOCS layout: ``NOCSDataset`` samples -> ``GpuCollate`` (decode on
+    """The test loop over a mounted dataset in the reference's NOCS or TOYL layout: ``NOCSDataset`` / ``TOYLDataset`` samples -> ``GpuCollate`` (decode on
     the host, resize / normalise on the GPU) -> ``test_step``.  Rank 0 writes the prediction CSV; scoring it is the offline
     scorer's job (``oryon_b200.utils.evaluator`` / the reference's scripts/evaluation/compute_metrics.py read it back)."""
-    from oryon_b200.datasets import NOCSDataset
-    ds = NOCSDataset(dataset_args(args, f"cuda:{local}"), eval=True)
+    from oryon_b200.datasets import NOCSDataset, TOYLDataset
+    cls = {"nocs": NOCSDataset, "toyl": TOYLDataset}[args.dataset_type or ("toyl" if args.dataset.lower().startswith("toyl") else "nocs")]
+    ds = cls(dataset_args(args, f"cuda:{local}"), eval=True)
     if len(ds) == 0:
         raise SystemExit(f"run_test.py: no pair of split {args.split!r} matches object split {args.obj!r}")
     pipe, model = build_pipeline(local, args.precision, args)
@@ -177,6 +178,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=1, help="on_test_start seed (utils/misc.py:186-196)")
     ap.add_argument("--dataset", default=None, help="name of a mounted dataset in the reference's NOCS layout (args.dataset.test.name), e.g. nocs; "
                                                     "default: synthetic pairs")
+    ap.add_argument("--dataset-type", default=None, choices=["nocs", "toyl"], help="on-disk layout (default: from the dataset name)")
     ap.add_argument("--root", default="data", help="args.dataset.root")
     ap.add_argument("--split", default="cross_scene_test", help="args.dataset.test.split (a directory under fixed_split/)")
     ap.add_argument("--obj", default="all", help="args.dataset.test.obj (a key of object_splits.json)")
