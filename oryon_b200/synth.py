@@ -539,7 +539,7 @@ def write_toyl_tree(root: str, seed: int = 0, name: str = "toyl", split: str = "
     with open(os.path.join(base, "templates.json"), "w") as f:
         json.dump(["a photo of a {}.", "a blurry photo of the {}.", "a toy {}."], f)
     with open(os.path.join(base, "object_splits.json"), "w") as f:
-        json.dump({"all": ["1", "5", "12"], "cars": ["5"]}, f)
+        json.dump({"all": ["1", "5", "12"], "cars": ["5"], "ducks": ["1"]}, f)
     with open(os.path.join(base, "models_name.json"), "w") as f:
         json.dump({str(k): v for k, v in objs.items()}, f)
 
