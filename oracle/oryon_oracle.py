@@ -132,6 +132,25 @@ def nn_correspondences(feats1: Tensor, feats2: Tensor, mask1: Tensor, mask2: Ten
 # --------------------------------------------------------------------------------------------
 
 
+def nn_correspondences_kp(feats1: Tensor, feats2: Tensor, kp1: Tensor, kp2: Tensor, threshold: float, max_corrs: int,
+                          max_source: Optional[int] = None, keep_empty: bool = False,
+                          generator: Optional[torch.Generator] = None, return_debug: bool = False):
+    """Matches between two descriptor sets ``[N,D]`` with key points ``[N,2]``, as the reference's key-point baselines
+    compute them (scripts/evaluation/sift_nocs.py:25-45; sift_toyl.py:25-51 = ``max_source=1000, keep_empty=True``: the
+    source subsample when N1 > 1000 (:32-35) is the first draw, and an empty match set skips the final draw (:45-47))."""
+    if max_source is not None and feats1.shape[0] > max_source:
+        idxs = sample_select(feats1.shape[0], max_source, generator)
+        feats1, kp1 = feats1[idxs], kp1[idxs]
+    min_dist, nn_idx = match_rows(feats1, feats2)
+    valid = torch.nonzero(min_dist < threshold).squeeze(1)
+    final_corrs = torch.cat((kp1[valid], kp2[nn_idx][valid]), dim=1)
+    if not (keep_empty and final_corrs.shape[0] == 0):
+        final_corrs = final_corrs[sample_select(final_corrs.shape[0], max_corrs, generator)]
+    if return_debug:
+        return final_corrs, dict(nn_idx=nn_idx, min_dist=min_dist, valid=valid, feats1=feats1, kp1=kp1)
+    return final_corrs
+
+
 def scale_coords(coords: Tensor, source_scale, target_scale) -> Tensor:
     """(y,x) * (target/source) in float32; the ratio is a Python float (reference
     utils/coordinates.py:5-13)."""

@@ -610,3 +610,53 @@ def write_toyl_tree(root: str, seed: int = 0, name: str = "toyl", split: str = "
     with open(os.path.join(sp, "annots.pkl"), "wb") as f:
         pickle.dump(annots, f)
     return dict(base=base, name=name, split=split, pairs=pairs)
+
+
+# ------------------------------------------------------------------------------------------------
+# textured frames for the key-point baselines (scripts/evaluation/sift_baseline.py)
+# ------------------------------------------------------------------------------------------------
+
+# case -> (frame size, seed, query related to anchor, distance threshold)
+SIFT_CASES = {"k0_small": ((160, 200), 900, True, 0.25), "k1_large": ((240, 320), 901, True, 0.25), "k2_unrelated": ((120, 160), 902, False, 0.02),
+              "k3_tight": ((160, 200), 903, True, 0.05)}
+
+
+def _texture(g: np.random.Generator, h: int, w: int) -> np.ndarray:
+    """Float image in [0,1] with structure at several scales (blobs + edges): box-filtered noise octaves and rectangles."""
+    img = np.zeros((h, w))
+    for k, amp in ((3, 0.35), (7, 0.3), (15, 0.2), (31, 0.15)):
+        n = g.normal(size=(h + k, w + k))
+        c = np.cumsum(np.cumsum(n, 0), 1)
+        box = (c[k:, k:] - c[:-k, k:] - c[k:, :-k] + c[:-k, :-k]) / k          # variance-preserving box filter
+        img += amp * box[:h, :w]
+    img = (img - img.min()) / (img.max() - img.min())
+    for _ in range(max(6, h * w // 6000)):
+        y0, x0 = int(g.integers(0, h - 8)), int(g.integers(0, w - 8))
+        hh, ww = int(g.integers(4, max(5, h // 6))), int(g.integers(4, max(5, w // 6)))
+        img[y0:y0 + hh, x0:x0 + ww] = 0.6 * img[y0:y0 + hh, x0:x0 + ww] + 0.4 * g.uniform()
+    return img
+
+
+def textured_frame_pair(seed: int, hw: Tuple[int, int], related: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Two uint8 grey frames ``[H,W]``: the anchor is a crop of a synthetic texture, the query the same texture seen through a
+    small similarity transform (bilinear sampling) with additive noise -- or, with ``related=False``, another texture."""
+    g = np.random.default_rng(seed)
+    H, W = hw
+    pad = 24
+    tex = _texture(g, H + 2 * pad, W + 2 * pad)
+    anchor = tex[pad:pad + H, pad:pad + W]
+    if related:
+        ang, s = np.deg2rad(g.uniform(-6, 6)), g.uniform(0.95, 1.05)
+        ty, tx = g.uniform(-8, 8, size=2)
+        yy, xx = np.meshgrid(np.arange(H) - H / 2, np.arange(W) - W / 2, indexing="ij")
+        sy = s * (np.cos(ang) * yy - np.sin(ang) * xx) + H / 2 + pad + ty
+        sx = s * (np.sin(ang) * yy + np.cos(ang) * xx) + W / 2 + pad + tx
+        sy, sx = np.clip(sy, 0, tex.shape[0] - 1.001), np.clip(sx, 0, tex.shape[1] - 1.001)
+        y0, x0 = np.floor(sy).astype(int), np.floor(sx).astype(int)
+        fy, fx = sy - y0, sx - x0
+        query = (tex[y0, x0] * (1 - fy) * (1 - fx) + tex[y0, x0 + 1] * (1 - fy) * fx + tex[y0 + 1, x0] * fy * (1 - fx)
+                 + tex[y0 + 1, x0 + 1] * fy * fx) + g.normal(size=(H, W)) * 0.01
+    else:
+        query = _texture(g, H, W)
+    to_u8 = lambda a: np.clip(np.round(a * 255.0), 0, 255).astype(np.uint8)  # noqa: E731
+    return to_u8(anchor), to_u8(query)

@@ -193,6 +193,46 @@ def nn_correspondences(feats1: Tensor, feats2: Tensor, mask1: Tensor, mask2: Ten
     return final_corrs
 
 
+def nn_correspondences_kp(feats1: Tensor, feats2: Tensor, kp1: Tensor, kp2: Tensor, threshold: float, max_corrs: int,
+                          max_source: Optional[int] = None, keep_empty: bool = False, *, return_debug: bool = False):
+    """Matches between two descriptor SETS ``[N1,D]`` / ``[N2,D]`` with key-point coordinates ``kp1 [N1,2]`` / ``kp2 [N2,2]``:
+    rows ``(kp1, kp2[nearest])`` of the pairs whose ``0.5*(1-cos)`` is below ``threshold``, resampled to exactly
+    ``max_corrs`` rows -- the function of the same purpose in the reference's key-point baselines
+    (scripts/evaluation/sift_nocs.py:25-45; sift_toyl.py:25-51 with ``max_source=1000, keep_empty=True``: more than
+    ``max_source`` source descriptors are subsampled first, and an empty match set is returned as ``[0,4]`` instead of
+    reaching ``torch.multinomial``, which raises on it).  The draws use the default generator of ``feats1.device`` as the
+    reference's ``torch_sample_select`` calls do; the distances and the row argmin run in ``oryon_match_nn``."""
+    if feats1.dim() != 2 or feats2.dim() != 2 or feats1.shape[1] != feats2.shape[1]:
+        raise ValueError("nn_correspondences_kp: descriptor sets must be [N,D] with equal D")
+    if kp1.shape[0] != feats1.shape[0] or kp2.shape[0] != feats2.shape[0]:
+        raise ValueError("nn_correspondences_kp: one key point per descriptor")
+    orig_device = feats1.device
+    if max_source is not None and feats1.shape[0] > max_source:
+        idxs = torch_sample_select(feats1, max_source)
+        feats1, kp1 = feats1[idxs], kp1[idxs]
+    n1, n2 = int(feats1.shape[0]), int(feats2.shape[0])
+    if n1 == 0 or n2 == 0:
+        raise RuntimeError("nn_correspondences_kp: empty descriptor set (amin over an empty dimension)")
+    dev = device_of(feats1, feats2)
+    # both sets as [1,D,cap] maps of one width, addressed through explicit position lists
+    cap = max(n1, n2)
+    fa = torch.zeros(1, feats1.shape[1], cap, dtype=torch.float32, device=dev)
+    fq = torch.zeros(1, feats1.shape[1], cap, dtype=torch.float32, device=dev)
+    fa[0, :, :n1] = as_device(feats1, dev, torch.float32).T
+    fq[0, :, :n2] = as_device(feats2, dev, torch.float32).T
+    pos = torch.arange(cap, dtype=torch.int32, device=dev)[None].contiguous()
+    idx, dist = match_nn(fa, fq, pos, pos, [n1], [n2])
+    idx, dist = idx[0, :n1], dist[0, :n1]
+    valid = torch.nonzero(dist < threshold).squeeze(1)
+    nearest = idx.long()[valid]
+    final_corrs = torch.cat((kp1[valid.to(kp1.device)], kp2[nearest.to(kp2.device)].to(kp1.device)), dim=1).to(orig_device)
+    if not (keep_empty and final_corrs.shape[0] == 0):
+        final_corrs = final_corrs[torch_sample_select(final_corrs, max_corrs)]
+    if return_debug:
+        return final_corrs, dict(nn_idx=idx, min_dist=dist, valid=valid)
+    return final_corrs
+
+
 def lift_pcd(depth: Tensor, camera: Tensor, xy_idxs: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
     """Pin-hole lifting of a depth image ``[H,W,C]`` to a point cloud ``[n,3]`` in depth units (reference
     utils/pcd.py:35-81).  With ``xy_idxs = (x, y)`` only those pixels are lifted; without, every pixel in
