@@ -520,7 +520,7 @@ def write_nocs_tree(root: str, seed: int = 0, name: str = "nocs", split: str = "
 
 
 def write_toyl_tree(root: str, seed: int = 0, name: str = "toyl", split: str = "cross_scene_test", hw: Tuple[int, int] = (48, 64),
-                    n_scenes: int = 2, n_imgs: int = 3) -> Dict:
+                    n_scenes: int = 2, n_imgs: int = 3, mask_scale: int = 1) -> Dict:
     """Writes ``<root>/<name>/...`` in the on-disk layout of the reference's TOYL data (datasets.py:546-630,
     utils/data/toyl.py): BOP scene folders ``split/test/<scene:06d>/{rgb,depth,mask_visib}/<img:06d>.png`` with
     ``scene_gt.json`` / ``scene_gt_info.json``, ``models_name.json``, ``models_bop/obj_<id:06d>.ply`` (one ASCII, the others
@@ -582,12 +582,12 @@ def write_toyl_tree(root: str, seed: int = 0, name: str = "toyl", split: str = "
             mask = np.zeros((H, W), np.uint8)
             gt[str(im)], gt_info[str(im)] = [], []
             for k, oid in enumerate(present):
-                y0, x0 = 3 + 13 * k, 6 + 15 * k
-                mask[y0:y0 + 9, x0:x0 + 11] = k + 1
+                y0, x0, hh, ww = (3 + 13 * k) * mask_scale, (6 + 15 * k) * mask_scale, 9 * mask_scale, 11 * mask_scale
+                mask[y0:y0 + hh, x0:x0 + ww] = k + 1
                 R = _axis_rotation(g.normal(size=3), float(g.uniform(0.1, 2.5)))
                 gt[str(im)].append({"cam_R_m2c": R.reshape(-1).tolist(), "cam_t_m2c": (g.normal(size=3) * 80.0 + np.array([0, 0, 900.0])).tolist(),
                                     "obj_id": oid})
-                gt_info[str(im)].append({"bbox_visib": [x0, y0, 11, 9], "bbox_obj": [x0, y0, 11, 9], "px_count_visib": 99})
+                gt_info[str(im)].append({"bbox_visib": [x0, y0, ww, hh], "bbox_obj": [x0, y0, ww, hh], "px_count_visib": hh * ww})
             Image.fromarray(mask).save(os.path.join(sd, "mask_visib", f"{im:06d}.png"))
         with open(os.path.join(sd, "scene_gt.json"), "w") as f:
             json.dump(gt, f)
@@ -637,26 +637,40 @@ def _texture(g: np.random.Generator, h: int, w: int) -> np.ndarray:
     return img
 
 
+def _warped_view(tex: np.ndarray, g: np.random.Generator, H: int, W: int, pad: int) -> np.ndarray:
+    """The texture seen through a small similarity transform (bilinear sampling) with additive noise."""
+    ang, s = np.deg2rad(g.uniform(-6, 6)), g.uniform(0.95, 1.05)
+    ty, tx = g.uniform(-8, 8, size=2)
+    yy, xx = np.meshgrid(np.arange(H) - H / 2, np.arange(W) - W / 2, indexing="ij")
+    sy = s * (np.cos(ang) * yy - np.sin(ang) * xx) + H / 2 + pad + ty
+    sx = s * (np.sin(ang) * yy + np.cos(ang) * xx) + W / 2 + pad + tx
+    sy, sx = np.clip(sy, 0, tex.shape[0] - 1.001), np.clip(sx, 0, tex.shape[1] - 1.001)
+    y0, x0 = np.floor(sy).astype(int), np.floor(sx).astype(int)
+    fy, fx = sy - y0, sx - x0
+    return (tex[y0, x0] * (1 - fy) * (1 - fx) + tex[y0, x0 + 1] * (1 - fy) * fx + tex[y0 + 1, x0] * fy * (1 - fx)
+            + tex[y0 + 1, x0 + 1] * fy * fx) + g.normal(size=(H, W)) * 0.01
+
+
+def _to_u8(a: np.ndarray) -> np.ndarray:
+    return np.clip(np.round(a * 255.0), 0, 255).astype(np.uint8)
+
+
 def textured_frame_pair(seed: int, hw: Tuple[int, int], related: bool = True) -> Tuple[np.ndarray, np.ndarray]:
     """Two uint8 grey frames ``[H,W]``: the anchor is a crop of a synthetic texture, the query the same texture seen through a
-    small similarity transform (bilinear sampling) with additive noise -- or, with ``related=False``, another texture."""
+    small similarity transform with additive noise -- or, with ``related=False``, another texture."""
     g = np.random.default_rng(seed)
     H, W = hw
     pad = 24
     tex = _texture(g, H + 2 * pad, W + 2 * pad)
     anchor = tex[pad:pad + H, pad:pad + W]
-    if related:
-        ang, s = np.deg2rad(g.uniform(-6, 6)), g.uniform(0.95, 1.05)
-        ty, tx = g.uniform(-8, 8, size=2)
-        yy, xx = np.meshgrid(np.arange(H) - H / 2, np.arange(W) - W / 2, indexing="ij")
-        sy = s * (np.cos(ang) * yy - np.sin(ang) * xx) + H / 2 + pad + ty
-        sx = s * (np.sin(ang) * yy + np.cos(ang) * xx) + W / 2 + pad + tx
-        sy, sx = np.clip(sy, 0, tex.shape[0] - 1.001), np.clip(sx, 0, tex.shape[1] - 1.001)
-        y0, x0 = np.floor(sy).astype(int), np.floor(sx).astype(int)
-        fy, fx = sy - y0, sx - x0
-        query = (tex[y0, x0] * (1 - fy) * (1 - fx) + tex[y0, x0 + 1] * (1 - fy) * fx + tex[y0 + 1, x0] * fy * (1 - fx)
-                 + tex[y0 + 1, x0 + 1] * fy * fx) + g.normal(size=(H, W)) * 0.01
-    else:
-        query = _texture(g, H, W)
-    to_u8 = lambda a: np.clip(np.round(a * 255.0), 0, 255).astype(np.uint8)  # noqa: E731
-    return to_u8(anchor), to_u8(query)
+    query = _warped_view(tex, g, H, W, pad) if related else _texture(g, H, W)
+    return _to_u8(anchor), _to_u8(query)
+
+
+def textured_frames(seed: int, hw: Tuple[int, int], n: int) -> list:
+    """``n`` uint8 grey views ``[H,W]`` of one synthetic texture (the first is the plain crop): any two of them match."""
+    g = np.random.default_rng(seed)
+    H, W = hw
+    pad = 24
+    tex = _texture(g, H + 2 * pad, W + 2 * pad)
+    return [_to_u8(tex[pad:pad + H, pad:pad + W])] + [_to_u8(_warped_view(tex, g, H, W, pad)) for _ in range(n - 1)]

@@ -56,6 +56,17 @@ def dict_from_preds(perf_file: str):
     return preds, ious_a, ious_q, iou_present
 
 
+def zero_based_faces(obj_models: dict) -> dict:
+    """Face indices as the rasteriser needs them: OBJ files (NOCS) count from 1, PLY files (TOYL) from 0."""
+    out = {}
+    for k, m in obj_models.items():
+        m = dict(m)
+        if "faces" in m and len(m["faces"]) and int(np.min(m["faces"])) >= 1 and int(np.max(m["faces"])) == len(m["pts"]):
+            m["faces"] = np.asarray(m["faces"]) - 1
+        out[k] = m
+    return out
+
+
 class CudaPoseErrors:
     """Object models / symmetry sets resident on the GPU + ``oryon_eval_pose_errors``.  ``__call__(cls_ids, pred [P,4,4],
     gt [P,4,4], cams [P,3,3]) -> float64 [P,6]``: R error (deg), T error (cm), ADD or ADD-S (m), ADD-S flag, MSSD (mm),

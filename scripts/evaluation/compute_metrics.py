@@ -30,7 +30,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oryon_b200.utils.evaluator import Evaluator, dict_from_preds  # noqa: E402
+from oryon_b200.utils.evaluator import Evaluator, dict_from_preds, zero_based_faces  # noqa: E402
 
 
 def pair_results(dataset, preds: dict, ious_a: dict, ious_q: dict, iou_present: bool) -> Iterator[Tuple[bool, dict]]:
@@ -52,17 +52,6 @@ def pair_results(dataset, preds: dict, ious_a: dict, ious_q: dict, iou_present: 
             res["iou_a"] = torch.tensor(ious_a[instance_id]).unsqueeze(0)
             res["iou_q"] = torch.tensor(ious_q[instance_id]).unsqueeze(0)
         yield bool(valid), res
-
-
-def zero_based_faces(obj_models: dict) -> dict:
-    """Face indices as the rasteriser needs them: OBJ files (NOCS) count from 1, PLY files (TOYL) from 0."""
-    out = {}
-    for k, m in obj_models.items():
-        m = dict(m)
-        if "faces" in m and len(m["faces"]) and int(np.min(m["faces"])) >= 1 and int(np.max(m["faces"])) == len(m["pts"]):
-            m["faces"] = np.asarray(m["faces"]) - 1
-        out[k] = m
-    return out
 
 
 def compute_metrics(results_file: str, dataset, exp_tag: str = "", compute_vsd: bool = True, print_summary: bool = False,

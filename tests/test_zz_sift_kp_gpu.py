@@ -53,3 +53,28 @@ def test_kp_correspondences_vs_reference_golden(case, variant):
         assert np.array_equal(got.numpy(), want)
     else:
         pytest.skip("near-tie rows differ from the reference argmin; covered by test_kp_rows_vs_reference_golden")
+
+
+def test_sift_baseline_loop_on_the_library(tmp_path):
+    """scripts/evaluation/sift_baseline.py end to end on liboryon_b200 (matching, lifting, PointDSC, evaluator incl. VSD) over the
+    textured synthetic TOYL tree: one line per pair with the ids of the split and a rigid transform, all pairs registered."""
+    need_gpu()
+    import json
+    from test_sift_baseline_cpu import baseline, toyl_dataset, write_textured_toyl_tree
+    d = str(tmp_path / "data")
+    ds = toyl_dataset(d, write_textured_toyl_tree(d))
+    root = tmp_path / "pointdsc" / "snapshot" / "PointDSC_3DMatch_release"
+    (root / "models").mkdir(parents=True)
+    cfg = dict(synth.POINTDSC_DEFAULT_CFG)
+    json.dump(cfg, open(root / "config.json", "w"))
+    torch.save(synth.pointdsc_state_dict(300), str(root / "models" / "model_best.pkl"))
+    out = tmp_path / "sift_toyl_oracle.txt"
+    torch.manual_seed(5)
+    ev = baseline.run_baseline(ds, baseline.CudaPath(str(tmp_path / "pointdsc"), "cuda:0"), "toyl", "oracle", None, True, str(out))
+    lines = out.read_text().splitlines()
+    assert len(lines) == len(ds) and len(ev.metrics["instance_id"]) == len(ds) and len(ev.metrics["VSD"]) == len(ds)
+    for line, inst in zip(lines, ds.instances):
+        id_a, id_q, pose = line.split(",")
+        assert id_a == f"{inst[1]} {inst[2]} {inst[-1]}" and id_q == f"{inst[3]} {inst[4]} {inst[-1]}"
+        T = np.asarray([float(v) for v in pose.split(" ")]).reshape(3, 4)
+        assert np.isfinite(T).all() and abs(np.linalg.det(T[:, :3]) - 1.0) < 1e-3
