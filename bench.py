@@ -118,6 +118,42 @@ def cpu_port_sample(rows, threads, D=WORKLOAD["D"], n=WORKLOAD["H"] * WORKLOAD["
     return best
 
 
+def eager_torch_sample(device, dtype, rows, D=WORKLOAD["D"], n=WORKLOAD["H"] * WORKLOAD["W"], row_chunk=256, repeats=3, seed=0):
+    """Optional extra (`--eager-baseline`): the reference's own formulation of the matcher (utils/pcd.py:202-204: broadcast
+    `cosine_similarity`, `amin`, `argmin`) as plain PyTorch eager ops on `device` -- what the unmodified reference does with
+    `corrs_device='cuda'` (float16, :195-197) or with float32 features moved to the GPU -- in row chunks, because the
+    N1 x N2 x D broadcast of one config-2 pair (94 GB in float16) does not fit.  Seconds per call, best of `repeats`."""
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn(rows, D, generator=g).to(device=device, dtype=dtype)
+    f2 = torch.randn(n, D, generator=g).to(device=device, dtype=dtype)
+    cos = torch.nn.functional.cosine_similarity
+    sync = torch.cuda.synchronize if torch.device(device).type == "cuda" else (lambda *a: None)
+    best = float("inf")
+    for _ in range(repeats + 1):                   # the first pass warms the allocator up
+        sync()
+        t0 = time.perf_counter()
+        mins, args_ = [], []
+        for r0 in range(0, rows, row_chunk):
+            d = 0.5 * (-1 * cos(f1[r0:r0 + row_chunk].unsqueeze(1), f2.unsqueeze(0), dim=2) + 1)
+            mins.append(torch.amin(d, dim=1))
+            args_.append(torch.argmin(d, dim=1))
+        torch.cat(mins), torch.cat(args_)
+        sync()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def eager_baseline(device, rows=None):
+    n = WORKLOAD["H"] * WORKLOAD["W"]
+    rows = rows or n
+    out = {"what": "reference formulation (utils/pcd.py:202-204) as PyTorch eager ops on the GPU, row chunks of 256; not the product path",
+           "sample": f"{rows} of {n} anchor rows of one pair x all {n} query positions, D={WORKLOAD['D']}"}
+    for name, dt in (("f32", torch.float32), ("f16", torch.float16)):
+        sec = eager_torch_sample(device, dt, rows)
+        out[name] = {"pairs_per_s": (rows / n) / sec, "ms_per_pair": sec * 1e3 * n / rows}
+    return out
+
+
 NCU_TRAFFIC_BYTES = 331.953664e6 + 25.663232e6   # profiles/r01_match_kernels_ncu_run38.md (config 2, one launch)
 
 
@@ -286,6 +322,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=4096, help="anchor rows of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager-baseline", action="store_true", help="also time the reference's formulation as PyTorch eager ops on the GPU (extra key)")
     ap.add_argument("--no-full-path", action="store_true", help="skip the extra full-pipeline measurement (network + post-network)")
     ap.add_argument("--full-pairs", type=int, default=16)
     ap.add_argument("--full-path-medium", action="store_true", help="also time the full path with single-product fp16 GEMMs (not the parity mode)")
@@ -449,6 +486,11 @@ def main():
             line["cpu_baseline"] = {"value": (args.cpu_rows / n) / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_rows} of {n} anchor rows of one pair x all {n} query positions, D={D}; "
                                               f"{sec:.1f} s measured, scaled by {n / args.cpu_rows:.1f}"}
+        if args.eager_baseline and world == 1:
+            try:
+                line["gpu_eager_baseline"] = eager_baseline(f"cuda:{local}")
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": repr(e)}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -44,3 +44,19 @@ def test_product_arms_fail_loudly_without_a_gpu(script):
     p = _run(script)
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout) and "no CPU fallback" in (p.stderr + p.stdout)
     assert p.stdout.strip() == "", "nothing that could be mistaken for a result line"
+
+
+def test_eager_baseline_helper_matches_the_oracle_formulation():
+    """`bench.py --eager-baseline` times the reference's formulation as PyTorch eager ops; on a tiny CPU case the helper runs and its
+    arithmetic is the oracle's (same broadcast cosine / amin / argmin)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oryon_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.eager_torch_sample("cpu", torch.float32, 48, D=16, n=200, row_chunk=20, repeats=1) > 0
+    import oryon_oracle as oracle
+    g = torch.Generator().manual_seed(0)
+    f1, f2 = torch.randn(48, 16, generator=g), torch.randn(200, 16, generator=g)
+    d = 0.5 * (-1 * torch.nn.functional.cosine_similarity(f1.unsqueeze(1), f2.unsqueeze(0), dim=2) + 1)
+    md, mi = oracle.match_rows(f1, f2)
+    assert torch.equal(torch.amin(d, 1), md) and torch.equal(torch.argmin(d, 1), mi)
