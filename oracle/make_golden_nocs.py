@@ -39,7 +39,7 @@ import torchvision  # noqa: E402
 import torchvision.transforms.functional as TVF  # noqa: E402
 
 _orig_resize = TVF.resize
-TVF.resize = functools.wraps(_orig_resize)(lambda img, size, interpolation, **kw: _orig_resize(img, size, interpolation, antialias=False, **kw))
+TVF.resize = functools.wraps(_orig_resize)(lambda img, size, interpolation, **kw: _orig_resize(img, size, interpolation, **{**kw, "antialias": False}))
 
 from omegaconf import DictConfig  # noqa: E402  (shim: dict with attribute access)
 from utils.data import common as ref_common, nocs as ref_nocs  # noqa: E402  (reference)

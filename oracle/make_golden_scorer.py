@@ -29,6 +29,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, HERE)
 import make_golden_toyl as mgt  # noqa: E402  (installs the shims and stand-ins at import)
+import make_golden_nocs as mgn  # noqa: E402
 import vsd_oracle  # noqa: E402
 
 _stub = types.ModuleType("bop_toolkit_lib.renderer_vispy")
@@ -44,7 +45,7 @@ from oryon_b200 import synth  # noqa: E402
 HW = (480, 640)
 
 
-def reference_scorer(datasets_env: dict, args) -> dict:
+def reference_scorer(datasets_env: dict, args, evaluator_cls=Evaluator) -> dict:
     src = open(os.path.join(mgt.ref_shims.REFERENCE_ROOT, "scripts", "evaluation", "compute_metrics.py")).read().split("\n")
     start = next(i for i, l in enumerate(src) if l.startswith("def dict_from_preds"))
     end = next(i for i, l in enumerate(src) if l.startswith("def main"))
@@ -53,7 +54,8 @@ def reference_scorer(datasets_env: dict, args) -> dict:
         load = staticmethod(lambda path: args)
 
     env = {"os": os, "sys": sys, "np": np, "json": json, "torch": torch, "Optional": Optional, "join": os.path.join, "OmegaConf": OmegaConf,
-           "open_dict": lambda a: contextlib.nullcontext(a), "Evaluator": Evaluator, "NOCSDataset": None, "TOYLDataset": datasets_env["TOYLDataset"]}
+           "open_dict": lambda a: contextlib.nullcontext(a), "Evaluator": evaluator_cls, "NOCSDataset": datasets_env.get("NOCSDataset"),
+           "TOYLDataset": datasets_env.get("TOYLDataset")}
     exec("\n".join(src[start:end]), env)
     return env
 
@@ -70,7 +72,7 @@ def perturbed_predictions(ds, seed: int):
         d[:3, :3] = synth._axis_rotation(g.normal(size=3), 0.02 * (i + 1) ** 2)
         d[:3, 3] = g.normal(size=3) * 0.002 * (i + 1) ** 2
         pred = (d @ rel).astype(np.float32) if i != len(ds) - 1 else np.zeros((4, 4), np.float32)
-        sa, ia, sq, iq, obj = instance_id.split("_")
+        sa, ia, sq, iq, obj = instance_id.split("_", 4)          # NOCS object names hold underscores
         pose = " ".join(str(n) for n in pred[:3, :].flatten())
         lines.append(",".join([f"{sa} {ia} {obj}", f"{sq} {iq} {obj}", pose, str(np.float32(g.uniform(0.2, 1.0))), str(np.float32(g.uniform(0.2, 1.0)))]) + "\n")
     return lines
@@ -98,6 +100,36 @@ def main(seed=0):
             out[tag] = dict(obj=obj_split, csv=csv_lines, metrics=json.load(open(os.path.splitext(csv)[0] + ".json")), latex=open(tex).read())
             print(tag, out[tag]["latex"])
     with open(os.path.join(ROOT, "tests", "golden", f"scorer_{seed}.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    main_nocs(seed)
+
+
+class EvaluatorWithoutVSD(Evaluator):
+    """The reference evaluator with ``compute_vsd`` forced off: the scorer hard-codes ``compute_vsd=True`` (:84), and the NOCS
+    models carry 1-based OBJ face indices that only the reference's OpenGL renderer can take as they are."""
+
+    def __init__(self, exp_tag, compute_vsd=True, compute_iou=True):
+        super().__init__(exp_tag, compute_vsd=False, compute_iou=compute_iou)
+
+
+def main_nocs(seed=0):
+    """``tests/golden/scorer_nocs_<seed>.json``: the same for the NOCS tree (pairs keyed by object NAME), VSD / AR off."""
+    env = mgn.reference_dataset_classes()
+    with tempfile.TemporaryDirectory() as d:
+        info = synth.write_nocs_tree(d, seed)
+        args = mgt.cfg(dict(augs=dict(), debug_valid="no", use_seed=False, seed=1, exp_tag="synthetic nocs",
+                            dataset=dict(root=d, max_corrs=500, img_size=[224, 224], test=dict(name=info["name"], split=info["split"], obj="all")),
+                            test=dict(mask="predicted", add_description="yes")))
+        lines = perturbed_predictions(env["NOCSDataset"](args, eval=True), seed + 1)
+        csv_lines = [",".join(l.split(",")[:3]) + "\n" for l in lines]          # the split holds an invalid pair: no IoUs (see main)
+        os.makedirs(os.path.join(d, "results"), exist_ok=True)
+        csv = os.path.join(d, "results", "nocs_noiou_r_s_t.csv")
+        open(csv, "w").writelines(csv_lines)
+        tex = os.path.join(d, "results", "nocs.tex")
+        reference_scorer(env, args, EvaluatorWithoutVSD)["compute_metrics"](csv, False, tex)
+        out = dict(obj="all", csv=csv_lines, metrics=json.load(open(os.path.splitext(csv)[0] + ".json")), latex=open(tex).read())
+        print("nocs", out["latex"])
+    with open(os.path.join(ROOT, "tests", "golden", f"scorer_nocs_{seed}.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 

@@ -29,7 +29,7 @@ ref_shims.install()
 import torchvision.transforms.functional as TVF  # noqa: E402
 
 _orig_resize = TVF.resize
-TVF.resize = functools.wraps(_orig_resize)(lambda img, size, interpolation, **kw: _orig_resize(img, size, interpolation, antialias=False, **kw))
+TVF.resize = functools.wraps(_orig_resize)(lambda img, size, interpolation, **kw: _orig_resize(img, size, interpolation, **{**kw, "antialias": False}))
 
 from utils.data import common as ref_common  # noqa: E402  (reference)
 from utils import augmentations as ref_augs  # noqa: E402

@@ -10,11 +10,12 @@ import numpy as np
 import pytest
 
 from oryon_b200 import synth
-from oryon_b200.datasets import TOYLDataset
+from oryon_b200.datasets import NOCSDataset, TOYLDataset
 from oryon_b200.utils.evaluator import format_sym_set
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "scorer_0.json")))
+GOLD["nocs"] = json.load(open(os.path.join(ROOT, "tests", "golden", "scorer_nocs_0.json")))      # NOCS tree, pairs keyed by object name, VSD off
 
 _spec = importlib.util.spec_from_file_location("oryon_compute_metrics", os.path.join(ROOT, "scripts", "evaluation", "compute_metrics.py"))
 scorer = importlib.util.module_from_spec(_spec)
@@ -27,8 +28,18 @@ def tree(tmp_path_factory):
     return d, synth.write_toyl_tree(d, 0, hw=(480, 640))
 
 
+@pytest.fixture(scope="module")
+def nocs_tree(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("nocs_scorer"))
+    return d, synth.write_nocs_tree(d, 0)
+
+
 def _dataset(tree, obj_split):
     d, info = tree
+    if info["name"] == "nocs":
+        args = dict(device="cuda:0", dataset=dict(root=d, max_corrs=500, img_size=[224, 224], test=dict(name=info["name"], split=info["split"], obj=obj_split)),
+                    test=dict(mask="predicted", add_description="yes"))
+        return NOCSDataset(args, eval=True)
     args = dict(device="cuda:0", dataset=dict(root=d, max_corrs=500, img_size=[224, 224], test=dict(name=info["name"], split=info["split"], obj=obj_split)),
                 test=dict(mask="predicted", add_description="yes"))
     return TOYLDataset(args, eval=True)
@@ -41,7 +52,9 @@ def _score(tree, tag, backend_factory, tmp_path):
     csv.write_text("".join(gold["csv"]))
     tex = tmp_path / f"{tag}.tex"
     models, _, symms = ds.get_object_info()
-    ev = scorer.compute_metrics(str(csv), ds, "synthetic", True, False, str(tex), pose_errors=backend_factory(models, symms))
+    vsd = tag != "nocs"
+    ev = scorer.compute_metrics(str(csv), ds, "synthetic nocs" if tag == "nocs" else "synthetic", vsd, False, str(tex),
+                                pose_errors=backend_factory(models, symms))
     got = json.load(open(tmp_path / f"toyl_{tag}.json"))
     assert list(got.keys()) == list(gold["metrics"].keys())
     for k, v in gold["metrics"].items():
@@ -49,7 +62,7 @@ def _score(tree, tag, backend_factory, tmp_path):
             assert got[k] == v, k
         else:
             np.testing.assert_allclose(np.asarray(got[k], dtype=np.float64), np.asarray(v, dtype=np.float64), rtol=1e-9, atol=1e-7, err_msg=k)
-    for k in ("VSD", "AR", "MSSD", "MSPD", "ADD(S)-0.1d"):
+    for k in (("VSD", "AR") if vsd else ()) + ("MSSD", "MSPD", "ADD(S)-0.1d"):
         assert [float(x) for x in got[k]] == [float(x) for x in gold["metrics"][k]], k       # thresholded: exact
     assert tex.read_text() == gold["latex"]
     return ev
@@ -65,6 +78,11 @@ def test_scorer_matches_reference_scorer(tree, tag, tmp_path):
     ev = _score(tree, tag, _oracle_backend, tmp_path)
     if tag == "noiou":
         assert "1_0_2_2_5" in ev.metrics["instance_id"]              # the pair without correspondences: a failure row
+
+
+def test_scorer_matches_reference_scorer_nocs(nocs_tree, tmp_path):
+    ev = _score(nocs_tree, "nocs", _oracle_backend, tmp_path)
+    assert "1_1_2_0_bowl_synth_b" in ev.metrics["instance_id"] and sum(ev.counts["Missing segm"]) == 1
 
 
 def test_scorer_failure_rows_keep_ious(tree, tmp_path):
