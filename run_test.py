@@ -134,6 +134,18 @@ def dataset_pair_ids(ds, pair_index: int) -> tuple:
     return ds.frame_ids(pair_index)
 
 
+def score_csv(csv_path: str, ds, exp_tag: str = "", compute_vsd: bool = True, pose_errors=None):
+    """What the reference's ``on_test_end`` leaves behind (pipeline.py:357-370: summary, metrics JSON, LaTeX row), computed on
+    rank 0 from the gathered prediction CSV by the offline scorer (scripts/evaluation/compute_metrics.py) -- every pair
+    exactly once, whatever the number of ranks.  The JSON goes next to the CSV, summary and LaTeX row to stdout (= stderr
+    while the loop owns the result line)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oryon_compute_metrics", os.path.join(ROOT, "scripts", "evaluation", "compute_metrics.py"))
+    scorer = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scorer)
+    return scorer.compute_metrics(csv_path, ds, exp_tag, compute_vsd, True, None, pose_errors=pose_errors)
+
+
 def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real_stdout: int) -> None:
     """The test loop over a mounted dataset in the reference's NOCS or TOYL layout: ``NOCSDataset`` / ``TOYLDataset`` samples -> ``GpuCollate`` (decode on
     the host, resize / normalise on the GPU) -> ``test_step``.  Rank 0 writes the prediction CSV; scoring it is the offline
@@ -154,6 +166,8 @@ def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real
     res = run_sharded(len(ds), args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize,
                       id_fn=lambda i: dataset_pair_ids(ds, i))
     pipe.on_test_end()
+    if rank == 0 and args.score:
+        score_csv(args.out, ds, exp_tag=f"{args.dataset} {args.split} {args.obj} ({args.mask})", compute_vsd=not args.no_vsd)
     if rank == 0:
         line = json.dumps({"metric": "image-pairs/sec (whole test loop, decode included)", "value": len(ds) / res["seconds"], "unit": "pairs/s",
                            "n_gpus": world, "pairs": len(ds), "batch": args.batch, "seconds": res["seconds"], "status": res["status"],
@@ -189,6 +203,8 @@ def main(argv=None):
     ap.add_argument("--swin", default=None, help="torchvision swin_b weights")
     ap.add_argument("--catseg", default=None, help="CATSeg checkpoint (pretrained_models/catseg.pth)")
     ap.add_argument("--ckpt", default=None, help="the reference's Lightning checkpoint (args.eval.ckpt)")
+    ap.add_argument("--score", action="store_true", help="dataset mode: rank 0 scores the gathered CSV at the end (metrics JSON next to --out, LaTeX row)")
+    ap.add_argument("--no-vsd", action="store_true", help="with --score: skip VSD / AR")
     ap.add_argument("--pointdsc", default=None, help="PointDSC snapshot directory (args.pretrained.pointdsc)")
     args = ap.parse_args(argv)
 

@@ -97,3 +97,10 @@ def test_dataset_mode_ids_and_config_from_a_nocs_tree(tmp_path):
     from oryon_b200.utils.evaluator import dict_from_preds
     preds, *_ = dict_from_preds(str(path))
     assert "1_0_2_0_mug_synth_a" in preds and len(preds) == len(ds)
+    # --score: rank 0 scores the gathered CSV over the same dataset (the reference's on_test_end outputs); oracle error backend on the CPU
+    from oryon_b200.utils.evaluator import format_sym_set
+    from test_evaluator_cpu import _OracleBackend
+    models, _, symms = ds.get_object_info()
+    ev = run_test.score_csv(str(path), ds, "loop", compute_vsd=False, pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
+    assert len(ev.metrics["instance_id"]) == len(ds) and (tmp_path / "pred.json").exists()
+    assert sum(ev.counts["Missing segm"]) == 1                      # the tree's pair without correspondences
