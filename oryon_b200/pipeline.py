@@ -1,6 +1,7 @@
 """Mirror of the inference part of the reference ``pipeline.py``: ``FPM_Pipeline`` with ``forward`` (:593),
 ``test_step`` (:306-355), ``is_detection_valid`` (:372-395), ``get_featmap_corrs`` (:397-427), ``get_pose``
-(:429-472) and ``add_pred_pose`` (:490-497).  Same names, argument meaning, failure rows and CSV wire format.
+(:429-472), ``add_pred_pose`` (:490-497), ``get_dataset`` (:84-98), ``get_pred_filename`` (:474-488) and
+``get_test_dataloader`` (:533-549).  Same names, argument meaning, failure rows and CSV wire format.
 
 Every arithmetic step runs in liboryon_b200.so: the network (``oryon_backbone_forward``), mask post-processing
 (``oryon_mask_postproc``), matching (``oryon_match_nn``), scaling / lifting (``oryon_corrs_to_pcd``) and
@@ -72,6 +73,54 @@ def format_pred_line(id_a: str, id_q: str, mask_a_iou, mask_q_iou, pred_pose: np
     return ",".join([id_a, id_q, pose, str(mask_a_iou), str(mask_q_iou)]) + "\n"
 
 
+def get_dataset(args, eval: bool = True):
+    """``FPM_Pipeline.get_dataset`` (pipeline.py:84-98): the dataset class named by ``args.dataset.test.name`` (``train.name``
+    when not ``eval``).  The test-time readers are here; 'shapenet6d' is the reference's TRAINING set and is not."""
+    from .datasets import NOCSDataset, TOYLDataset
+    name = _get(args, "dataset.test.name" if eval else "dataset.train.name")
+    if name == "nocs":
+        return NOCSDataset(args, eval)
+    if name == "toyl":
+        return TOYLDataset(args, eval)
+    if name == "shapenet6d":
+        raise NotImplementedError("Dataset shapenet6d is the reference's training set: outside the inference path")
+    raise RuntimeError(f"Dataset {name} not supported")
+
+
+def pred_filenames(args, now=None, rand_seed: Optional[int] = None) -> Tuple[str, str, str]:
+    """The three result files of a test run (pipeline.py:474-488): ``<name>_<split>_<obj>_<ddmmYYYY_HHMM>_<rand>.csv`` / ``.json``
+    and ``config_<ddmmYYYY_HHMM>_<rand>.yaml`` under ``args.tmp.results_out`` -- the naming the reference's offline scorer
+    relies on to find the configuration next to a CSV (scripts/evaluation/compute_metrics.py:56-58).  ``rand`` is drawn from
+    numpy's global generator as in the reference."""
+    import os
+    from datetime import datetime
+    stamp = (now or datetime.now()).strftime("%d%m%Y_%H%M")
+    rand = int(np.random.randint(0, 1000)) if rand_seed is None else int(rand_seed)
+    base = f"{_get(args, 'dataset.test.name')}_{_get(args, 'dataset.test.split')}_{_get(args, 'dataset.test.obj')}_{stamp}_{rand}"
+    out = _get(args, "tmp.results_out", ".")
+    return os.path.join(out, base + ".csv"), os.path.join(out, base + ".json"), os.path.join(out, f"config_{stamp}_{rand}.yaml")
+
+
+class TestLoader:
+    """What ``get_test_dataloader`` returns in place of ``DataLoader(test_set, batch_size, collate_fn=test_set.collate,
+    shuffle=False, num_workers=8)`` (pipeline.py:533-549): batches of consecutive samples in dataset order, the last one short,
+    each collated by the dataset's ``GpuCollate`` (decode on the host, resize / normalise on the GPU).  ``indices`` restricts the
+    loader to a rank's share of the pairs (``sharding.shard_pairs``)."""
+    __test__ = False            # not a pytest class
+
+    def __init__(self, dataset, batch_size: int, indices: Optional[List[int]] = None, collate=None):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+        self.indices = list(range(len(dataset))) if indices is None else list(indices)
+        self.collate = collate if collate is not None else dataset.collate
+
+    def __len__(self) -> int:
+        return (len(self.indices) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for b0 in range(0, len(self.indices), self.batch_size):
+            yield self.collate([self.dataset[i] for i in self.indices[b0:b0 + self.batch_size]])
+
+
 class FPM_Pipeline:
     def __init__(self, args, test_model: bool = False, *, model: Optional[Oryon] = None, pointdsc_solver=None, evaluator=None):
         self.args = args
@@ -103,6 +152,21 @@ class FPM_Pipeline:
     # ---- LightningModule surface -----------------------------------------------------------------------
     def forward(self, x: dict) -> Dict[str, Tensor]:
         return self.model.forward(x)
+
+    def get_dataset(self, eval: bool = True):
+        return get_dataset(self.args, eval)
+
+    def get_pred_filename(self) -> Tuple[str, str]:
+        """Paths of the prediction CSV and the metrics JSON (pipeline.py:474-488; the reference returns open file objects and also
+        dumps its hydra configuration next to them)."""
+        csv, metrics, _ = pred_filenames(self.args)
+        return csv, metrics
+
+    def get_test_dataloader(self, indices: Optional[List[int]] = None) -> "TestLoader":
+        test_set = self.get_dataset(eval=True)
+        print("TESTING on {}, split {}, object split {}. Samples: {}".format(test_set.name, test_set.split, test_set.obj, len(test_set)))
+        self.test_dataset = test_set
+        return TestLoader(test_set, int(_get(self.args, "dataset.batch_size", 32)), indices)
 
     def on_test_start(self, pred_path: Optional[str] = None, seed: Optional[int] = None):
         """Opens the prediction CSV and seeds numpy / torch as ``set_deterministic_seed`` (utils/misc.py:186-196,

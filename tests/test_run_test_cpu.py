@@ -104,3 +104,33 @@ def test_dataset_mode_ids_and_config_from_a_nocs_tree(tmp_path):
     ev = run_test.score_csv(str(path), ds, "loop", compute_vsd=False, pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
     assert len(ev.metrics["instance_id"]) == len(ds) and (tmp_path / "pred.json").exists()
     assert sum(ev.counts["Missing segm"]) == 1                      # the tree's pair without correspondences
+
+
+def test_pipeline_test_side_surface(tmp_path):
+    """get_dataset / get_pred_filename / get_test_dataloader (pipeline.py:84-98, :474-488, :533-549) as module-level helpers (the
+    class itself needs a GPU): dataset selection by name, the file naming the offline scorer relies on, consecutive batches."""
+    import datetime
+    from oryon_b200 import pipeline, synth
+    from oryon_b200.datasets import NOCSDataset, TOYLDataset
+    nocs, toyl = synth.write_nocs_tree(str(tmp_path), 0), synth.write_toyl_tree(str(tmp_path), 0)
+    args = dict(device="cuda:0", tmp=dict(results_out=str(tmp_path)),
+                dataset=dict(root=str(tmp_path), max_corrs=500, img_size=[224, 224], batch_size=4, test=dict(name="nocs", split=nocs["split"], obj="all")),
+                test=dict(mask="oracle", add_description="yes"))
+    ds = pipeline.get_dataset(args, eval=True)
+    assert isinstance(ds, NOCSDataset) and len(ds) == len(nocs["pairs"])
+    args["dataset"]["test"]["name"] = "toyl"
+    assert isinstance(pipeline.get_dataset(args, eval=True), TOYLDataset)
+    args["dataset"]["test"]["name"] = "linemod"
+    with pytest.raises(RuntimeError, match="Dataset linemod not supported"):
+        pipeline.get_dataset(args, eval=True)
+    args["dataset"]["test"]["name"] = "nocs"
+    csv, metrics, cfg = pipeline.pred_filenames(args, now=datetime.datetime(2024, 3, 9, 7, 5), rand_seed=42)
+    assert os.path.basename(csv) == "nocs_cross_scene_test_all_09032024_0705_42.csv" and metrics == csv[:-4] + ".json"
+    assert os.path.basename(cfg) == "config_09032024_0705_42.yaml"
+    # the reference scorer rebuilds the configuration name from the last three '_' fields of the CSV name (compute_metrics.py:56-57)
+    assert "config_" + "_".join(os.path.splitext(os.path.basename(csv))[0].split("_")[-3:]) + ".yaml" == os.path.basename(cfg)
+    loader = pipeline.TestLoader(ds, 4, collate=lambda samples: [s[5] for s in samples])        # stand-in collate: the pair ids
+    batches = list(loader)
+    assert len(loader) == len(batches) == 2 and [len(b) for b in batches] == [4, 2]
+    assert [i for b in batches for i in b] == [ds[i][5] for i in range(len(ds))]
+    assert [len(b) for b in pipeline.TestLoader(ds, 4, indices=[3, 4, 5], collate=lambda s: s)] == [3]
