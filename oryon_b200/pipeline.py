@@ -367,7 +367,7 @@ class FPM_Pipeline:
             poses = {b: T[i] for i, b in enumerate(todo)}
         return [corrs[b] if counts[b] >= 0 else None for b in range(B)], poses
 
-    def test_step(self, batch: dict, batch_idx: int = 0) -> List[dict]:
+    def test_step(self, batch: dict, batch_idx: int = 0, *, register_as_test: bool = True) -> List[dict]:
         """The reference's hot loop (pipeline.py:306-355) for one batch; returns (and accumulates in ``self.rows``)
         one record per pair: ids, ``pred_pose_rel`` (identity on failure, :335-350), ``pred_pose`` =
         ``pred_pose_rel @ anchor pose`` (:320), IoUs, status, and writes the CSV line when a file is open."""
@@ -409,22 +409,46 @@ class FPM_Pipeline:
                              iou_q=float(iou_q[b]), status=status, corrs=corrs[b]))
         self.rows.extend(rows)
         if self.evaluator is not None:
-            self._register(batch, rows)
+            self._register(batch, rows, test=register_as_test)
         return rows
 
-    def _register(self, batch: dict, rows: List[dict]) -> None:
-        """Evaluator bookkeeping of the reference's loop (pipeline.py:321-350), in pair order; consecutive successful
-        pairs go to the (batched, GPU) ``register_test`` in one call."""
+    def validation_step(self, batch: dict, batch_idx: int = 0) -> List[dict]:
+        """The inference part of the reference's ``validation_step`` (pipeline.py:196-247): the same per-pair path as
+        ``test_step``, registered through ``register_eval`` / ``register_valid_failure`` (no instance ids), no prediction CSV.
+        The loss terms of that hook (``FeatureLoss``) are training code and are not computed: the records are returned instead
+        of a loss."""
+        pred_file, self.pred_file = self.pred_file, None
+        try:
+            return self.test_step(batch, batch_idx, register_as_test=False)
+        finally:
+            self.pred_file = pred_file
+
+    @staticmethod
+    def _eval_depth(batch: dict, i: int):
+        """The query depth frame the evaluator's VSD term reads (``batch['query']['eval_depth'][i]``, pipeline.py:328), or None."""
+        frames = batch["query"].get("eval_depth") if isinstance(batch.get("query"), dict) else None
+        if frames is None:
+            return None
+        d = frames[i]
+        return d.squeeze().cpu().numpy() if isinstance(d, Tensor) else np.asarray(d).squeeze()
+
+    def _register(self, batch: dict, rows: List[dict], test: bool = True) -> None:
+        """Evaluator bookkeeping of the reference's loop (pipeline.py:321-350; :207-245 for validation), in pair order;
+        consecutive successful pairs go to the (batched, GPU) ``register_test`` / ``register_eval`` in one call."""
         def flush(run):
             if not run:
                 return
             sel = torch.tensor(run)
-            self.evaluator.register_test({
+            payload = {
                 "iou_a": torch.tensor([rows[i]["iou_a"] for i in run]), "iou_q": torch.tensor([rows[i]["iou_q"] for i in run]),
                 "gt_pose": batch["query"]["pose"].cpu()[sel], "pred_pose": torch.stack([rows[i]["pred_pose"] for i in run]),
                 "pred_pose_rel": torch.stack([rows[i]["pred_pose_rel"] for i in run]), "cls_id": [batch["cls_id"][i] for i in run],
-                "camera": [batch["query"]["camera"][i].cpu().numpy() for i in run], "depth": [None for _ in run],
-                "instance_id": [batch["instance_id"][i] for i in run]})
+                "camera": [batch["query"]["camera"][i].cpu().numpy() for i in run], "depth": [self._eval_depth(batch, i) for i in run]}
+            if test:
+                payload["instance_id"] = [batch["instance_id"][i] for i in run]
+                self.evaluator.register_test(payload)
+            else:
+                self.evaluator.register_eval(payload)
 
         run: List[int] = []
         for i, r in enumerate(rows):
@@ -433,6 +457,10 @@ class FPM_Pipeline:
                 continue
             flush(run)
             run = []
-            self.evaluator.register_test_failure({"iou_a": torch.tensor([r["iou_a"]]), "iou_q": torch.tensor([r["iou_q"]]),
-                                                  "cls_id": [batch["cls_id"][i]], "instance_id": [batch["instance_id"][i]]})
+            failure = {"iou_a": torch.tensor([r["iou_a"]]), "iou_q": torch.tensor([r["iou_q"]]), "cls_id": [batch["cls_id"][i]],
+                       "instance_id": [batch["instance_id"][i]]}
+            if test:
+                self.evaluator.register_test_failure(failure)
+            else:
+                self.evaluator.register_valid_failure(failure)
         flush(run)
