@@ -674,3 +674,13 @@ def textured_frames(seed: int, hw: Tuple[int, int], n: int) -> list:
     pad = 24
     tex = _texture(g, H + 2 * pad, W + 2 * pad)
     return [_to_u8(tex[pad:pad + H, pad:pad + W])] + [_to_u8(_warped_view(tex, g, H, W, pad)) for _ in range(n - 1)]
+
+
+def rescale_cases(seed: int = 0) -> Dict:
+    """name -> (coords, orig_scale, new_scale) for ``utils.misc.rescale_coords``: feature-map -> image and back, with out-of-range rows."""
+    g = _gen(4000 + seed)
+    f2 = torch.rand(40, 2, generator=g) * 230.0 - 10.0
+    i4 = torch.randint(-5, 200, (37, 4), generator=g)
+    fb = torch.rand(3, 25, 4, generator=g) * 192.0
+    return {"float_2col_up": (f2, (192, 192), (480, 640)), "int_4col_up": (i4, (192, 192), (224, 224)),
+            "float_batched_down": (fb, (192, 192), (48, 64)), "int_2col_down": (i4[:, :2].clone(), (192, 192), (24, 24))}
