@@ -168,6 +168,13 @@ class FPM_Pipeline:
         self.test_dataset = test_set
         return TestLoader(test_set, int(_get(self.args, "dataset.batch_size", 32)), indices)
 
+    def get_valid_dataloader(self, indices: Optional[List[int]] = None) -> "TestLoader":
+        """The validation loader reads the same evaluation dataset, in order (pipeline.py:517-531)."""
+        valid_set = self.get_dataset(eval=True)
+        print("VALIDATING on {}, split {}, object split {}. Samples: {}".format(valid_set.name, valid_set.split, valid_set.obj, len(valid_set)))
+        self.valid_dataset = valid_set
+        return TestLoader(valid_set, int(_get(self.args, "dataset.batch_size", 32)), indices)
+
     def on_test_start(self, pred_path: Optional[str] = None, seed: Optional[int] = None):
         """Opens the prediction CSV and seeds numpy / torch as ``set_deterministic_seed`` (utils/misc.py:186-196,
         pipeline.py:296-299: ``args.seed`` if ``use_seed`` else 1)."""
