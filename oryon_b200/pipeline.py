@@ -104,21 +104,46 @@ def pred_filenames(args, now=None, rand_seed: Optional[int] = None) -> Tuple[str
 class TestLoader:
     """What ``get_test_dataloader`` returns in place of ``DataLoader(test_set, batch_size, collate_fn=test_set.collate,
     shuffle=False, num_workers=8)`` (pipeline.py:533-549): batches of consecutive samples in dataset order, the last one short,
-    each collated by the dataset's ``GpuCollate`` (decode on the host, resize / normalise on the GPU).  ``indices`` restricts the
-    loader to a rank's share of the pairs (``sharding.shard_pairs``)."""
+    each collated by the dataset's ``GpuCollate`` (resize / normalise on the GPU) in the consumer's thread, on its stream.
+    The host part of a sample -- PNG decoding, ~10-20 ms per 480 x 640 frame, what the reference gives its 8 worker processes --
+    runs on ``workers`` threads (the decoders release the GIL), ``prefetch`` batches ahead of the consumer, so that the GPU step
+    of batch k overlaps the decoding of batches k+1.. .  ``indices`` restricts the loader to a rank's share of the pairs
+    (``sharding.shard_pairs``); ``workers=0`` reads in the calling thread."""
     __test__ = False            # not a pytest class
 
-    def __init__(self, dataset, batch_size: int, indices: Optional[List[int]] = None, collate=None):
+    def __init__(self, dataset, batch_size: int, indices: Optional[List[int]] = None, collate=None, workers: int = 8, prefetch: int = 2):
         self.dataset, self.batch_size = dataset, int(batch_size)
         self.indices = list(range(len(dataset))) if indices is None else list(indices)
         self.collate = collate if collate is not None else dataset.collate
+        self.workers, self.prefetch = int(workers), max(1, int(prefetch))
 
     def __len__(self) -> int:
         return (len(self.indices) + self.batch_size - 1) // self.batch_size
 
+    def _chunks(self) -> List[List[int]]:
+        return [self.indices[b0:b0 + self.batch_size] for b0 in range(0, len(self.indices), self.batch_size)]
+
     def __iter__(self):
-        for b0 in range(0, len(self.indices), self.batch_size):
-            yield self.collate([self.dataset[i] for i in self.indices[b0:b0 + self.batch_size]])
+        chunks = self._chunks()
+        if self.workers <= 0:
+            for chunk in chunks:
+                yield self.collate([self.dataset[i] for i in chunk])
+            return
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(self.workers, thread_name_prefix="oryon-decode") as pool:
+            pending: deque = deque()
+            nxt = 0
+            try:
+                while nxt < len(chunks) or pending:
+                    while nxt < len(chunks) and len(pending) <= self.prefetch:
+                        pending.append([pool.submit(self.dataset.__getitem__, i) for i in chunks[nxt]])
+                        nxt += 1
+                    yield self.collate([f.result() for f in pending.popleft()])      # a reader error surfaces here, in order
+            finally:
+                for futs in pending:
+                    for f in futs:
+                        f.cancel()
 
 
 class FPM_Pipeline:

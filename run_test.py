@@ -159,8 +159,15 @@ def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real
     if model.tokenizer is None:
         raise SystemExit("run_test.py: text prompts need the CLIP BPE vocabulary (--bpe)")
 
+    # this rank's batches, decoded on worker threads ahead of the GPU (the reference's DataLoader has 8 worker processes)
+    from oryon_b200.pipeline import TestLoader
+    batches = iter(TestLoader(ds, args.batch, list(sharding.shard_pairs(len(ds), rank, world)), workers=args.workers))
+
     def step(idx: Sequence[int]) -> List[dict]:
-        return pipe.test_step(ds.collate([ds[i] for i in idx]), idx[0] // args.batch)
+        batch = next(batches)
+        if len(batch["instance_id"]) != len(idx):
+            raise RuntimeError("run_test.py: loader and loop disagree on the batch boundaries")
+        return pipe.test_step(batch, idx[0] // args.batch)
 
     pipe.on_test_start(seed=args.seed + rank)
     res = run_sharded(len(ds), args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize,
@@ -203,6 +210,7 @@ def main(argv=None):
     ap.add_argument("--swin", default=None, help="torchvision swin_b weights")
     ap.add_argument("--catseg", default=None, help="CATSeg checkpoint (pretrained_models/catseg.pth)")
     ap.add_argument("--ckpt", default=None, help="the reference's Lightning checkpoint (args.eval.ckpt)")
+    ap.add_argument("--workers", type=int, default=8, help="dataset mode: decoding threads of the loader (pipeline.py:545 num_workers=8); 0 = in line")
     ap.add_argument("--score", action="store_true", help="dataset mode: rank 0 scores the gathered CSV at the end (metrics JSON next to --out, LaTeX row)")
     ap.add_argument("--no-vsd", action="store_true", help="with --score: skip VSD / AR")
     ap.add_argument("--pointdsc", default=None, help="PointDSC snapshot directory (args.pretrained.pointdsc)")

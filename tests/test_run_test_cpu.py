@@ -134,3 +134,20 @@ def test_pipeline_test_side_surface(tmp_path):
     assert len(loader) == len(batches) == 2 and [len(b) for b in batches] == [4, 2]
     assert [i for b in batches for i in b] == [ds[i][5] for i in range(len(ds))]
     assert [len(b) for b in pipeline.TestLoader(ds, 4, indices=[3, 4, 5], collate=lambda s: s)] == [3]
+    # decoding threads: same batches, same order, reader errors surface at the batch they belong to
+    want = list(pipeline.TestLoader(ds, 4, collate=lambda samples: [s[5] for s in samples], workers=0))
+    assert list(pipeline.TestLoader(ds, 4, collate=lambda samples: [s[5] for s in samples], workers=3, prefetch=1)) == want == batches
+
+    class Broken:
+        def __len__(self):
+            return 5
+
+        def __getitem__(self, i):
+            if i == 3:
+                raise OSError("unreadable frame")
+            return i
+    got = []
+    with pytest.raises(OSError, match="unreadable frame"):
+        for b in pipeline.TestLoader(Broken(), 2, collate=lambda s: s, workers=2):
+            got.append(b)
+    assert got == [[0, 1]]
