@@ -151,3 +151,51 @@ def test_pipeline_test_side_surface(tmp_path):
         for b in pipeline.TestLoader(Broken(), 2, collate=lambda s: s, workers=2):
             got.append(b)
     assert got == [[0, 1]]
+
+
+def test_dataset_mode_glue_on_cpu(monkeypatch, tmp_path):
+    """``run_test.run_dataset`` end to end with the GPU parts replaced by stand-ins (pipeline, collate, synchronize; oracle error
+    backend for ``--score``): reader -> threaded loader -> step per batch -> gathered CSV with the frames' ids -> scorer JSON ->
+    the one result line.  What is NOT covered here is what the stand-ins replace; tools/gpu_dataset_mode.py runs the real thing."""
+    import argparse
+    import json
+    from oryon_b200 import datasets, synth
+    from oryon_b200.utils.evaluator import format_sym_set
+    from test_evaluator_cpu import _OracleBackend
+    info = synth.write_nocs_tree(str(tmp_path), 0)
+    seen = []
+
+    class FakePipe:
+        def on_test_start(self, pred_path=None, seed=None):
+            self.seed = seed
+
+        def test_step(self, batch, batch_idx):
+            seen.append(list(batch["instance_id"]))
+            return _fake_rows(list(range(len(batch["instance_id"]))))
+
+        def on_test_end(self):
+            pass
+
+    monkeypatch.setattr(run_test, "build_pipeline", lambda *a, **k: (FakePipe(), argparse.Namespace(tokenizer=object())))
+    monkeypatch.setattr(datasets.GpuCollate, "__call__", lambda self, data: dict(instance_id=[s[5] for s in data]))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    orig_score = run_test.score_csv
+
+    def score(csv, ds, exp_tag="", compute_vsd=True):
+        models, _, symms = ds.get_object_info()
+        return orig_score(csv, ds, exp_tag, compute_vsd, pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
+    monkeypatch.setattr(run_test, "score_csv", score)
+    out = tmp_path / "pred.csv"
+    args = argparse.Namespace(dataset=info["name"], dataset_type=None, root=str(tmp_path), split=info["split"], obj="all", mask="oracle",
+                              add_description="yes", batch=4, precision=3, out=str(out), seed=1, workers=2, score=True, no_vsd=True)
+    r, w = os.pipe()
+    run_test.run_dataset(args, 1, 0, 0, torch.device("cpu"), w)
+    os.close(w)
+    line = json.loads(os.read(r, 1 << 16).decode())
+    os.close(r)
+    ids = ["_".join(str(e) for e in (sa, ia, sq, iq, obj)) for sa, ia, sq, iq, obj in info["pairs"]]
+    assert seen == [ids[:4], ids[4:]] and line["pairs"] == len(ids) and line["status"]["ok"] + line["status"]["no_corrs"] + line["status"]["invalid_mask"] == len(ids)
+    csv_lines = out.read_text().splitlines()
+    assert [l.split(",")[0] for l in csv_lines] == [f"{sa} {ia} {obj}" for sa, ia, _, _, obj in info["pairs"]]
+    metrics = json.load(open(tmp_path / "pred.json"))
+    assert metrics["instance_id"] == ids and sum(metrics["Missing segm"]) == 1
