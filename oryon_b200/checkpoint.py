@@ -16,6 +16,7 @@ tests/golden/ckpt_remap.json, recorded by executing the reference's own loop (or
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Mapping, Optional
 
 import torch
@@ -100,3 +101,42 @@ def assemble_state_dict(clip: Optional[Mapping[str, Tensor]] = None, swin: Optio
         if part:
             out.update(part)
     return out
+
+
+# the files the reference's constructors read, where its libraries put them
+CLIP_CACHE_FILE = os.path.join("~", ".cache", "clip", "ViT-L-14-336px.pt")                  # clip.load("ViT-L/14@336px"), models/vlm.py:19
+SWIN_HUB_FILE = os.path.join("~", ".cache", "torch", "hub", "checkpoints", "swin_b-68c6b09e.pth")   # swin_b(weights=Swin_B_Weights.DEFAULT), net.py:46
+CATSEG_FILE = os.path.join("pretrained_models", "catseg.pth")                               # net.py:104
+
+
+def reference_layout_files(args=None, root: str = ".", home: Optional[str] = None) -> Dict[str, Optional[str]]:
+    """Where ``Oryon(args, device)`` finds its weights in a reference installation: the OpenAI CLIP download in ``~/.cache/clip``,
+    torchvision's ``swin_b`` weights in the torch hub cache, ``pretrained_models/catseg.pth`` when ``args.model.use_catseg_ckpt``
+    (net.py:102-104) and the Lightning checkpoint ``args.eval.ckpt`` that ``trainer.test(..., ckpt_path=...)`` loads on top
+    (run_test.py:42).  ``None`` for a part the configuration does not ask for."""
+    def get(path, default=None):
+        cur = args
+        for key in path.split("."):
+            if cur is None:
+                return default
+            cur = cur.get(key) if isinstance(cur, Mapping) else getattr(cur, key, None)
+        return default if cur is None else cur
+
+    expand = (lambda p: p.replace("~", home, 1)) if home is not None else os.path.expanduser
+    ckpt = get("eval.ckpt")
+    return {"clip": expand(CLIP_CACHE_FILE), "swin": expand(SWIN_HUB_FILE),
+            "catseg": os.path.join(root, CATSEG_FILE) if get("model.use_catseg_ckpt", False) else None,
+            "lightning": (ckpt if os.path.isabs(str(ckpt)) else os.path.join(root, str(ckpt))) if ckpt else None}
+
+
+def reference_layout_state_dict(args=None, root: str = ".", home: Optional[str] = None) -> Dict[str, Tensor]:
+    """The state_dict the reference ends up with after ``Oryon.__init__`` and the checkpoint load, read from the files of
+    ``reference_layout_files``; a file the configuration asks for and that is missing raises ``FileNotFoundError`` naming it."""
+    files = reference_layout_files(args, root, home)
+    missing = [f"{k}: {v}" for k, v in files.items() if v is not None and not os.path.exists(v)]
+    if missing:
+        raise FileNotFoundError("pretrained weights not found (" + "; ".join(missing) + ")")
+    vlm = "clip"
+    return assemble_state_dict(clip_state_dict(files["clip"]), swin_state_dict(files["swin"]),
+                               torch.load(files["catseg"], map_location="cpu")["model"] if files["catseg"] else None,
+                               lightning_model_state_dict(files["lightning"]) if files["lightning"] else None, vlm)

@@ -44,6 +44,15 @@ class Oryon:
         self.training = False
         self._loaded = False
         self._prompt_cache: Dict[tuple, Tensor] = {}
+        self._load_error: Optional[str] = None
+        if state_dict is None and args is not None:
+            # the reference's constructor reads its pretrained files itself (net.py:27-34, :99-139); so does this one when they
+            # lie where the reference's libraries put them.  Missing files are reported by the first forward, not silently skipped.
+            from . import checkpoint
+            try:
+                state_dict = checkpoint.reference_layout_state_dict(args)
+            except FileNotFoundError as e:
+                self._load_error = str(e)
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -105,7 +114,7 @@ class Oryon:
     # ---- network ----------------------------------------------------------------------------------------
     def forward_tensors(self, rgb_a: Tensor, rgb_q: Tensor, prompt_emb: Tensor, return_debug: bool = False):
         if not self._loaded:
-            raise _lib.OryonError("Oryon: weights not loaded (load_state_dict)")
+            raise _lib.OryonError("Oryon: weights not loaded (load_state_dict)" + (f"; {self._load_error}" if self._load_error else ""))
         dev = self.device
         ra, rq = as_device(rgb_a, dev, torch.float32), as_device(rgb_q, dev, torch.float32)
         te = as_device(prompt_emb, dev, torch.float32)

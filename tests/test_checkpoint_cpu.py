@@ -73,3 +73,32 @@ def test_clip_archive_loader(tmp_path):
     plain = str(tmp_path / "plain.pt")
     torch.save({"visual.weight": torch.zeros(2, 2, dtype=torch.float16)}, plain)
     assert ck.clip_state_dict(plain)["vlm.clip_model.visual.weight"].dtype == torch.float32
+
+
+def test_reference_layout_discovery(tmp_path):
+    """``Oryon(args, device)`` without an explicit state_dict reads the files of a reference installation (net.py:27-34, :99-139,
+    run_test.py:42): paths, the use_catseg_ckpt / eval.ckpt switches, the load order, and a loud error naming what is missing."""
+    import pytest
+    home, root = tmp_path / "home", tmp_path / "repo"
+    args = dict(model=dict(use_catseg_ckpt=True, image_encoder=dict(vlm="clip")), eval=dict(ckpt="ckpts/last.ckpt"))
+    files = ck.reference_layout_files(args, str(root), str(home))
+    assert files == {"clip": str(home / ".cache/clip/ViT-L-14-336px.pt"), "swin": str(home / ".cache/torch/hub/checkpoints/swin_b-68c6b09e.pth"),
+                     "catseg": str(root / "pretrained_models/catseg.pth"), "lightning": str(root / "ckpts/last.ckpt")}
+    assert ck.reference_layout_files(dict(model=dict(use_catseg_ckpt=False)), str(root), str(home))["catseg"] is None
+    assert ck.reference_layout_files(None, str(root), str(home))["lightning"] is None
+    with pytest.raises(FileNotFoundError, match="ViT-L-14-336px.pt"):
+        ck.reference_layout_state_dict(args, str(root), str(home))
+    for f in files.values():
+        os.makedirs(os.path.dirname(f), exist_ok=True)
+    torch.save({"visual.conv1.weight": torch.ones(2, 2, dtype=torch.float16)}, files["clip"])
+    from torchvision.models import swin_b
+    torch.save(swin_b(weights=None).state_dict(), files["swin"])
+    torch.save({"model": {"sem_seg_head.predictor.clip_model.visual.conv1.weight": torch.full((2, 2), 2.0),
+                          "sem_seg_head.predictor.transformer.head.weight": torch.full((1,), 3.0)}}, files["catseg"])
+    with pytest.raises(FileNotFoundError, match="last.ckpt"):
+        ck.reference_layout_state_dict(args, str(root), str(home))
+    torch.save({"state_dict": {"model.decoder.head.weight": torch.full((1,), 4.0)}}, files["lightning"])
+    sd = ck.reference_layout_state_dict(args, str(root), str(home))
+    assert float(sd["vlm.clip_model.visual.conv1.weight"][0, 0]) == 2.0          # CATSeg's CLIP over the stock download
+    assert float(sd["decoder.head.weight"][0]) == 4.0                              # the Lightning checkpoint last
+    assert any(k.startswith("guidance_backbone.features.") for k in sd)
