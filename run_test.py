@@ -159,30 +159,86 @@ def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real
     if model.tokenizer is None:
         raise SystemExit("run_test.py: text prompts need the CLIP BPE vocabulary (--bpe)")
 
-    # this rank's batches, decoded on worker threads ahead of the GPU (the reference's DataLoader has 8 worker processes)
+    dataset_loop(ds, pipe, batch=args.batch, seed=args.seed, workers=args.workers, out=args.out, score=args.score, compute_vsd=not args.no_vsd,
+                 label=f"{args.dataset}/{args.split}/{args.obj}", exp_tag=f"{args.dataset} {args.split} {args.obj} ({args.mask})",
+                 precision=args.precision, world=world, rank=rank, dev=dev, real_stdout=real_stdout)
+
+
+def dataset_loop(ds, pipe, *, batch: int, seed: int, workers: int, out: Optional[str], score: bool, compute_vsd: bool, label: str, exp_tag: str,
+                 precision: int, world: int, rank: int, dev: torch.device, real_stdout: int) -> Dict:
+    """This rank's share of ``ds`` through ``pipe.test_step``, batches decoded on worker threads ahead of the GPU (the reference's
+    DataLoader has 8 worker processes), the gathered CSV written by rank 0, optionally scored there; one JSON line on rank 0."""
     from oryon_b200.pipeline import TestLoader
-    batches = iter(TestLoader(ds, args.batch, list(sharding.shard_pairs(len(ds), rank, world)), workers=args.workers))
+    batches = iter(TestLoader(ds, batch, list(sharding.shard_pairs(len(ds), rank, world)), workers=workers))
 
     def step(idx: Sequence[int]) -> List[dict]:
-        batch = next(batches)
-        if len(batch["instance_id"]) != len(idx):
+        b = next(batches)
+        if len(b["instance_id"]) != len(idx):
             raise RuntimeError("run_test.py: loader and loop disagree on the batch boundaries")
-        return pipe.test_step(batch, idx[0] // args.batch)
+        return pipe.test_step(b, idx[0] // batch)
 
-    pipe.on_test_start(seed=args.seed + rank)
-    res = run_sharded(len(ds), args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize,
-                      id_fn=lambda i: dataset_pair_ids(ds, i))
+    pipe.on_test_start(seed=seed + rank)
+    res = run_sharded(len(ds), batch, step, out_path=out, device=dev, sync=torch.cuda.synchronize, id_fn=lambda i: dataset_pair_ids(ds, i))
     pipe.on_test_end()
-    if rank == 0 and args.score:
-        score_csv(args.out, ds, exp_tag=f"{args.dataset} {args.split} {args.obj} ({args.mask})", compute_vsd=not args.no_vsd)
+    if rank == 0 and score and out is not None:
+        score_csv(out, ds, exp_tag=exp_tag, compute_vsd=compute_vsd)
     if rank == 0:
         line = json.dumps({"metric": "image-pairs/sec (whole test loop, decode included)", "value": len(ds) / res["seconds"], "unit": "pairs/s",
-                           "n_gpus": world, "pairs": len(ds), "batch": args.batch, "seconds": res["seconds"], "status": res["status"],
-                           "gemm_precision": args.precision, "data": f"{args.dataset}/{args.split}/{args.obj}", "csv": args.out})
+                           "n_gpus": world, "pairs": len(ds), "batch": batch, "seconds": res["seconds"], "status": res["status"],
+                           "gemm_precision": precision, "data": label, "csv": out})
         sys.stdout.flush()
         os.write(real_stdout, (line + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    return res
+
+
+def config_run_files(cfg, rank: int = 0, now=None, rand_seed: Optional[int] = None) -> tuple:
+    """Result files of a configuration-driven run, named as ``FPM_Pipeline.get_pred_filename`` names them (pipeline.py:474-488)
+    under ``tmp.results_out`` (default ``<exp_root>/<exp_name>/results``, utils/misc.py:385), plus the copy of the configuration
+    the reference's offline scorer looks for next to the CSV (compute_metrics.py:56-58).  Written by rank 0."""
+    import yaml
+    from oryon_b200.config import select
+    from oryon_b200.pipeline import pred_filenames
+    if select(cfg, "tmp.results_out") is None:
+        cfg.setdefault("tmp", type(cfg)())["results_out"] = os.path.join(str(select(cfg, "exp_root", "exp_data")), str(select(cfg, "exp_name", "baseline")), "results")
+    csv, metrics, cfg_copy = pred_filenames(cfg, now=now, rand_seed=rand_seed)
+    if rank == 0:
+        os.makedirs(os.path.dirname(csv), exist_ok=True)
+        with open(cfg_copy, "w") as f:
+            yaml.safe_dump(json.loads(json.dumps(cfg)), f)
+    return csv, metrics, cfg_copy
+
+
+def run_config(cfg, opts, world: int, rank: int, local: int, dev: torch.device, real_stdout: int) -> None:
+    """``python run_test.py -cp exp_data/baseline/ dataset.test.name=nocs test.mask=oracle`` (the reference's command line): the
+    whole run is described by the configuration file -- dataset, masks, solver, seeds, ``pretrained.*``, ``eval.ckpt`` -- and the
+    weights are read where a reference installation keeps them (``Oryon(args, device)``, oryon_b200/checkpoint.py)."""
+    from oryon_b200 import pipeline
+    from oryon_b200.config import select
+    from oryon_b200.net import Oryon
+    cfg["device"] = f"cuda:{local}"
+    ds = pipeline.get_dataset(cfg, eval=True)
+    if len(ds) == 0:
+        raise SystemExit("run_test.py: the pair split is empty for this object split")
+    tokenizer = None
+    vocab = select(cfg, "pretrained.vocabulary")
+    if vocab and os.path.exists(vocab):
+        from oryon_b200.models.tokenizer import SimpleTokenizer
+        tokenizer = SimpleTokenizer(vocab)
+    model = Oryon(cfg, cfg["device"], precision=opts.precision, tokenizer=tokenizer)
+    if model.tokenizer is None:
+        raise SystemExit(f"run_test.py: CLIP BPE vocabulary not found (pretrained.vocabulary = {vocab})")
+    pipe = pipeline.FPM_Pipeline(cfg, test_model=True, model=model)
+    out = opts.out
+    if out is None:
+        # every rank derives the same names: the stamp comes from rank 0's clock only through the CSV it alone writes
+        out = config_run_files(cfg, rank)[0]
+    seed = int(select(cfg, "seed", 1)) if select(cfg, "use_seed", False) else 1
+    name, split, obj = select(cfg, "dataset.test.name"), select(cfg, "dataset.test.split"), select(cfg, "dataset.test.obj")
+    dataset_loop(ds, pipe, batch=int(select(cfg, "dataset.batch_size", 32)), seed=seed, workers=opts.workers, out=out, score=not opts.no_score,
+                 compute_vsd=bool(select(cfg, "compute_vsd", True)) and not opts.no_vsd, label=f"{name}/{split}/{obj}",
+                 exp_tag=str(select(cfg, "exp_tag", "")), precision=opts.precision, world=world, rank=rank, dev=dev, real_stdout=real_stdout)
 
 
 def main(argv=None):
@@ -210,6 +266,10 @@ def main(argv=None):
     ap.add_argument("--swin", default=None, help="torchvision swin_b weights")
     ap.add_argument("--catseg", default=None, help="CATSeg checkpoint (pretrained_models/catseg.pth)")
     ap.add_argument("--ckpt", default=None, help="the reference's Lightning checkpoint (args.eval.ckpt)")
+    ap.add_argument("-cp", "--config-path", default=None, help="the reference's way: folder (or file) of the hydra configuration, e.g. exp_data/baseline/")
+    ap.add_argument("-cn", "--config-name", default="config")
+    ap.add_argument("overrides", nargs="*", help="with -cp: dotted overrides, e.g. dataset.test.name=nocs test.mask=oracle")
+    ap.add_argument("--no-score", action="store_true", help="with -cp: do not score the CSV at the end")
     ap.add_argument("--workers", type=int, default=8, help="dataset mode: decoding threads of the loader (pipeline.py:545 num_workers=8); 0 = in line")
     ap.add_argument("--score", action="store_true", help="dataset mode: rank 0 scores the gathered CSV at the end (metrics JSON next to --out, LaTeX row)")
     ap.add_argument("--no-vsd", action="store_true", help="with --score: skip VSD / AR")
@@ -227,6 +287,11 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=dev)
 
     from oryon_b200 import synth
+    if args.config_path is not None:
+        from oryon_b200.config import load_config
+        return run_config(load_config(args.config_path, args.config_name, args.overrides), args, world, rank, local, dev, real_stdout)
+    if args.overrides:
+        raise SystemExit(f"run_test.py: overrides {args.overrides} need a configuration (-cp)")
     if args.dataset is not None:
         return run_dataset(args, world, rank, local, dev, real_stdout)
     pipe, model = build_pipeline(local, args.precision)
