@@ -425,7 +425,7 @@ NOCS_TREE_OBJECTS = {"mug_synth_a": (6, ["mug", "white", "red"]), "bowl_synth_b"
 
 
 def write_nocs_tree(root: str, seed: int = 0, name: str = "nocs", split: str = "cross_scene_test", hw: Tuple[int, int] = (48, 64),
-                    n_scenes: int = 2, n_imgs: int = 3) -> Dict:
+                    n_scenes: int = 2, n_imgs: int = 3, mask_scale: int = 1) -> Dict:
     """Writes ``<root>/<name>/...`` with ``n_scenes x n_imgs`` frames (colour / label mask / 16-bit depth PNGs, meta and
     detection text files, per-frame pose pickles), three object models (one with a continuous, one with a discrete
     symmetry), the prompt templates, the object split and a fixed pair split (instance list, annotations, tracked list).
@@ -479,8 +479,8 @@ def write_nocs_tree(root: str, seed: int = 0, name: str = "nocs", split: str = "
             meta, det, poses = [], [], []
             for k, obj in enumerate(present):
                 mask_id = k + 1
-                y0, x0 = 4 + 12 * k, 5 + 14 * k
-                hh, ww = (10, 12) if not (s == 2 and im == 2 and k == 0) else (1, 1)   # one single-pixel object
+                y0, x0 = (4 + 12 * k) * mask_scale, (5 + 14 * k) * mask_scale
+                hh, ww = (10 * mask_scale, 12 * mask_scale) if not (s == 2 and im == 2 and k == 0) else (1, 1)   # one single-pixel object
                 mask[y0:y0 + hh, x0:x0 + ww] = mask_id
                 meta.append(f"{mask_id} {NOCS_TREE_OBJECTS[obj][0]} {obj}\n")
                 det.append(f"{mask_id} {x0} {y0} {ww - 1} {hh - 1}\n")

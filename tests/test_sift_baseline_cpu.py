@@ -117,3 +117,32 @@ def test_baseline_registers_failures_for_empty_masks(tree, tmp_path):
                                pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
     assert len(out.read_text().splitlines()) == len(ds) - 1 and sum(ev.counts["Missing segm"]) == 1
     assert len(ev.metrics["instance_id"]) == len(ds)
+
+
+def test_baseline_loop_nocs_variant(tmp_path):
+    """The NOCS form of the loop (sift_nocs.py): pairs keyed by object NAME, no source subsample, OBJ models; the frame with a
+    single-pixel object has no key point inside its mask -> failure rows for the pairs that use it."""
+    from PIL import Image
+    from oryon_b200.datasets import NOCSDataset
+    from test_evaluator_cpu import _OracleBackend
+    d = str(tmp_path)
+    info = synth.write_nocs_tree(d, 0, hw=HW, mask_scale=5)
+    frames = synth.textured_frames(77, HW, 6)
+    for n, (s, im, _) in enumerate(info["frames"]):
+        g = frames[n].astype(np.float32)
+        rgb = np.stack([g, np.clip(g * 0.9 + 10, 0, 255), np.clip(g * 1.05, 0, 255)], -1).astype(np.uint8)
+        Image.fromarray(rgb).save(os.path.join(info["base"], f"split/real_test/scene_{s}/{im:04d}_color.png"))
+    args = dict(device="cuda:0", dataset=dict(root=d, max_corrs=500, img_size=[224, 224], test=dict(name=info["name"], split=info["split"], obj="all")),
+                test=dict(mask="oracle", add_description="yes"))
+    ds = NOCSDataset(args, eval=True)
+    models, _, symms = ds.get_object_info()
+    out = tmp_path / "sift_nocs_oracle.txt"
+    torch.manual_seed(5)
+    ev = baseline.run_baseline(ds, OraclePath(), "nocs", "oracle", None, False, str(out),
+                               pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
+    lines = out.read_text().splitlines()
+    single_pixel = [i for i, (sa, ia, sq, iq, obj) in enumerate(info["pairs"]) if (sq, iq) == (2, 2) and obj == list(synth.NOCS_TREE_OBJECTS)[0]]
+    assert len(ev.metrics["instance_id"]) == len(ds) and len(lines) == len(ds) - len(single_pixel) and len(single_pixel) >= 1
+    assert sum(ev.counts["Missing segm"]) == len(single_pixel)
+    assert ev.metrics["cls_id"] == [p[-1] for p in info["pairs"]]                  # object names
+    assert all(l.split(",")[0].split(" ")[2] in synth.NOCS_TREE_OBJECTS for l in lines)
