@@ -110,7 +110,8 @@ def get_obj_rendering(root: str, obj_id: str) -> dict:
         normals = [[float(t) for t in line.split(" ")[:3]] for line in f.readlines()]
     with open(base + ".obj") as f:
         faces = [[int(tok.split("/")[0]) for tok in line.split(" ")[1:4]] for line in f.readlines() if line.startswith("f")]
-    return {"pts": np.asarray(pts) * 1000, "normals": np.asarray(normals), "faces": np.asarray(faces)}
+    # "faces_base": not in the reference's dict -- tells the rasteriser's caller that these indices count from 1 (OBJ convention)
+    return {"pts": np.asarray(pts) * 1000, "normals": np.asarray(normals), "faces": np.asarray(faces), "faces_base": 1}
 
 
 def _rotation_matrix(angle: float, direction) -> np.ndarray:

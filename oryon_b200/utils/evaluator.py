@@ -57,12 +57,18 @@ def dict_from_preds(perf_file: str):
 
 
 def zero_based_faces(obj_models: dict) -> dict:
-    """Face indices as the rasteriser needs them: OBJ files (NOCS) count from 1, PLY files (TOYL) from 0."""
+    """Face indices as the rasteriser needs them: OBJ files (NOCS) count from 1, PLY files (TOYL) from 0.  The NOCS reader marks its
+    models with ``faces_base``; unmarked models are shifted only when their indices cannot be 0-based (minimum >= 1 and the maximum
+    equal to the vertex count)."""
     out = {}
     for k, m in obj_models.items():
         m = dict(m)
-        if "faces" in m and len(m["faces"]) and int(np.min(m["faces"])) >= 1 and int(np.max(m["faces"])) == len(m["pts"]):
-            m["faces"] = np.asarray(m["faces"]) - 1
+        if "faces" in m and len(m["faces"]):
+            base = m.pop("faces_base", None)
+            if base is None:
+                base = 1 if (int(np.min(m["faces"])) >= 1 and int(np.max(m["faces"])) == len(m["pts"])) else 0
+            if base:
+                m["faces"] = np.asarray(m["faces"]) - int(base)
         out[k] = m
     return out
 
