@@ -155,7 +155,9 @@ class Evaluator(object):
 
     # ---- object info ------------------------------------------------------------------------------------
     def add_object_info(self, obj_models: dict, obj_diams: dict, obj_symms: dict):
-        """Models / diameters in mm, BOP symmetry lists (utils/evaluator.py:111-119)."""
+        """Models / diameters in mm, BOP symmetry lists (utils/evaluator.py:111-119).  Meshes marked (or recognisable) as 1-based OBJ
+        indices are shifted for the rasteriser (``zero_based_faces``); the reference hands them to OpenGL as they are."""
+        obj_models = zero_based_faces(obj_models)
         self.obj_models, self.obj_diams = obj_models, obj_diams
         self.obj_symms = {k: format_sym_set(s) for k, s in obj_symms.items()}
         self.add_diams = {k: get_diameter(m["pts"]) / 1000. for k, m in obj_models.items()}
