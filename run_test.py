@@ -270,6 +270,9 @@ def main(argv=None):
     ap.add_argument("-cn", "--config-name", default="config")
     ap.add_argument("overrides", nargs="*", help="with -cp: dotted overrides, e.g. dataset.test.name=nocs test.mask=oracle")
     ap.add_argument("--no-score", action="store_true", help="with -cp: do not score the CSV at the end")
+    ap.add_argument("--torch-threads", type=int, default=2, help="intra-op threads of the host-side torch ops (the per-pair multinomial draws on <= 36 864 "
+                                                                  "weights): with the decoding threads busy, a full OpenMP team per tiny op costs milliseconds; "
+                                                                  "ignored when OMP_NUM_THREADS is set (torchrun sets it to 1)")
     ap.add_argument("--workers", type=int, default=8, help="dataset mode: decoding threads of the loader (pipeline.py:545 num_workers=8); 0 = in line")
     ap.add_argument("--score", action="store_true", help="dataset mode: rank 0 scores the gathered CSV at the end (metrics JSON next to --out, LaTeX row)")
     ap.add_argument("--no-vsd", action="store_true", help="with --score: skip VSD / AR")
@@ -281,6 +284,8 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("run_test.py: no CUDA device; the product path has no CPU fallback")
+    if "OMP_NUM_THREADS" not in os.environ:
+        torch.set_num_threads(max(1, args.torch_threads))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
