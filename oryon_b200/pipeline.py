@@ -108,7 +108,9 @@ class TestLoader:
     The host part of a sample -- PNG decoding, ~10-20 ms per 480 x 640 frame, what the reference gives its 8 worker processes --
     runs on ``workers`` threads (the decoders release the GIL), ``prefetch`` batches ahead of the consumer, so that the GPU step
     of batch k overlaps the decoding of batches k+1.. .  ``indices`` restricts the loader to a rank's share of the pairs
-    (``sharding.shard_pairs``); ``workers=0`` reads in the calling thread."""
+    (``sharding.shard_pairs``); ``workers=0`` reads in the calling thread.  With the worker threads busy, keep torch's intra-op thread
+    count small (``torch.set_num_threads(1..2)``, as ``run_test.py`` does): the loop's own CPU ops are tiny and a full OpenMP team
+    per op costs more than the op."""
     __test__ = False            # not a pytest class
 
     def __init__(self, dataset, batch_size: int, indices: Optional[List[int]] = None, collate=None, workers: int = 8, prefetch: int = 2):
