@@ -111,10 +111,16 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         if _cdll is not None:
             return _cdll
         path = library_path()
-        if not os.path.exists(path):
+        if not os.path.exists(path) or not _build.is_current():
+            # a library built from other sources than the ones in the tree (edited csrc/, stale .so) would silently run old
+            # kernels: rebuild it (under the build's file lock, so concurrent ranks are safe) or refuse
+            what = "is missing" if not os.path.exists(path) else "is stale (csrc/ or the header changed since it was built)"
             if not build_if_missing:
-                raise OryonError(f"{path} is missing: run `python -m oryon_b200.build` (no fallback path exists)")
-            _build.build()
+                raise OryonError(f"{path} {what}: run `python -m oryon_b200.build` (no fallback path exists)")
+            try:
+                _build.build()
+            except RuntimeError as e:
+                raise OryonError(f"{path} {what} and cannot be rebuilt: {e}") from e
         lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported

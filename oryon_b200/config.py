@@ -62,10 +62,49 @@ def _resolve(cfg: Config, node: Any, depth: int = 0) -> Any:
     return node
 
 
-def apply_overrides(cfg: Config, overrides: Iterable[str]) -> Config:
-    """``key.sub=value`` items as hydra takes them on the command line; values are parsed as YAML scalars (``32``, ``true``,
-    ``null``, ``[192,192]``, plain strings); a leading ``+`` (hydra's "add a new key") is accepted."""
+_OVERRIDE_LOADER = None
+
+
+def _override_loader():
+    """A YAML loader whose plain scalars resolve the way hydra's override grammar does: ``true`` / ``false`` (any case) are
+    booleans, ``null`` is None, ``[+-]?(0|[1-9][0-9_]*)`` an int, decimal / exponent forms (and ``inf`` / ``nan``) a float -- and
+    everything else stays a STRING.  PyYAML's own resolvers follow YAML 1.1, where ``yes`` / ``no`` / ``on`` / ``off`` are
+    booleans, ``007`` is the integer 7 and ``1:30`` a sexagesimal number; hydra keeps all of those as the strings the reference
+    compares against (``test.add_description`` in 'yes' / 'no' / 'wrong' / 'desconly', datasets.py)."""
+    global _OVERRIDE_LOADER
+    if _OVERRIDE_LOADER is None:
+        import yaml
+
+        class Loader(yaml.SafeLoader):
+            pass
+
+        Loader.yaml_implicit_resolvers = {}
+        Loader.add_implicit_resolver("tag:yaml.org,2002:bool", re.compile(r"^(?:true|false)$", re.I), list("tTfF"))
+        Loader.add_implicit_resolver("tag:yaml.org,2002:null", re.compile(r"^(?:null)$", re.I), list("nN"))
+        Loader.add_implicit_resolver("tag:yaml.org,2002:int", re.compile(r"^[-+]?(?:0|[1-9][0-9_]*)$"), list("-+0123456789"))
+        Loader.add_implicit_resolver(
+            "tag:yaml.org,2002:float",
+            re.compile(r"^[-+]?(?:(?:[0-9][0-9_]*)?\.[0-9_]+(?:[eE][-+]?[0-9]+)?|[0-9][0-9_]*\.?(?:[eE][-+]?[0-9]+)|[0-9][0-9_]*\.|inf|nan)$", re.I),
+            list("-+0123456789.iInN"))
+        _OVERRIDE_LOADER = Loader
+    return _OVERRIDE_LOADER
+
+
+def parse_override_value(raw: str) -> Any:
+    """The value of a ``key=value`` override with hydra's typing (see ``_override_loader``); lists / dicts in flow syntax and
+    quoted strings work as on hydra's command line."""
     import yaml
+    if raw == "":
+        return None
+    value = yaml.load(raw, Loader=_override_loader())
+    if isinstance(value, float) and re.fullmatch(r"[-+]?nan", raw.strip(), re.I):
+        return float("nan")
+    return value
+
+
+def apply_overrides(cfg: Config, overrides: Iterable[str]) -> Config:
+    """``key.sub=value`` items as hydra takes them on the command line (``32``, ``true``, ``null``, ``[192,192]``; ``yes``, ``no``,
+    ``007`` stay strings, see ``parse_override_value``); a leading ``+`` (hydra's "add a new key") is accepted."""
     for item in overrides:
         if "=" not in item:
             raise ValueError(f"config override {item!r} is not of the form key=value")
@@ -76,7 +115,7 @@ def apply_overrides(cfg: Config, overrides: Iterable[str]) -> Config:
             if not isinstance(cur.get(k), Mapping):
                 cur[k] = Config()
             cur = cur[k]
-        cur[keys[-1]] = _wrap(yaml.safe_load(raw)) if raw != "" else None
+        cur[keys[-1]] = _wrap(parse_override_value(raw))
     return cfg
 
 

@@ -20,7 +20,7 @@ any attribute-style mapping with the keys of configs/config.yaml that the infere
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -34,13 +34,26 @@ from .utils.pcd import corrs_to_pcd, mask_to_roi, match_nn, nn_correspondences, 
 from .utils.pointdsc.init import get_pointdsc_pose, get_pointdsc_solver, pointdsc_poses
 
 
-def _get(obj, path: str, default=None):
+_ABSENT = object()
+
+
+def _get(obj, path: str, default=None, *, keep_none: bool = False):
+    """``obj.a.b.c`` of a dict / attribute-style configuration.  A missing key gives ``default``; a key that is present with the
+    value ``None`` (``src_sampling: null``) gives ``default`` too unless ``keep_none`` -- the reference distinguishes the two where
+    ``None`` is a setting of its own (``if subsample_source is not None``, utils/pcd.py:187)."""
     cur = obj
     for key in path.split("."):
-        if cur is None:
+        if cur is None or cur is _ABSENT:
             return default
-        cur = cur.get(key) if isinstance(cur, dict) else getattr(cur, key, None)
-    return default if cur is None else cur
+        if isinstance(cur, dict):
+            cur = cur.get(key, _ABSENT)
+        else:
+            cur = getattr(cur, key, _ABSENT)
+    if cur is _ABSENT:
+        return default
+    if cur is None:
+        return None if keep_none else default
+    return cur
 
 
 def mask_postproc(logits: Optional[Tensor], gt: Optional[Tensor], size: Tuple[int, int], mask_th: float = 0.5) -> Dict[str, Tensor]:
@@ -167,7 +180,8 @@ class FPM_Pipeline:
         self.mask_th = float(_get(args, "test.mask_threshold", 0.5))
         self.dist_th = float(_get(args, "test.dist_th", 0.25))
         self.n_corrs = int(_get(args, "test.n_corrs", _get(args, "dataset.max_corrs", 500)))
-        self.src_sampling = _get(args, "test.src_sampling", 5000)
+        self.src_sampling = _get(args, "test.src_sampling", 5000, keep_none=True)   # an explicit null = no source subsample
+        self.per_pair_seed = bool(_get(args, "test.per_pair_seed", False))          # draws seeded per pair
         self.featmap_size = tuple(_get(args, "model.image_encoder.img_size", (192, 192)))
         self.pred_file = None
         self.rows: List[dict] = []
@@ -203,12 +217,14 @@ class FPM_Pipeline:
         return TestLoader(valid_set, int(_get(self.args, "dataset.batch_size", 32)), indices)
 
     def on_test_start(self, pred_path: Optional[str] = None, seed: Optional[int] = None):
-        """Opens the prediction CSV and seeds numpy / torch as ``set_deterministic_seed`` (utils/misc.py:186-196,
-        pipeline.py:296-299: ``args.seed`` if ``use_seed`` else 1)."""
+        """Opens the prediction CSV and seeds numpy / torch as ``set_deterministic_seed`` (utils/misc.py:186-196) with
+        ``args.seed`` whenever it is not None, else 1 (pipeline.py:296-299; ``use_seed`` only gates the dataset constructor)."""
         if pred_path is not None:
             self.pred_file = open(pred_path, "w")
         if seed is None:
-            seed = int(_get(self.args, "seed", 1)) if _get(self.args, "use_seed", False) else 1
+            cfg_seed = _get(self.args, "seed", None)
+            seed = int(cfg_seed) if cfg_seed is not None else 1
+        self._seed = int(seed)
         np.random.seed(seed)
         torch.manual_seed(seed)
         torch.cuda.manual_seed(seed)
@@ -283,7 +299,8 @@ class FPM_Pipeline:
             self.pred_file.write(line)
         return line
 
-    def select_correspondences(self, results: dict, net_output: dict, valid: List[bool]) -> List[Optional[Tensor]]:
+    def select_correspondences(self, results: dict, net_output: dict, valid: List[bool],
+                               pair_index: Optional[Sequence[int]] = None) -> List[Optional[Tensor]]:
         """Batched ``nn_correspondences`` for every valid pair: one ROI compaction and one matching launch over ALL
         ROI pixels, then per pair, in order, the reference's two draws (utils/pcd.py:187-190, :211) and selections."""
         ma, mq, na, nq = self._masks_and_counts(results)
@@ -301,6 +318,7 @@ class FPM_Pipeline:
         for b in range(B):
             if not valid[b]:
                 continue
+            self._seed_pair(pair_index, b)
             n1 = n_a[b]
             pix1, pix2 = roi_a[b, :n1], roi_q[b, :n_q[b]]
             ib, db = idx[b, :n1], dist[b, :n1]
@@ -339,7 +357,14 @@ class FPM_Pipeline:
         sz = sz.cpu() if isinstance(sz, Tensor) else torch.as_tensor(sz)
         return bool((sz[:, 0] == depth.shape[1]).all()) and bool((sz[:, 1] == depth.shape[2]).all())
 
-    def draw_rows(self, dist: Tensor, n_a: List[int], valid: List[bool]) -> Tensor:
+    def _seed_pair(self, pair_index: Optional[Sequence[int]], b: int) -> None:
+        """``test.per_pair_seed``: the generators are re-seeded from (run seed, global pair index) before a pair's draws, so a
+        pair's correspondences -- hence its CSV line -- do not depend on how the pair list was sharded.  Off by
+        default: one rank then reproduces the reference's single sequential draw stream."""
+        if self.per_pair_seed and pair_index is not None:
+            torch.manual_seed((getattr(self, "_seed", 1) * 1000003 + int(pair_index[b])) & 0x7FFFFFFFFFFFFFFF)
+
+    def draw_rows(self, dist: Tensor, n_a: List[int], valid: List[bool], pair_index: Optional[Sequence[int]] = None) -> Tensor:
         """The two draws of ``nn_correspondences`` (utils/pcd.py:187-190, :211) for every valid pair, in the
         reference's order, on the CPU generator, from the HOST copy of the nearest-neighbour distances.  Returns
         ``int32 [B,n_corrs]`` positions in each pair's anchor ROI list (first entry -1: no correspondences)."""
@@ -348,6 +373,7 @@ class FPM_Pipeline:
         for b in range(B):
             if not valid[b]:
                 continue
+            self._seed_pair(pair_index, b)
             n1 = n_a[b]
             sel = None
             if self.src_sampling is not None and n1 > self.src_sampling:
@@ -383,7 +409,7 @@ class FPM_Pipeline:
             self._host_rows = torch.empty(B, self.n_corrs, dtype=torch.int32).pin_memory()
         self._host_dist.copy_(dist, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()                  # sync 1: distances for the draws
-        self._host_rows.copy_(self.draw_rows(self._host_dist, n_a, valid))
+        self._host_rows.copy_(self.draw_rows(self._host_dist, n_a, valid, batch.get("pair_index")))
         corrs, pa, pq, nv = select_lift_batched(self._host_rows, roi_a, roi_q, idx, depth_a, depth_q, batch["anchor"]["camera"],
                                                 batch["query"]["camera"], self.featmap_size)
         counts = nv.tolist()                                                    # sync 2: points that survived the bounds test
@@ -414,7 +440,7 @@ class FPM_Pipeline:
         if tail is not None:
             corrs, poses = tail
         else:
-            corrs = self.select_correspondences(results, outputs, valid)
+            corrs = self.select_correspondences(results, outputs, valid, batch.get("pair_index"))
             # lifting per pair, registration for all pairs with correspondences at once
             todo, pa, pq = [], [], []
             for b in range(B):

@@ -117,7 +117,8 @@ def build_pipeline(local_rank: int, precision: int, opts=None, evaluator=None):
     mask = opts.mask if opts is not None else "oracle"
     args = dict(device=dev, corrs_device="cpu", dataset=dict(img_size=[224, 224], max_corrs=500),
                 model=dict(image_encoder=dict(img_size=[192, 192])),
-                test=dict(mask=mask, src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
+                test=dict(mask=mask, src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5,
+                          per_pair_seed=bool(opts is not None and getattr(opts, "per_pair_seed", False))))
     return FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver, evaluator=evaluator), model
 
 
@@ -134,16 +135,26 @@ def dataset_pair_ids(ds, pair_index: int) -> tuple:
     return ds.frame_ids(pair_index)
 
 
-def score_csv(csv_path: str, ds, exp_tag: str = "", compute_vsd: bool = True, pose_errors=None):
-    """What the reference's ``on_test_end`` leaves behind (pipeline.py:357-370: summary, metrics JSON, LaTeX row), computed on
-    rank 0 from the gathered prediction CSV by the offline scorer (scripts/evaluation/compute_metrics.py) -- every pair
-    exactly once, whatever the number of ranks.  The JSON goes next to the CSV, summary and LaTeX row to stdout (= stderr
-    while the loop owns the result line)."""
+def pair_instance_id(ds, pair_index: int) -> str:
+    """The pair id the dataset gives pair ``pair_index`` (datasets.py:448: ``<scene_a>_<img_a>_<scene_q>_<img_q>_<obj>``)."""
+    inst = ds.instances[pair_index]
+    return f"{inst[1]}_{inst[2]}_{inst[3]}_{inst[4]}_{inst[-1]}"
+
+
+def score_csv(csv_path: str, ds, exp_tag: str = "", compute_vsd: bool = True, pose_errors=None, failed=None):
+    """Summary, metrics JSON and LaTeX row (pipeline.py:357-370) computed on rank 0 from the gathered prediction CSV by the
+    offline scorer (scripts/evaluation/compute_metrics.py) -- every pair exactly once, whatever the number of ranks.  With
+    ``failed`` = the ids of the pairs whose in-loop status was not 'ok', those are registered through ``register_test_failure``
+    as the reference's test loop does (pipeline.py:335-342: every metric of the pair zero, 'Missing segm' 1), so the outputs are
+    what the reference's ``on_test_end`` leaves behind; with ``failed=None`` they follow the OFFLINE scorer's semantics (validity
+    from the dataset's oracle mask only, identity pose scored for in-loop failures), which differ whenever a pair fails with
+    predicted masks.  The JSON goes next to the CSV, summary and LaTeX row to stdout (= stderr while the loop owns the result
+    line)."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("oryon_compute_metrics", os.path.join(ROOT, "scripts", "evaluation", "compute_metrics.py"))
     scorer = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(scorer)
-    return scorer.compute_metrics(csv_path, ds, exp_tag, compute_vsd, True, None, pose_errors=pose_errors)
+    return scorer.compute_metrics(csv_path, ds, exp_tag, compute_vsd, True, None, pose_errors=pose_errors, failed=failed)
 
 
 def run_dataset(args, world: int, rank: int, local: int, dev: torch.device, real_stdout: int) -> None:
@@ -175,13 +186,15 @@ def dataset_loop(ds, pipe, *, batch: int, seed: int, workers: int, out: Optional
         b = next(batches)
         if len(b["instance_id"]) != len(idx):
             raise RuntimeError("run_test.py: loader and loop disagree on the batch boundaries")
+        b["pair_index"] = list(idx)
         return pipe.test_step(b, idx[0] // batch)
 
-    pipe.on_test_start(seed=seed + rank)
+    pipe.on_test_start(seed=seed)
     res = run_sharded(len(ds), batch, step, out_path=out, device=dev, sync=torch.cuda.synchronize, id_fn=lambda i: dataset_pair_ids(ds, i))
     pipe.on_test_end()
     if rank == 0 and score and out is not None:
-        score_csv(out, ds, exp_tag=exp_tag, compute_vsd=compute_vsd)
+        failed = {pair_instance_id(ds, r["pair_index"]) for r in res["records"] if r["status"] != "ok"}
+        score_csv(out, ds, exp_tag=exp_tag, compute_vsd=compute_vsd, failed=failed)
     if rank == 0:
         line = json.dumps({"metric": "image-pairs/sec (whole test loop, decode included)", "value": len(ds) / res["seconds"], "unit": "pairs/s",
                            "n_gpus": world, "pairs": len(ds), "batch": batch, "seconds": res["seconds"], "status": res["status"],
@@ -234,7 +247,7 @@ def run_config(cfg, opts, world: int, rank: int, local: int, dev: torch.device, 
     if out is None:
         # every rank derives the same names: the stamp comes from rank 0's clock only through the CSV it alone writes
         out = config_run_files(cfg, rank)[0]
-    seed = int(select(cfg, "seed", 1)) if select(cfg, "use_seed", False) else 1
+    seed = int(select(cfg, "seed")) if select(cfg, "seed") is not None else 1      # pipeline.py:296-299: args.seed whenever it is set
     name, split, obj = select(cfg, "dataset.test.name"), select(cfg, "dataset.test.split"), select(cfg, "dataset.test.obj")
     dataset_loop(ds, pipe, batch=int(select(cfg, "dataset.batch_size", 32)), seed=seed, workers=opts.workers, out=out, score=not opts.no_score,
                  compute_vsd=bool(select(cfg, "compute_vsd", True)) and not opts.no_vsd, label=f"{name}/{split}/{obj}",
@@ -276,6 +289,9 @@ def main(argv=None):
     ap.add_argument("--workers", type=int, default=8, help="dataset mode: decoding threads of the loader (pipeline.py:545 num_workers=8); 0 = in line")
     ap.add_argument("--score", action="store_true", help="dataset mode: rank 0 scores the gathered CSV at the end (metrics JSON next to --out, LaTeX row)")
     ap.add_argument("--no-vsd", action="store_true", help="with --score: skip VSD / AR")
+    ap.add_argument("--per-pair-seed", action="store_true", help="re-seed the draw generators from (seed, global pair index) before every pair: "
+                                                                 "the prediction rows then do not depend on the number of ranks (SURVEY.md 8e); "
+                                                                 "default: the reference's single sequential draw stream per rank")
     ap.add_argument("--pointdsc", default=None, help="PointDSC snapshot directory (args.pretrained.pointdsc)")
     args = ap.parse_args(argv)
 
@@ -299,7 +315,7 @@ def main(argv=None):
         raise SystemExit(f"run_test.py: overrides {args.overrides} need a configuration (-cp)")
     if args.dataset is not None:
         return run_dataset(args, world, rank, local, dev, real_stdout)
-    pipe, model = build_pipeline(local, args.precision)
+    pipe, model = build_pipeline(local, args.precision, args)
     batches = []
     for k in range(args.distinct_batches):
         b = synth.synthetic_batch(100 + k, args.batch)
@@ -319,11 +335,12 @@ def main(argv=None):
 
     def step(idx: Sequence[int]) -> List[dict]:
         b = take(batches[(idx[0] // args.batch) % len(batches)], len(idx))
+        b["pair_index"] = list(idx)
         return pipe.test_step(b, idx[0] // args.batch)
 
-    pipe.on_test_start(seed=args.seed + rank)       # per-rank draw sequences; one rank = the reference's order
+    pipe.on_test_start(seed=args.seed)              # one rank = the reference's draw order; --per-pair-seed: sharding-independent rows
     step(list(range(min(args.batch, args.pairs))))  # warm-up: workspaces, arena, clocks
-    pipe.on_test_start(seed=args.seed + rank)
+    pipe.on_test_start(seed=args.seed)
     res = run_sharded(args.pairs, args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize)
     pipe.on_test_end()
     if rank == 0:

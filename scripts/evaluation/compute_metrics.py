@@ -55,7 +55,12 @@ def pair_results(dataset, preds: dict, ious_a: dict, ious_q: dict, iou_present: 
 
 
 def compute_metrics(results_file: str, dataset, exp_tag: str = "", compute_vsd: bool = True, print_summary: bool = False,
-                    out_file: Optional[str] = None, pose_errors: Optional[Callable] = None) -> Evaluator:
+                    out_file: Optional[str] = None, pose_errors: Optional[Callable] = None, failed: Optional[set] = None) -> Evaluator:
+    """``failed``: pair ids (``<scene_a>_<img_a>_<scene_q>_<img_q>_<obj>``) whose IN-LOOP status was not 'ok' (no correspondences,
+    empty predicted mask).  The reference's offline scorer cannot know them -- it judges validity from the dataset alone and scores
+    the identity pose such pairs carry in the CSV -- but its test loop registers them with ``register_test_failure``
+    (pipeline.py:335-342), which zeroes every metric of the pair.  Passing the set reproduces the evaluator state the reference's
+    ``on_test_end`` saves; leaving it ``None`` reproduces scripts/evaluation/compute_metrics.py."""
     metric_file = os.path.splitext(results_file)[0] + ".json"
     preds, ious_a, ious_q, iou_present = dict_from_preds(results_file)
     if not iou_present:
@@ -65,7 +70,7 @@ def compute_metrics(results_file: str, dataset, exp_tag: str = "", compute_vsd: 
     models, diams, symms = dataset.get_object_info()
     evaluator.add_object_info(zero_based_faces(models), diams, symms)
     for valid, res in pair_results(dataset, preds, ious_a, ious_q, iou_present):
-        if valid:
+        if valid and not (failed and res["instance_id"][0] in failed):
             evaluator.register_test(res)
         else:
             evaluator.register_test_failure(res)

@@ -114,7 +114,7 @@ def test_config_driven_run_on_cpu(monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     orig_score = run_test.score_csv
 
-    def score(csv, ds, exp_tag="", compute_vsd=True):
+    def score(csv, ds, exp_tag="", compute_vsd=True, failed=None):
         made["score"] = (exp_tag, compute_vsd)
         models, _, symms = ds.get_object_info()
         return orig_score(csv, ds, exp_tag, compute_vsd, pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
@@ -126,7 +126,7 @@ def test_config_driven_run_on_cpu(monkeypatch, tmp_path):
     os.close(w)
     line = json.loads(os.read(r, 1 << 16).decode())
     os.close(r)
-    assert made["model"] == (True, "cuda:0", 3) and made["pipe"] == ("oracle", 500, True, True) and made["seed"] == 1      # use_seed False -> 1
+    assert made["model"] == (True, "cuda:0", 3) and made["pipe"] == ("oracle", 500, True, True) and made["seed"] == 7      # args.seed whenever it is set (pipeline.py:296-299); use_seed only gates the dataset constructor
     assert made["score"] == ("Synthetic", False) and line["pairs"] == len(info["pairs"]) and line["batch"] == 4
     results = tmp_path / "exp_data" / "trial" / "results"
     names = sorted(os.listdir(results))
@@ -135,3 +135,67 @@ def test_config_driven_run_on_cpu(monkeypatch, tmp_path):
     # the copy of the configuration sits where the reference's offline scorer looks for it (compute_metrics.py:56-58)
     assert "config_" + "_".join(csv[:-4].split("_")[-3:]) + ".yaml" in names
     assert line["csv"] == str(results / csv) and len((results / csv).read_text().splitlines()) == len(info["pairs"])
+
+
+def test_override_scalars_follow_hydra_not_yaml11(tmp_path):
+    """``test.add_description=yes`` must stay the STRING the dataset compares against (YAML 1.1 would make it True)."""
+    d = _write_cfg(tmp_path)
+    for word in ("yes", "no", "on", "off", "wrong", "desconly"):
+        cfg = config.load_config(d, overrides=[f"test.add_description={word}"])
+        assert cfg.test.add_description == word and isinstance(cfg.test.add_description, str)
+    cfg = config.load_config(d, overrides=["dataset.test.split=007", "dataset.test.obj=1:30", "seed=12", "test.dist_th=1e-1", "use_seed=True",
+                                           "tmp.results_out=null", "dataset.img_size=[192, 192]", "exp_tag='yes'"])
+    assert cfg.dataset.test.split == "007" and cfg.dataset.test.obj == "1:30" and cfg.seed == 12 and cfg.test.dist_th == 0.1
+    assert cfg.use_seed is True and cfg.tmp.results_out is None and cfg.dataset.img_size == [192, 192] and cfg.exp_tag == "yes"
+    # the prompt really changes with the flag
+    from oryon_b200.datasets import _PairSplitDataset
+    ds = _PairSplitDataset.__new__(_PairSplitDataset)
+    ds.prompt_templates = ["a photo of a {}."]
+    item = {"metadata": {"cls_names": ["mug"], "cls_descs": [["red", "blue"]]}}
+    ds.add_description = config.load_config(d, overrides=["test.add_description=yes"]).test.add_description
+    assert ds.get_item_prompt(item) == ["red mug", "a photo of a red mug."]
+    ds.add_description = config.load_config(d, overrides=["test.add_description=no"]).test.add_description
+    assert ds.get_item_prompt(item) == ["mug", "a photo of a mug."]
+
+
+def test_pipeline_seed_and_null_src_sampling():
+    """on_test_start seeds with args.seed whenever it is set (pipeline.py:296-299; use_seed does not gate it), and an
+    explicit ``test.src_sampling: null`` means NO source subsample (utils/pcd.py:187), not the default 5000."""
+    from oryon_b200 import pipeline
+    assert pipeline._get({"test": {"src_sampling": None}}, "test.src_sampling", 5000, keep_none=True) is None
+    assert pipeline._get({"test": {}}, "test.src_sampling", 5000, keep_none=True) == 5000
+    assert pipeline._get({"test": {"src_sampling": None}}, "test.src_sampling", 5000) == 5000
+    assert pipeline._get(config.Config({"test": config.Config({"src_sampling": None})}), "test.src_sampling", 5000, keep_none=True) is None
+    assert pipeline._get(config.Config({"test": config.Config()}), "test.src_sampling", 5000, keep_none=True) == 5000
+    pipe = pipeline.FPM_Pipeline.__new__(pipeline.FPM_Pipeline)
+    pipe.pred_file, pipe.args = None, {"seed": 7, "use_seed": False}
+    pipe.on_test_start()
+    a = torch.rand(3)
+    torch.manual_seed(7)
+    assert torch.equal(a, torch.rand(3))
+    pipe.args = {"seed": None, "use_seed": True}
+    pipe.on_test_start()
+    a = torch.rand(3)
+    torch.manual_seed(1)
+    assert torch.equal(a, torch.rand(3))
+
+
+def test_per_pair_seed_makes_draws_independent_of_sharding():
+    from oryon_b200 import pipeline
+    pipe = pipeline.FPM_Pipeline.__new__(pipeline.FPM_Pipeline)
+    pipe.pred_file, pipe.args = None, {"seed": 3}
+    pipe.n_corrs, pipe.src_sampling, pipe.dist_th, pipe.per_pair_seed = 50, 100, 0.25, True
+    pipe.on_test_start()
+    g = torch.Generator().manual_seed(0)
+    dist = torch.rand(6, 400, generator=g) * 0.5
+    n_a = [400, 300, 80, 400, 120, 400]
+    whole = pipe.draw_rows(dist, n_a, [True] * 6, pair_index=list(range(10, 16)))
+    pipe.on_test_start()
+    torch.rand(17)                                   # another rank's generator is somewhere else in its stream
+    part = pipe.draw_rows(dist[3:], n_a[3:], [True] * 3, pair_index=[13, 14, 15])
+    assert torch.equal(whole[3:], part)
+    pipe.per_pair_seed = False
+    pipe.on_test_start()
+    seq = pipe.draw_rows(dist, n_a, [True] * 6, pair_index=list(range(10, 16)))
+    pipe.on_test_start()
+    assert torch.equal(seq, pipe.draw_rows(dist, n_a, [True] * 6)) and not torch.equal(seq[3:], part)

@@ -181,9 +181,12 @@ def test_dataset_mode_glue_on_cpu(monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     orig_score = run_test.score_csv
 
-    def score(csv, ds, exp_tag="", compute_vsd=True):
+    def score(csv, ds, exp_tag="", compute_vsd=True, failed=None):
         models, _, symms = ds.get_object_info()
-        return orig_score(csv, ds, exp_tag, compute_vsd, pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}))
+        scored["failed"] = failed
+        return orig_score(csv, ds, exp_tag, compute_vsd, pose_errors=_OracleBackend(models, {k: format_sym_set(s) for k, s in symms.items()}),
+                          failed=failed)
+    scored = {}
     monkeypatch.setattr(run_test, "score_csv", score)
     out = tmp_path / "pred.csv"
     args = argparse.Namespace(dataset=info["name"], dataset_type=None, root=str(tmp_path), split=info["split"], obj="all", mask="oracle",
@@ -198,4 +201,12 @@ def test_dataset_mode_glue_on_cpu(monkeypatch, tmp_path):
     csv_lines = out.read_text().splitlines()
     assert [l.split(",")[0] for l in csv_lines] == [f"{sa} {ia} {obj}" for sa, ia, _, _, obj in info["pairs"]]
     metrics = json.load(open(tmp_path / "pred.json"))
-    assert metrics["instance_id"] == ids and sum(metrics["Missing segm"]) == 1
+    # in-loop failures (status != ok) are registered as failures, like the reference's on_test_end state (pipeline.py:335-342),
+    # on top of the pair the dataset itself marks invalid
+    n_failed_in_loop = line["status"]["no_corrs"] + line["status"]["invalid_mask"]
+    assert len(scored["failed"]) == n_failed_in_loop and scored["failed"] <= set(ids)
+    invalid_by_dataset = 1
+    assert metrics["instance_id"] == ids
+    assert invalid_by_dataset <= sum(metrics["Missing segm"]) <= invalid_by_dataset + n_failed_in_loop
+    missing = {i for i, m in zip(ids, metrics["Missing segm"]) if m}
+    assert scored["failed"] <= missing
