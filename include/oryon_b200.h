@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORYON_ABI_VERSION 1
+#define ORYON_ABI_VERSION 2
 
 typedef struct oryon_handle oryon_handle;
 
@@ -102,6 +102,16 @@ int oryon_match_nn(oryon_handle* h, const float* feat_a, const float* feat_q, in
  *   stats[0] rows re-scored from the candidate list   stats[1] candidate chunks re-scored
  *   stats[2] rows that overflowed to the exact fallback   stats[3] kernels launched by the call */
 int oryon_match_last_stats(oryon_handle* h, int64_t stats[4], void* stream);
+
+/* Diagnostic: with `enable` != 0 the re-scoring pass of every following oryon_match_nn call on this handle also records, per
+ * anchor row, how long its candidate list was (one atomic per row: off by default).  oryon_match_list_hist reads the
+ * histogram of the LAST call (synchronises the stream):
+ *   hist[0..16]  rows whose lists hold that many 8-column candidate chunks     hist[17] rows that overflowed (exact fallback)
+ *   hist[18..25] rows by candidate COLUMNS re-scored in float32: 1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65+
+ * What it answers: on smooth feature maps (the reference's decoder outputs) how far the tensor-core
+ * candidate filter is from its best case of one column per row. */
+int oryon_match_set_hist(oryon_handle* h, int enable);
+int oryon_match_list_hist(oryon_handle* h, int64_t hist[26], void* stream);
 
 /* HOST-ONLY diagnostic (no device work, no handle): the work decomposition oryon_match_nn uses for its tensor-core pass on
  * a device with `sm_count` SMs.  The units (pair, 256-row anchor block, 128-column query tile) of the batch are distributed

@@ -14,7 +14,7 @@ from typing import Dict, Optional
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MATCH_TC_REFINED = 0
 MATCH_EXACT_FP32 = 1
@@ -59,6 +59,8 @@ SIGNATURES = {
     "oryon_match_nn": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "oryon_match_last_stats": (c_int, [c_void_p, POINTER(c_int64), c_void_p]),
+    "oryon_match_set_hist": (c_int, [c_void_p, c_int]),
+    "oryon_match_list_hist": (c_int, [c_void_p, POINTER(c_int64), c_void_p]),
     "oryon_match_plan": (c_int, [POINTER(c_int32), POINTER(c_int32), c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
                                  POINTER(c_int32)]),
     "oryon_mask_to_roi": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

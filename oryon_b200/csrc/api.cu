@@ -52,6 +52,7 @@ int run_match(oryon_handle*, const float*, const float*, int, int, int, int, con
               const int32_t*, int, int, int, int32_t*, float*, cudaStream_t);
 int run_mask_to_roi(oryon_handle*, const int32_t*, int, int, int, int32_t*, int32_t*, cudaStream_t);
 int read_stats(oryon_handle*, int64_t*, cudaStream_t);
+int read_hist(oryon_handle*, int64_t*, cudaStream_t);
 int plan_debug(const int32_t*, const int32_t*, int, int, int, int32_t*, int, int32_t*, int32_t*);
 }  // namespace match
 namespace stage {
@@ -206,6 +207,16 @@ int oryon_match_nn(oryon_handle* h, const float* feat_a, const float* feat_q, in
 
 int oryon_match_last_stats(oryon_handle* h, int64_t stats[4], void* stream) {
   return oryon::match::read_stats(h, stats, static_cast<cudaStream_t>(stream));
+}
+
+int oryon_match_set_hist(oryon_handle* h, int enable) {
+  ORYON_REQUIRE(h, "oryon_match_set_hist: null handle");
+  h->match_hist = enable != 0;
+  return ORYON_OK;
+}
+
+int oryon_match_list_hist(oryon_handle* h, int64_t hist[26], void* stream) {
+  return oryon::match::read_hist(h, hist, static_cast<cudaStream_t>(stream));
 }
 
 int oryon_match_plan(const int32_t* n_a, const int32_t* n_q, int B, int sm_count, int kind, int32_t* segs_out, int seg_cap,

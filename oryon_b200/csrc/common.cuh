@@ -86,6 +86,7 @@ struct oryon_handle {
   oryon::DeviceBuffer pair_meta;            // per-pair {n_a, n_q} on device
   oryon::DeviceBuffer match_plan;           // segment table of the tensor-core pass (match.cu: Seg)
   int64_t last_launches = 0;
+  bool match_hist = false;                  // oryon_match_set_hist: the refine pass also records candidate-list length histograms
 
   // ---- lift workspace ----
   oryon::DeviceBuffer lift_scratch;

@@ -615,7 +615,14 @@ struct RefineArgs {
   int32_t* overflow_rows;      // packed b * npad_a + r
   int32_t* overflow_count;     // device counter
   unsigned long long* stats;   // [0] rows refined, [1] chunks scored, [2] overflow rows
+  unsigned long long* hist;    // optional (oryon_match_set_hist): [0..17] rows by candidate chunks (17 = overflow), [18..25] rows by
+                               // candidate columns re-scored (1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65+)
 };
+
+__device__ __forceinline__ void record_hist(unsigned long long* hist, int chunks, int cols, bool overflow) {
+  atomicAdd(hist + (overflow ? 17 : min(chunks, 16)), 1ull);
+  if (!overflow) atomicAdd(hist + 18 + (cols <= 1 ? 0 : cols <= 2 ? 1 : min(32 - __clz(cols - 1), 7)), 1ull);
+}
 
 __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
   const int lane = threadIdx.x & 31;
@@ -644,10 +651,12 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
     }
     if (overflow) {
       if (lane == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = a.item_base + item;
+      if (lane == 0 && a.hist) record_hist(a.hist, 0, 0, true);
       ++n_over;
       continue;
     }
     ++n_rows;
+    int h_chunks = 0, h_cols = 0;
     const float4* arow = reinterpret_cast<const float4*>(a.rows32_a + ((size_t)b * a.npad_a + r) * a.D4);
     float best = -INFINITY;
     int best_j = 0x7fffffff;
@@ -675,13 +684,15 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
           if (acc > best || (acc == best && col < best_j)) best = acc, best_j = col;
+          ++h_cols;
         }
-        ++n_chunks;
+        ++n_chunks, ++h_chunks;
       }
     }
     if (lane == 0) {
       a.out_idx[o] = best_j;
       a.out_dist[o] = 0.5f * (-1.f * best + 1.f);
+      if (a.hist) record_hist(a.hist, h_chunks, h_cols, false);
     }
   }
   if (lane == 0 && a.stats) {
@@ -725,9 +736,11 @@ __global__ void __launch_bounds__(256) refine_rows4_kernel(RefineArgs a) {
     }
     if (overflow) {
       if (sub == 0) a.overflow_rows[atomicAdd(a.overflow_count, 1)] = a.item_base + item, ++n_over;
+      if (sub == 0 && a.hist) record_hist(a.hist, 0, 0, true);
       continue;
     }
     if (sub == 0) ++n_rows;
+    int h_chunks = 0, h_cols = 0;
     const float4* arow = reinterpret_cast<const float4*>(a.rows32_a + ((size_t)b * a.npad_a + r) * a.D4);
     float best = -INFINITY;
     int best_j = 0x7fffffff;
@@ -755,13 +768,16 @@ __global__ void __launch_bounds__(256) refine_rows4_kernel(RefineArgs a) {
 #pragma unroll
           for (int off = 4; off >= 1; off >>= 1) acc += __shfl_xor_sync(gmask, acc, off);
           if (acc > best || (acc == best && col < best_j)) best = acc, best_j = col;
+          ++h_cols;
         }
         if (sub == 0) ++n_chunks;
+        ++h_chunks;
       }
     }
     if (sub == 0) {
       a.out_idx[o] = best_j;
       a.out_dist[o] = 0.5f * (-1.f * best + 1.f);
+      if (a.hist) record_hist(a.hist, h_chunks, h_cols, false);
     }
   }
   if (sub == 0 && a.stats) {
@@ -968,11 +984,11 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   ORYON_CUDA_CHECK(cudaSetDevice(h->device));
   int rc;
   if ((rc = h->pair_meta.reserve(sizeof(PairMeta) * B, st))) return rc;
-  if ((rc = h->counters.reserve(256, st))) return rc;
+  if ((rc = h->counters.reserve(512, st))) return rc;
   ORYON_CUDA_CHECK(cudaMemcpyAsync(h->pair_meta.ptr, meta.data(), sizeof(PairMeta) * B, cudaMemcpyHostToDevice, st));
-  ORYON_CUDA_CHECK(cudaMemsetAsync(h->counters.ptr, 0, 256, st));
+  ORYON_CUDA_CHECK(cudaMemsetAsync(h->counters.ptr, 0, 512, st));
   const PairMeta* d_meta = h->pair_meta.as<PairMeta>();
-  // counters: [0] overflow count (int32), bytes 64.. : stats (3 x u64)
+  // counters: [0] overflow count (int32), bytes 64.. : stats (3 x u64), bytes 128.. : optional list-length histogram (26 x u64)
   int32_t* d_overflow_count = h->counters.as<int32_t>();
   unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(h->counters.as<char>() + 64);
 
@@ -1135,6 +1151,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     ra.overflow_rows = h->overflow_rows.as<int32_t>();
     ra.overflow_count = d_overflow_count;
     ra.stats = d_stats;
+    ra.hist = h->match_hist ? reinterpret_cast<unsigned long long*>(h->counters.as<char>() + 128) : nullptr;
     static const bool refine_v1 = std::getenv("ORYON_REFINE_V1") != nullptr;   // A/B switch: one warp per row
     const int warps_needed = refine_v1 ? k.nb * npad_a : (k.nb * npad_a + 3) / 4;
     const int blocks = std::min((warps_needed + 7) / 8, h->sm_count * 16);
@@ -1201,6 +1218,17 @@ int read_stats(oryon_handle* h, int64_t stats[4], cudaStream_t st) {
     ORYON_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   stats[0] = (int64_t)s[0], stats[1] = (int64_t)s[1], stats[2] = (int64_t)s[2], stats[3] = h->last_launches;
+  return ORYON_OK;
+}
+
+int read_hist(oryon_handle* h, int64_t hist[26], cudaStream_t st) {
+  ORYON_REQUIRE(h && hist, "oryon_match_list_hist: null argument");
+  unsigned long long v[26] = {0};
+  if (h->counters.ptr && h->counters.bytes >= 128 + sizeof(v)) {
+    ORYON_CUDA_CHECK(cudaMemcpyAsync(v, h->counters.as<char>() + 128, sizeof(v), cudaMemcpyDeviceToHost, st));
+    ORYON_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  for (int i = 0; i < 26; ++i) hist[i] = (int64_t)v[i];
   return ORYON_OK;
 }
 

@@ -142,6 +142,26 @@ def match_last_stats(device: Optional[torch.device] = None) -> dict:
     return dict(rows_refined=s[0], chunks_rescored=s[1], rows_overflowed=s[2], kernels_launched=s[3])
 
 
+HIST_CHUNK_BINS = [str(i) for i in range(17)] + ["overflow"]
+HIST_COLUMN_BINS = ["1", "2", "3-4", "5-8", "9-16", "17-32", "33-64", "65+"]
+
+
+def match_set_hist(enable: bool, device: Optional[torch.device] = None) -> None:
+    """Diagnostic switch (``oryon_match_set_hist``): record candidate-list length histograms in the re-scoring pass."""
+    dev = device or device_of()
+    _lib.check(_lib.load().oryon_match_set_hist(_lib.handle(dev.index), int(bool(enable))))
+
+
+def match_list_hist(device: Optional[torch.device] = None) -> dict:
+    """Histograms of the last ``match_nn`` call (``oryon_match_list_hist``): anchor rows by candidate chunks kept by the
+    tensor-core pass and by candidate columns re-scored in float32."""
+    dev = device or device_of()
+    h = (ctypes.c_int64 * 26)()
+    _lib.check(_lib.load().oryon_match_list_hist(_lib.handle(dev.index), h, stream_ptr(dev)))
+    return dict(rows_by_chunks=dict(zip(HIST_CHUNK_BINS, [int(v) for v in h[:18]])),
+                rows_by_columns=dict(zip(HIST_COLUMN_BINS, [int(v) for v in h[18:26]])))
+
+
 # ------------------------------------------------------------------------------------------------
 # reference interface
 # ------------------------------------------------------------------------------------------------

@@ -19,21 +19,29 @@ def _run(*argv, env=None):
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    p = _run("bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rows", "64")
+    p = _run("bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0")     # one pair of the full path through the oracle port
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [x for x in p.stdout.splitlines() if x.strip()]
     assert len(lines) == 1, p.stdout
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["metric"] == "image-pairs/sec" and line["unit"] == "pairs/s"
-    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 0
+    assert abs(line["ms_per_step"] * line["steps"] * 1e-3 * line["value"] - line["steps"]) < 1e-6      # the printed step time is the time spent
+    assert line["status"]["ok"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    # both arms print the SAME config (the driver compares them)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oryon_bench_cfg", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert line["config"] == bench.workload_config()
 
 
 def test_reference_arm_under_a_multi_rank_launch_only_rank0_works():
-    p = _run("bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--ref-rows", "64", env={"RANK": "1", "WORLD_SIZE": "2"})
+    p = _run("bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", env={"RANK": "1", "WORLD_SIZE": "2"})
     assert p.returncode == 0 and p.stdout.strip() == ""
 
 

@@ -90,8 +90,66 @@ def test_nn_correspondences_vs_reference_golden(golden_dir, case):
     same_rows = torch.equal(dbg["nn_idx"].cpu().long(), rdbg["nn_idx"]) and torch.equal(dbg["valid"].cpu(), rdbg["valid"])
     if same_rows:
         assert np.array_equal(corrs.cpu().numpy(), g["corrs"])
-    else:  # a near-tie row picked a distance-equivalent neighbour: every row must still be a thresholded NN pair
-        pytest.skip("near-tie rows differ from the reference argmin; covered by test_match_rows_vs_reference_golden")
+    else:  # a near-tie row picked a distance-equivalent neighbour: every returned row must still be a thresholded NN pair
+        _check_corr_rows_are_nn_pairs(corrs.cpu(), fa, fq, ma, mq, th)
+
+
+def _check_corr_rows_are_nn_pairs(corrs, fa, fq, ma, mq, th):
+    """Every ``(y1,x1,y2,x2)`` row: both pixels inside their masks, the query pixel a nearest neighbour of the anchor pixel among
+    the query ROI up to DIST_TOL (float64 evaluation), and its distance below the threshold."""
+    roi2, f2 = _roi_feats(fq, mq)
+    q = torch.nn.functional.normalize(f2.double(), dim=1)
+    a = torch.nn.functional.normalize(fa[:, corrs[:, 0], corrs[:, 1]].T.double(), dim=1)
+    d = 0.5 * (1 - a @ q.T)
+    assert bool((ma[corrs[:, 0], corrs[:, 1]] == 1).all()) and bool((mq[corrs[:, 2], corrs[:, 3]] == 1).all())
+    c = torch.nn.functional.normalize(fq[:, corrs[:, 2], corrs[:, 3]].T.double(), dim=1)
+    d_chosen = 0.5 * (1 - (a * c).sum(1))
+    assert bool((d_chosen - d.min(1).values <= DIST_TOL).all()) and bool((d_chosen < th + DIST_TOL).all())
+
+
+def test_corrs_device_cuda_branch():
+    """``corrs_device='cuda'`` (reference utils/pcd.py:195-197, utils/misc.py:242-254): the reference then evaluates the distances
+    in FLOAT16 on the GPU and draws from the CUDA generator.  What parity means for this branch, and is asserted here:
+      * draws: the two ``multinomial`` calls consume the default CUDA generator exactly as the reference's calls do (same
+        weights vector ``ones(N, float64)`` on the device, same ``n``, same order), so with the distances below the sampled rows
+        are reproduced by replaying those two draws;
+      * distances: the library does NOT emulate the float16 branch -- it returns the float32-exact nearest neighbour (the
+        'cpu' branch's arithmetic), which the float16 evaluation approximates: the float16 minimum differs from it by at most
+        F16_TOL, and wherever a row's float32 top-2 margin exceeds 2 * F16_TOL both branches pick the same column.  (Below that
+        margin the reference's own answer depends on float16 rounding and ATen's tie order.)"""
+    need_gpu()
+    F16_TOL = 2e-3
+    fa, fq, ma, mq, th, max_corrs, sub, seed = synth.match_inputs("m1_d32_64x64_subsample")
+    fa_d, fq_d, ma_d, mq_d = fa.cuda(), fq.cuda(), ma.cuda(), mq.cuda()
+    torch.manual_seed(seed)                      # seeds the CUDA generator too (utils/misc.py:194-195)
+    corrs, dbg = pcd.nn_correspondences(fa_d, fq_d, ma_d, mq_d, th, max_corrs, sub, "cuda", return_debug=True)
+    assert corrs is not None and corrs.is_cuda and corrs.dtype == torch.int64 and tuple(corrs.shape) == (max_corrs, 4)
+    # the reference's float16 branch on the same device, with the same generator state
+    torch.manual_seed(seed)
+    roi1 = torch.nonzero(ma_d == 1)
+    roi2 = torch.nonzero(mq_d == 1)
+    assert roi1.shape[0] > sub
+    idxs = pcd.torch_sample_select(roi1, sub)
+    roi1 = roi1[idxs]
+    f1 = fa_d[:, roi1[:, 0], roi1[:, 1]].T.to(torch.float16)
+    f2 = fq_d[:, roi2[:, 0], roi2[:, 1]].T.to(torch.float16)
+    d16 = 0.5 * (-1 * torch.nn.functional.cosine_similarity(f1.unsqueeze(1), f2.unsqueeze(0), dim=2) + 1)
+    min16, arg16 = torch.amin(d16, dim=1), torch.argmin(d16, dim=1)
+    # same source subsample (first draw identical), float32-exact distances close to the float16 ones
+    W = fa.shape[2]
+    assert torch.equal(dbg["pix1"].long(), roi1[:, 0] * W + roi1[:, 1])
+    assert float((dbg["min_dist"] - min16.float()).abs().max()) <= F16_TOL
+    d64 = 0.5 * (1 - torch.nn.functional.normalize(f1.double(), dim=1) @ torch.nn.functional.normalize(f2.double(), dim=1).T)
+    top2 = torch.topk(d64, 2, dim=1, largest=False)[0]
+    clear = (top2[:, 1] - top2[:, 0]) > 2 * F16_TOL
+    assert int(clear.sum()) > 0 and torch.equal(dbg["nn_idx"].long()[clear], arg16[clear])
+    # second draw replayed on the library's valid set: identical rows
+    valid = torch.nonzero(dbg["min_dist"] < th).squeeze(1)
+    assert torch.equal(valid, dbg["valid"])
+    final = torch.cat((roi1[valid], roi2[dbg["nn_idx"].long()[valid]]), dim=1)
+    sel = pcd.torch_sample_select(final, max_corrs)
+    assert torch.equal(corrs, final[sel])
+    _check_corr_rows_are_nn_pairs(corrs.cpu(), fa, fq, ma, mq, th)
 
 
 def test_host_tensors_are_accepted_and_result_returns_to_host():
