@@ -55,6 +55,7 @@ def workload_config() -> dict:
                    f"{FULL['head_bias_shift']} so that the predicted masks cover ~13 % of the feature map (unshifted: 79 %)",
         "l2": "a step streams 117 MB of inputs, ~1.7 GB of packed weights and GBs of activations: far beyond the 126 MB L2, no flush needed",
         "parallelism": "pairs sharded over the ranks (sharding.shard_pairs), no data-path collective, one all_gather of 16-float result rows",
+        "pipelining": "test.pipelined: the post-network tail of batch k runs on a second stream under the network pass of batch k+1",
     }
 
 
@@ -209,7 +210,7 @@ def prompt_lists(n=FULL["distinct_prompts"]):
     return [[f"object{i}"] + [f"a photo number {t} of a object{i}." for t in range(80)] for i in range(n)]
 
 
-def build_full_path(local, precision, mask_mode):
+def build_full_path(local, precision, mask_mode, pipelined=True):
     from oryon_b200 import synth
     from oryon_b200.models.tokenizer import SimpleTokenizer
     from oryon_b200.net import Oryon
@@ -223,7 +224,8 @@ def build_full_path(local, precision, mask_mode):
                             sigma_d=cfg["sigma_d"], k=cfg["k"], nms_radius=cfg["inlier_threshold"], device=dev)
     args = dict(device=dev, corrs_device="cpu", seed=1, dataset=dict(img_size=[224, 224], max_corrs=500),
                 model=dict(image_encoder=dict(img_size=[192, 192])),
-                test=dict(mask=mask_mode, src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5))
+                test=dict(mask=mask_mode, src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5,
+                          pipelined=pipelined))
     return FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver), model
 
 
@@ -548,6 +550,7 @@ def main():
     ap.add_argument("--matcher-only", action="store_true", help="only the config-2 matcher region (used by tools/ncu_traffic.py)")
     ap.add_argument("--matcher-seconds", type=float, default=2.0, help="minimum length of the config-2 roofline region")
     ap.add_argument("--eager-baseline", action="store_true", help="also time the reference's matcher formulation as PyTorch eager ops on the GPU")
+    ap.add_argument("--no-pipeline", action="store_true", help="A/B: run each batch's post-network tail before the next network pass instead of under it")
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's CPU set (A/B for the e2e scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -592,7 +595,7 @@ def main():
 
     # ---- the full path -----------------------------------------------------------------------------------------------
     B, K, W = FULL["B"], args.steps, args.warmup
-    pipe, model = build_full_path(local, args.precision, args.mask)
+    pipe, model = build_full_path(local, args.precision, args.mask, pipelined=not args.no_pipeline)
     prompts = prompt_lists()
     hb = host_batches(FULL["distinct_batches"], B)
     db = [to_device_batch(b, dev) for b in hb]
@@ -603,11 +606,18 @@ def main():
     assert len(mine) == K * B
 
     def run_steps(batches, n_steps, first_step=0, collect=None):
-        for s in range(n_steps):
-            p0 = (mine.start + (first_step + s) * B) % FULL["split_pairs"]
-            rows = pipe.test_step(step_batch(batches, prompts, first_step + s, p0, B), first_step + s)
-            if collect is not None:
-                collect.append(sharding.encode_rows(list(range(mine.start + s * B, mine.start + (s + 1) * B)), rows))
+        """`n_steps` test steps and the flush of the last one (pipelined mode: a step returns the rows of the batch before it)."""
+        done = 0
+        for s in range(n_steps + 1):
+            if s < n_steps:
+                p0 = (mine.start + (first_step + s) * B) % FULL["split_pairs"]
+                rows = pipe.test_step(step_batch(batches, prompts, first_step + s, p0, B), first_step + s)
+            else:
+                rows = pipe.flush()
+            if rows and collect is not None:
+                collect.append(sharding.encode_rows(list(range(mine.start + done * B, mine.start + (done + 1) * B)), rows))
+            done += 1 if rows else 0
+        assert done == n_steps, (done, n_steps)
 
     pipe.on_test_start()
     run_steps(db, W)

@@ -597,6 +597,231 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair version (cluster of 2, tcgen05 cta_group::2): the default tensor-core pass
+// ------------------------------------------------------------------------------------------------
+// ncu of match_tc_kernel (profiles/r01_match_tc_ncu_v4.md): tensor pipe 68.5 % active, and the reason is operand bandwidth -- a
+// 128x128x16 UMMA reads 8 KB of shared memory in its 64 cycles (128 B/clk, all an SM delivers) while TMA refills 32 B/clk.  Here the
+// two SMs of a TPC work as a pair on ONE 256-row anchor block: each CTA keeps ITS 128 anchor rows resident and stages HALF of every
+// 256-column query tile; one tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16, issued by the leader CTA) multiplies the pair's
+// rows with both halves, reading the peer's half over the inter-SM path.  Per SM and 128 cycles that is 4 KB of A + 4 KB of own
+// B + 4 KB of refill instead of 16 KB + 4 KB: shared-memory traffic per flop halves.  Each CTA receives its 128 rows x 256 columns
+// in its own tensor memory (two such accumulators = all 512 columns) and scans them with its 8 epilogue warps: warp (quarter,
+// half) owns 32 rows x 128 columns of every tile, so a row has two candidate lists per segment (merged by the refine pass like
+// the lists of a cut row block).  The anchor tile is double buffered, so the next row block's rows load during the current sweep.
+// Synchronisation: both producers report their TMA bytes to the LEADER's `full` / `a_full` barriers (cp.async.bulk.tensor
+// .cta_group::2 with a mapa'd barrier address; the leader alone expects the bytes of both halves); tcgen05.commit multicasts
+// `empty`, `a_empty` and `t_full` to both CTAs; the 16 epilogue warps of the pair arrive on the leader's `t_empty`.
+constexpr int kTileN2 = 256;       // query columns per tile of the pair kernel (128 staged by each CTA)
+
+template <int KB_ELEMS, int NUM_KB, int STAGES>
+struct Tc2Smem {
+  static constexpr int kRowBytes = KB_ELEMS * 2;
+  static constexpr int kABlock = kTileM * kRowBytes;            // one k-block of this CTA's 128 anchor rows
+  static constexpr int kABytes = kABlock * NUM_KB;              // one anchor buffer (two are kept)
+  static constexpr int kQStage = kTileM * kRowBytes;            // one k-block of this CTA's half (128 rows) of a query tile
+  static constexpr int kQBytes = kQStage * STAGES;
+  static constexpr int kBarBytes = 8 * (2 * STAGES + 4 + 4) + 16;
+  static constexpr int kTotal = 1024 /*align slack*/ + 2 * kABytes + kQBytes + kBarBytes;
+};
+
+template <int KB_ELEMS, int NUM_KB, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+match_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_q, TcArgs args) {
+  using L = Tc2Smem<KB_ELEMS, NUM_KB, STAGES>;
+  constexpr int kRowBytes = L::kRowBytes;
+  constexpr int kKSteps = KB_ELEMS / 16;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kTileM, kTileN2, /*fp16*/ 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                   // [2][NUM_KB][128 rows]
+  uint8_t* smem_q = smem + 2 * L::kABytes;                  // [STAGES][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_q + L::kQBytes);
+  uint64_t* full = bars;                 // [STAGES]  both producers -> leader's MMA warp (leader's copy is the live one)
+  uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> both producers (multicast commit)
+  uint64_t* a_full = bars + 2 * STAGES;  // [2]       anchor buffer landed in both CTAs (leader's copy)
+  uint64_t* a_empty = a_full + 2;        // [2]       all MMAs reading the buffer retired (multicast)
+  uint64_t* t_full = a_empty + 2;        // [2]       accumulator ready (multicast)
+  uint64_t* t_empty = t_full + 2;        // [2]       accumulator drained by all 16 epilogue warps of the pair (leader's copy)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_q);
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a_full[i], 1), ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 16);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_base_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();      // the peer's barriers are initialised and its tensor memory allocated before anything is signalled
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int pair_id = blockIdx.x >> 1;
+  const int seg_lo = args.seg_begin[pair_id], seg_hi = args.seg_begin[pair_id + 1];
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs: own anchor rows, own half of the query tiles) ============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_iter = 0;
+      for (int si = seg_lo; si < seg_hi; ++si) {
+        const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);
+        const int b = sg.x & 0xFFFFFF, rb = sg.y, j0 = sg.z, j1 = sg.w;
+        const uint32_t abuf = a_iter & 1;
+        ptx::mbar_wait(&a_empty[abuf], ((a_iter >> 1) & 1) ^ 1);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[abuf], 2 * L::kABytes);
+        const uint32_t a_bar = ptx::mapa_shared(ptx::smem_u32(&a_full[abuf]), 0);
+#pragma unroll
+        for (int kb = 0; kb < NUM_KB; ++kb)
+          ptx::tma_load_2d_pair(smem_a + abuf * L::kABytes + kb * L::kABlock, &tm_a, a_bar, kb * KB_ELEMS,
+                                b * args.npad_a + rb * kCtaRows + (int)rank * kTileM);
+        for (int j = j0; j < j1; ++j) {
+          for (int kb = 0; kb < NUM_KB; ++kb) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::kQStage);
+            ptx::tma_load_2d_pair(smem_q + stage * L::kQStage, &tm_q, ptx::mapa_shared(ptx::smem_u32(&full[stage]), 0), kb * KB_ELEMS,
+                                  b * args.npad_q + j * kTileN2 + (int)rank * kTileM);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+        ++a_iter;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ============================
+    if (rank == 0) {
+      uint32_t stage = 0, phase = 0, a_iter = 0, tile_iter = 0;
+      for (int si = seg_lo; si < seg_hi; ++si) {
+        const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);
+        const int j0 = __shfl_sync(0xffffffffu, sg.z, 0), j1 = __shfl_sync(0xffffffffu, sg.w, 0);
+        const uint32_t abuf = a_iter & 1;
+        ptx::mbar_wait(&a_full[abuf], (a_iter >> 1) & 1);
+        for (int j = j0; j < j1; ++j) {
+          const uint32_t buf = tile_iter & 1;
+          ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kTileN2;
+          for (int kb = 0; kb < NUM_KB; ++kb) {
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t dq0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_q + stage * L::kQStage), kRowBytes);
+            const uint64_t da0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_a + abuf * L::kABytes + kb * L::kABlock), kRowBytes);
+            const bool leader = ptx::elect_one();
+#pragma unroll
+            for (int k = 0; k < kKSteps; ++k)
+              if (leader) ptx::umma_f16_pair(d_tmem, da0 + 2 * k, dq0 + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            if (leader) {
+              ptx::umma_commit_pair(&empty[stage], 3);                       // both CTAs' stage slots reusable
+              if (kb == NUM_KB - 1) ptx::umma_commit_pair(&t_full[buf], 3);  // accumulator complete in both CTAs
+            }
+            __syncwarp();
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+          ++tile_iter;
+        }
+        if (ptx::elect_one()) ptx::umma_commit_pair(&a_empty[abuf], 3);
+        __syncwarp();
+        ++a_iter;
+      }
+    }
+  } else {
+    // ============================ epilogue (8 warps per CTA: 4 lane quarters x 2 column halves) ============================
+    const int ew = (warp - 2) & 7;
+    const int half = ew >> 2;              // columns [128 * half, +128) of every 256-column tile
+    const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
+    const int row_in_block = (int)rank * kTileM + quarter * 32 + lane;
+    const uint32_t t_empty_leader[2] = {ptx::mapa_shared(ptx::smem_u32(&t_empty[0]), 0), ptx::mapa_shared(ptx::smem_u32(&t_empty[1]), 0)};
+    uint32_t tile_iter = 0;
+    for (int si = seg_lo; si < seg_hi; ++si) {
+      const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);
+      const int b = sg.x & 0xFFFFFF, s = sg.x >> 24, rb = sg.y, j0 = sg.z, j1 = sg.w;
+      const PairMeta pm = args.meta[b];
+      const int row = rb * kCtaRows + row_in_block;
+      const bool row_ok = row < pm.n_a;
+      const size_t slot = (((size_t)b * args.splits + s) * 2 + half) * args.npad_a + row;
+      uint32_t* my_list = args.cand_chunk + slot * kCandCap;
+      float m_run = -INFINITY;
+      float thr = row_ok ? -INFINITY : INFINITY;  // rows beyond n_a never record anything
+      int cnt = 0;
+      for (int j = j0; j < j1; ++j) {
+        const uint32_t buf = tile_iter & 1;
+        ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kTileN2 + half * (kTileN2 / 2);
+        const int col_base = j * kTileN2 + half * (kTileN2 / 2);
+        const bool ragged = col_base + kTileN2 / 2 > pm.n_q;
+        uint32_t va[32], vb[32];
+        auto scan = [&](uint32_t (&v)[32], int g) {
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col_base + g * 32 + i >= pm.n_q) v[i] = 0xff800000u;  // -inf
+          }
+          float cm[32 / kChunk];
+#pragma unroll
+          for (int c = 0; c < 32 / kChunk; ++c) cm[c] = max8(v + c * kChunk);
+          float gm = cm[0];
+#pragma unroll
+          for (int c = 1; c < 32 / kChunk; ++c) gm = fmaxf(gm, cm[c]);
+          if (gm >= thr) {
+#pragma unroll
+            for (int c = 0; c < 32 / kChunk; ++c) {
+              if (cm[c] >= thr) {
+                if (cm[c] > m_run + args.ambiguity) cnt = 0;  // every earlier candidate is now out of range
+                if (cnt < kCandCap) {
+                  const float lim = cm[c] - args.ambiguity;
+                  uint32_t bits = 0;
+#pragma unroll
+                  for (int i = 0; i < kChunk; ++i) bits |= (__uint_as_float(v[c * kChunk + i]) >= lim ? 1u : 0u) << i;
+                  my_list[cnt] = static_cast<uint32_t>((col_base + g * 32) / kChunk + c) | (bits << 24);
+                }
+                ++cnt;
+                m_run = fmaxf(m_run, cm[c]);
+                thr = m_run - args.ambiguity;
+              }
+            }
+          }
+        };
+        ptx::tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
+        for (int g = 0; g < kTileN2 / 64; g += 2) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x32b_x32(taddr + (g + 1) * 32, vb);
+          scan(va, g);
+          ptx::tmem_ld_wait();
+          if (g + 2 < kTileN2 / 64) ptx::tmem_ld_32x32b_x32(taddr + (g + 2) * 32, va);
+          scan(vb, g + 1);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[buf]);
+        ++tile_iter;
+      }
+      if (row_ok) args.cand_m[slot] = m_run, args.cand_cnt[slot] = cnt;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();      // neither CTA leaves (or frees tensor memory) while the pair's last MMAs / arrivals may touch it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // refine: exact fp32 score of every column of every listed chunk; one warp per anchor row
 // ------------------------------------------------------------------------------------------------
 struct RefineArgs {
@@ -608,6 +833,7 @@ struct RefineArgs {
   const uint32_t* cand_chunk;
   const uint8_t* nseg;         // [B][npad_a / kCtaRows] candidate lists (segments) per anchor row block
   int B, npad_a, npad_q, D4, splits, cap_a;
+  int halves;                  // candidate lists per (row, segment): 1 (single-CTA kernel) or 2 (pair kernel: one per column half)
   int item_base;               // first pair of this launch * npad_a (overflow rows are packed with batch-wide pair indices)
   float ambiguity;
   int32_t* out_idx;
@@ -641,7 +867,7 @@ __global__ void __launch_bounds__(256) refine_rows_kernel(RefineArgs a) {
       if (lane == 0) a.out_idx[o] = -1, a.out_dist[o] = INFINITY;
       continue;
     }
-    const int lists = a.nseg[b * (a.npad_a / kCtaRows) + r / kCtaRows] * kEpiSets;
+    const int lists = a.nseg[b * (a.npad_a / kCtaRows) + r / kCtaRows] * a.halves;
     float m_all = -INFINITY;
     bool overflow = false;
     for (int s = 0; s < lists; ++s) {
@@ -726,7 +952,7 @@ __global__ void __launch_bounds__(256) refine_rows4_kernel(RefineArgs a) {
       if (sub == 0) a.out_idx[o] = -1, a.out_dist[o] = INFINITY;
       continue;
     }
-    const int lists = a.nseg[b * (a.npad_a / kCtaRows) + r / kCtaRows] * kEpiSets;
+    const int lists = a.nseg[b * (a.npad_a / kCtaRows) + r / kCtaRows] * a.halves;
     float m_all = -INFINITY;
     bool overflow = false;
     for (int s = 0; s < lists; ++s) {

@@ -189,6 +189,12 @@ class FPM_Pipeline:
         self.batched_tail = bool(_get(args, "test.batched_tail", True))   # False: per-pair selection / lifting (any frame sizes)
         self._host_dist: Optional[Tensor] = None
         self._host_rows: Optional[Tensor] = None
+        # test.pipelined: the post-network tail of batch k (matching, draws, lifting, registration, rows) runs on a second,
+        # high-priority stream UNDER the network pass of batch k+1 (see test_step).  Off by default: test_step then returns the
+        # rows of the batch it was given.
+        self.pipelined = bool(_get(args, "test.pipelined", False))
+        self._pending: Optional[dict] = None
+        self._tail_stream: Optional[torch.cuda.Stream] = None
 
     # ---- LightningModule surface -----------------------------------------------------------------------
     def forward(self, x: dict) -> Dict[str, Tensor]:
@@ -221,6 +227,7 @@ class FPM_Pipeline:
         ``args.seed`` whenever it is not None, else 1 (pipeline.py:296-299; ``use_seed`` only gates the dataset constructor)."""
         if pred_path is not None:
             self.pred_file = open(pred_path, "w")
+        self._pending = None
         if seed is None:
             cfg_seed = _get(self.args, "seed", None)
             seed = int(cfg_seed) if cfg_seed is not None else 1
@@ -230,10 +237,21 @@ class FPM_Pipeline:
         torch.cuda.manual_seed(seed)
         self.rows = []
 
-    def on_test_end(self):
+    def flush(self) -> List[dict]:
+        """Pipelined mode: finishes the batch whose tail is still outstanding and returns its rows (``[]`` if there is none)."""
+        rows: List[dict] = []
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            rows = self._back(pending)
+        return rows
+
+    def on_test_end(self) -> List[dict]:
+        """Closes the prediction CSV (after the last outstanding batch of the pipelined mode, whose rows are returned)."""
+        rows = self.flush()
         if self.pred_file is not None:
             self.pred_file.close()
             self.pred_file = None
+        return rows
 
     # ---- a7 -----------------------------------------------------------------------------------------------
     def mask_results(self, batch: dict, outputs: Dict[str, Tensor]) -> Dict[str, Tensor]:
@@ -430,9 +448,45 @@ class FPM_Pipeline:
     def test_step(self, batch: dict, batch_idx: int = 0, *, register_as_test: bool = True) -> List[dict]:
         """The reference's hot loop (pipeline.py:306-355) for one batch; returns (and accumulates in ``self.rows``)
         one record per pair: ids, ``pred_pose_rel`` (identity on failure, :335-350), ``pred_pose`` =
-        ``pred_pose_rel @ anchor pose`` (:320), IoUs, status, and writes the CSV line when a file is open."""
+        ``pred_pose_rel @ anchor pose`` (:320), IoUs, status, and writes the CSV line when a file is open.
+
+        ``test.pipelined``: the step is split into a FRONT (network pass + mask post-processing, enqueued on the current
+        stream) and a BACK (matching -> draws -> selection / lifting -> PointDSC -> rows).  The call enqueues the front of ITS
+        batch, then runs the back of the PREVIOUS batch on a second, high-priority stream -- its kernels and all of its host
+        work (two host synchronisations, the CPU-generator draws, the row bookkeeping) execute while the GPU is busy with the
+        network pass just enqueued -- and returns the previous batch's rows (``[]`` on the first call).  ``on_test_end`` /
+        ``flush`` finish the last batch.  CSV lines, evaluator registrations and the draws on the CPU generator keep the
+        reference's pair order, so a run produces the same files as the unpipelined loop; like the reference's own
+        ``test_step`` (which returns ``None``) the results of a batch are only complete at ``on_test_end``."""
+        front = self._front(batch, register_as_test)
+        if not self.pipelined:
+            return self._back(front)
+        if self._tail_stream is None:
+            self._tail_stream = torch.cuda.Stream(self.device, priority=-1)
+        front["ready"] = torch.cuda.Event()
+        front["ready"].record(torch.cuda.current_stream(self.device))
+        pending, self._pending = self._pending, front
+        return self._back(pending) if pending is not None else []
+
+    def _front(self, batch: dict, register_as_test: bool = True) -> dict:
         outputs = self.forward(batch)
         results = self.mask_results(batch, outputs)
+        return dict(batch=batch, outputs=outputs, results=results, register_as_test=register_as_test)
+
+    def _back(self, front: dict) -> List[dict]:
+        if front.get("ready") is None:
+            return self._back_on_current_stream(front)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._tail_stream):
+            self._tail_stream.wait_event(front["ready"])
+            rows = self._back_on_current_stream(front)
+            self._tail_stream.synchronize()      # everything that read this batch's tensors has run: they may be released
+        # tensors created by the back on the tail stream and handed to the caller (rows[i]['corrs']) are safe to use on `main`
+        main.wait_stream(self._tail_stream)
+        return rows
+
+    def _back_on_current_stream(self, front: dict) -> List[dict]:
+        batch, outputs, results, register_as_test = front["batch"], front["outputs"], front["results"], front["register_as_test"]
         B = outputs["featmap_a"].shape[0]
         _, _, na, nq = self._masks_and_counts(results)
         valid = [(a > 0 and q > 0) for a, q in zip(na.tolist(), nq.tolist())]
@@ -477,11 +531,13 @@ class FPM_Pipeline:
         ``test_step``, registered through ``register_eval`` / ``register_valid_failure`` (no instance ids), no prediction CSV.
         The loss terms of that hook (``FeatureLoss``) are training code and are not computed: the records are returned instead
         of a loss."""
+        self.flush()                                     # a validation batch is never deferred (no CSV, rows returned at once)
         pred_file, self.pred_file = self.pred_file, None
+        pipelined, self.pipelined = self.pipelined, False
         try:
             return self.test_step(batch, batch_idx, register_as_test=False)
         finally:
-            self.pred_file = pred_file
+            self.pred_file, self.pipelined = pred_file, pipelined
 
     @staticmethod
     def _eval_depth(batch: dict, i: int):

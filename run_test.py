@@ -44,11 +44,13 @@ def pair_ids(pair_index: int) -> tuple:
 
 def run_sharded(n_pairs: int, batch_size: int, step_fn: Callable[[Sequence[int]], List[dict]], *, out_path: Optional[str] = None,
                 device: Optional[torch.device] = None, sync: Optional[Callable[[], None]] = None,
-                id_fn: Callable[[int], tuple] = None) -> Dict:
+                id_fn: Callable[[int], tuple] = None, flush_fn: Optional[Callable[[], List[dict]]] = None) -> Dict:
     """The sharded test loop.  ``step_fn(pair_indices)`` returns one record per pair with the keys ``status``, ``iou_a``,
     ``iou_q``, ``pred_pose_rel`` (``FPM_Pipeline.test_step``'s records).  Returns, on every rank, the gathered table in pair
     order, the status counts and the loop time (max over ranks); rank 0 also writes ``out_path`` (``id_fn(pair_index)`` gives
-    the two ``'scene image object'`` ids of a CSV line; default: synthetic ids)."""
+    the two ``'scene image object'`` ids of a CSV line; default: synthetic ids).  A pipelined step (``test.pipelined``) returns
+    the records of an EARLIER batch (or none); ``flush_fn`` (``FPM_Pipeline.flush``) then delivers the last ones: records are
+    matched to pair indices in submission order."""
     from oryon_b200.pipeline import format_pred_line
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -60,15 +62,25 @@ def run_sharded(n_pairs: int, batch_size: int, step_fn: Callable[[Sequence[int]]
         if world > 1:
             dist.barrier()
 
-    local = []
+    local, submitted = [], []
+
+    def take(rows):
+        if not rows:
+            return
+        if not submitted or len(rows) != len(submitted[0]):
+            raise RuntimeError(f"step_fn returned {len(rows)} records for {len(submitted[0]) if submitted else 0} pairs")
+        local.append(sharding.encode_rows(submitted.pop(0), rows))
+
     barrier()
     t0 = time.perf_counter()
     for s in range(mine.start, mine.stop, batch_size):
         idx = list(range(s, min(s + batch_size, mine.stop)))
-        rows = step_fn(idx)
-        if len(rows) != len(idx):
-            raise RuntimeError(f"step_fn returned {len(rows)} records for {len(idx)} pairs")
-        local.append(sharding.encode_rows(idx, rows))
+        submitted.append(idx)
+        take(step_fn(idx))
+    if flush_fn is not None:
+        take(flush_fn())
+    if submitted:
+        raise RuntimeError(f"{len(submitted)} batches were submitted and never returned (a pipelined step needs flush_fn)")
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
     local_t = torch.cat(local) if local else torch.zeros(0, sharding.ROW_FLOATS, dtype=torch.float64)
@@ -118,7 +130,8 @@ def build_pipeline(local_rank: int, precision: int, opts=None, evaluator=None):
     args = dict(device=dev, corrs_device="cpu", dataset=dict(img_size=[224, 224], max_corrs=500),
                 model=dict(image_encoder=dict(img_size=[192, 192])),
                 test=dict(mask=mask, src_sampling=5000, solver="pointdsc", n_corrs=500, dist_th=0.25, mask_threshold=0.5,
-                          per_pair_seed=bool(opts is not None and getattr(opts, "per_pair_seed", False))))
+                          per_pair_seed=bool(opts is not None and getattr(opts, "per_pair_seed", False)),
+                          pipelined=not bool(opts is not None and getattr(opts, "no_pipeline", False))))
     return FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver, evaluator=evaluator), model
 
 
@@ -190,7 +203,8 @@ def dataset_loop(ds, pipe, *, batch: int, seed: int, workers: int, out: Optional
         return pipe.test_step(b, idx[0] // batch)
 
     pipe.on_test_start(seed=seed)
-    res = run_sharded(len(ds), batch, step, out_path=out, device=dev, sync=torch.cuda.synchronize, id_fn=lambda i: dataset_pair_ids(ds, i))
+    res = run_sharded(len(ds), batch, step, out_path=out, device=dev, sync=torch.cuda.synchronize, id_fn=lambda i: dataset_pair_ids(ds, i),
+                      flush_fn=getattr(pipe, "flush", None))
     pipe.on_test_end()
     if rank == 0 and score and out is not None:
         failed = {pair_instance_id(ds, r["pair_index"]) for r in res["records"] if r["status"] != "ok"}
@@ -242,6 +256,8 @@ def run_config(cfg, opts, world: int, rank: int, local: int, dev: torch.device, 
     model = Oryon(cfg, cfg["device"], precision=opts.precision, tokenizer=tokenizer)
     if model.tokenizer is None:
         raise SystemExit(f"run_test.py: CLIP BPE vocabulary not found (pretrained.vocabulary = {vocab})")
+    if select(cfg, "test.pipelined") is None and isinstance(cfg.get("test"), dict):
+        cfg["test"]["pipelined"] = not getattr(opts, "no_pipeline", False)      # tails run under the next batch's network pass
     pipe = pipeline.FPM_Pipeline(cfg, test_model=True, model=model)
     out = opts.out
     if out is None:
@@ -292,6 +308,7 @@ def main(argv=None):
     ap.add_argument("--per-pair-seed", action="store_true", help="re-seed the draw generators from (seed, global pair index) before every pair: "
                                                                  "the prediction rows then do not depend on the number of ranks (SURVEY.md 8e); "
                                                                  "default: the reference's single sequential draw stream per rank")
+    ap.add_argument("--no-pipeline", action="store_true", help="run every batch's post-network tail before the next network pass instead of under it")
     ap.add_argument("--pointdsc", default=None, help="PointDSC snapshot directory (args.pretrained.pointdsc)")
     args = ap.parse_args(argv)
 
@@ -340,8 +357,9 @@ def main(argv=None):
 
     pipe.on_test_start(seed=args.seed)              # one rank = the reference's draw order; --per-pair-seed: sharding-independent rows
     step(list(range(min(args.batch, args.pairs))))  # warm-up: workspaces, arena, clocks
+    pipe.flush()
     pipe.on_test_start(seed=args.seed)
-    res = run_sharded(args.pairs, args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize)
+    res = run_sharded(args.pairs, args.batch, step, out_path=args.out, device=dev, sync=torch.cuda.synchronize, flush_fn=pipe.flush)
     pipe.on_test_end()
     if rank == 0:
         line = json.dumps({"metric": "image-pairs/sec (whole test loop)", "value": args.pairs / res["seconds"], "unit": "pairs/s",

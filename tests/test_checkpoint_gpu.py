@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from gpu_util import need_gpu
-from oryon_b200 import synth
+from oryon_b200 import _lib, synth
 from oryon_b200 import synth_backbone as sb
 from oryon_b200.net import Oryon
 from oryon_b200.utils.pointdsc import init as pdsc
@@ -73,10 +73,13 @@ def test_reference_layout_files_to_loaded_model(tmp_path, monkeypatch):
     monkeypatch.chdir(root)
     rgb_a, rgb_q = sb.synthetic_images(1, 2), sb.synthetic_images(2, 2)
     tokens = sb.synthetic_tokens(3, 1)[0]
+    _lib.destroy_all()            # a library handle holds ONE packed network: a fresh handle per model of this test
     direct = Oryon(None, "cuda:0", state_dict=final, vis_layers=VIS, txt_layers=TXT)
     emb_d = direct.encode_tokens(tokens)
     out_d = {k: v.clone() for k, v in direct.forward_tensors(rgb_a, rgb_q, emb_d[None].expand(2, -1, -1).contiguous()).items()}
     emb_d = emb_d.clone()
+    torch.cuda.synchronize()
+    _lib.destroy_all()
     from_files = Oryon(args, "cuda:0", vis_layers=VIS, txt_layers=TXT)       # reads the four files like the reference's constructor + ckpt load
     assert from_files._load_error is None and from_files._loaded
     emb_f = from_files.encode_tokens(tokens)
@@ -89,8 +92,12 @@ def test_reference_layout_files_to_loaded_model(tmp_path, monkeypatch):
     wrong = dict(final)
     other = sb.oryon_state_dict(12, vis_layers=VIS, txt_layers=TXT)
     wrong.update({k: other[k] for k in final if k.startswith("decoder.")})
+    out_f = {k: v.clone() for k, v in out_f.items()}
+    _lib.destroy_all()
     out_w = Oryon(None, "cuda:0", state_dict=wrong, vis_layers=VIS, txt_layers=TXT).forward_tensors(rgb_a, rgb_q, emb_d[None].expand(2, -1, -1).contiguous())
     assert not torch.equal(out_w["featmap_a"], out_d["featmap_a"])
+    torch.cuda.synchronize()
+    _lib.destroy_all()
 
 
 def test_missing_file_is_named_by_the_first_forward(tmp_path, monkeypatch):
@@ -100,6 +107,7 @@ def test_missing_file_is_named_by_the_first_forward(tmp_path, monkeypatch):
     os.remove(os.path.join(root, "pretrained_models", "catseg.pth"))
     monkeypatch.setenv("HOME", home)
     monkeypatch.chdir(root)
+    _lib.destroy_all()
     model = Oryon(args, "cuda:0", vis_layers=VIS, txt_layers=TXT)
     with pytest.raises(RuntimeError, match="catseg.pth"):
         model.forward_tensors(sb.synthetic_images(1, 1), sb.synthetic_images(2, 1), torch.zeros(1, 80, 768))

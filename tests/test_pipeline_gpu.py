@@ -252,3 +252,31 @@ def test_decoded_frames_to_metrics_end_to_end(system, tmp_path):
         key = f"scene{i}_1{i}_scene{i}_2{i}_mug"
         np.testing.assert_array_equal(preds[key].astype(np.float32), r["pred_pose_rel"].numpy()[:3])
         assert np.float32(ia[key]) == np.float32(r["iou_a"])
+
+
+@pytest.mark.parametrize("mask_mode", ["oracle", "predicted"])
+def test_pipelined_steps_equal_unpipelined(system, mask_mode, tmp_path):
+    """``test.pipelined`` (the tail of batch k on a second stream under the network pass of batch k+1) must change nothing but
+    WHEN rows are returned: same CSV bytes, same statuses, correspondences and poses, rows delivered one call later and the
+    last batch by ``flush`` / ``on_test_end``."""
+    model, solver, _ = system
+    batches = [_stacked_batch(synth.synthetic_batch(40 + k, 3, empty_mask_pairs=(1,) if k == 1 else ())) for k in range(3)]
+    out = {}
+    for mode in (False, True):
+        args = dict(ARGS, test=dict(ARGS["test"], mask=mask_mode, pipelined=mode))
+        pipe = FPM_Pipeline(args, test_model=True, model=model, pointdsc_solver=solver)
+        path = str(tmp_path / f"pred_{int(mode)}.csv")
+        pipe.on_test_start(path)
+        returned = [pipe.test_step(dict(b), k) for k, b in enumerate(batches)]
+        returned.append(pipe.on_test_end())
+        torch.cuda.synchronize()
+        out[mode] = (returned, list(pipe.rows), open(path).read())
+    plain, piped = out[False], out[True]
+    assert [len(r) for r in plain[0]] == [3, 3, 3, 0] and [len(r) for r in piped[0]] == [0, 3, 3, 3]
+    assert piped[2] == plain[2] and len(plain[2].splitlines()) == 9
+    for a, b in zip(plain[1], piped[1]):
+        assert a["status"] == b["status"] and a["instance_id_a"] == b["instance_id_a"]
+        assert torch.equal(a["pred_pose_rel"], b["pred_pose_rel"]) and a["iou_a"] == b["iou_a"] or (a["iou_a"] != a["iou_a"])
+        assert (a["corrs"] is None) == (b["corrs"] is None) and (a["corrs"] is None or torch.equal(a["corrs"], b["corrs"]))
+    if mask_mode == "oracle":
+        assert [r["status"] for r in plain[1]][4] == "invalid_mask"
