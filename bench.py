@@ -462,7 +462,7 @@ def matcher_region(cfg, cfg_name, local, world, rank, barrier, peaks, min_second
     use_sustained = region_s >= 1.0
     peak_tf = sustained if use_sustained else burst
     hbm_peak = peaks.get("hbm_gbs") or 6650.0
-    traffic, traffic_src = measured_traffic("match_tc_kernel", cfg_name)
+    traffic, traffic_src = measured_traffic("match_tc_kernel", cfg_name)      # the tensor-core pass (match_tc2_kernel: CTA pairs)
     step_ms = ms_max / steps
     out = {
         "workload": f"{cfg_name}: B={B} pairs/GPU, D={D}, {H}x{W} ({n} positions/image), dense all-pairs NN matching ({4 * H}x{4 * W} frames at "

@@ -1083,6 +1083,19 @@ static int launch_tc(oryon_handle* h, const CUtensorMap& tma, const CUtensorMap&
   return ORYON_OK;
 }
 
+template <int KB_ELEMS, int NUM_KB, int STAGES>
+static int launch_tc2(oryon_handle* h, const CUtensorMap& tma, const CUtensorMap& tmq, const TcArgs& args, int pairs, cudaStream_t st) {
+  using L = Tc2Smem<KB_ELEMS, NUM_KB, STAGES>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  auto kern = match_tc2_kernel<KB_ELEMS, NUM_KB, STAGES>;
+  ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  h->span_begin(KID_MATCH_TC, st);
+  kern<<<2 * pairs, kTcThreads, L::kTotal, st>>>(tma, tmq, args);   // __cluster_dims__(2,1,1): CTAs 2p, 2p+1 form pair p
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct TcPlan {
@@ -1105,7 +1118,7 @@ struct TcPlan {
 // A quota is either 0 or >= tiles_max / (kMaxSplits - 1), so no row block is shared by more than kMaxSplits CTAs.
 enum PlanKind { kPlanHybrid = 0, kPlanContiguous = 1, kPlanWholeTasks = 2 };
 
-static void build_tc_plan(const std::vector<PairMeta>& meta, int rb_per_pair, int sm_count, int kind, TcPlan* plan) {
+static void build_tc_plan(const std::vector<PairMeta>& meta, int rb_per_pair, int n_workers, int kind, TcPlan* plan, int tile_n = kTileN) {
   struct Task {
     int b, rb, tiles;
   };
@@ -1117,7 +1130,7 @@ static void build_tc_plan(const std::vector<PairMeta>& meta, int rb_per_pair, in
   for (int b = 0; b < B; ++b) {
     const PairMeta& pm = meta[b];
     if (pm.n_a <= 0 || pm.n_q <= 0) continue;
-    const int tiles = (pm.n_q + kTileN - 1) / kTileN, rbs = (pm.n_a + kCtaRows - 1) / kCtaRows;
+    const int tiles = (pm.n_q + tile_n - 1) / tile_n, rbs = (pm.n_a + kCtaRows - 1) / kCtaRows;
     for (int rb = 0; rb < rbs; ++rb) tasks.push_back(Task{b, rb, tiles});
     units += (long long)rbs * tiles;
     tiles_max = std::max(tiles_max, tiles);
@@ -1126,7 +1139,7 @@ static void build_tc_plan(const std::vector<PairMeta>& meta, int rb_per_pair, in
     plan->begin.assign(1, 0);
     return;
   }
-  const int G = sm_count;
+  const int G = n_workers;   // CTAs of the single-CTA kernel, CTA pairs of the pair kernel
   const long long min_share = (tiles_max + kMaxSplits - 2) / (kMaxSplits - 1);
   size_t n_bulk = tasks.size() / G * G;
   if (kind == kPlanContiguous) n_bulk = 0;
@@ -1231,7 +1244,12 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   const int kb_elems = sw64 ? 32 : 64;
   const int Dpad = round_up(D, kb_elems);
   const int num_kb = Dpad / kb_elems;
-  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), kTileN);
+  // tensor-core pass: CTA pairs (tcgen05 cta_group::2, 256-column query tiles) unless ORYON_MATCH_1CTA is set (A/B switch: the
+  // single-CTA kernel of round 1)
+  static const bool force_1cta = std::getenv("ORYON_MATCH_1CTA") != nullptr;
+  const bool use_pair = !force_1cta && h->sm_count >= 2;
+  const int tile_n = use_pair ? kTileN2 : kTileN;
+  const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), tile_n);
 
   if ((rc = h->rows16_a.reserve((size_t)B * npad_a * Dpad * 2, st))) return rc;
   if ((rc = h->rows16_q.reserve((size_t)B * npad_q * Dpad * 2, st))) return rc;
@@ -1308,7 +1326,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     return !e ? kPlanHybrid : !strcmp(e, "contiguous") ? kPlanContiguous : !strcmp(e, "whole") ? kPlanWholeTasks : kPlanHybrid;
   }();
   const int rb_per_pair = npad_a / kCtaRows;
-  const int halves = kEpiSets;   // candidate lists per (row, segment): one per epilogue warp set
+  const int halves = use_pair ? 2 : kEpiSets;   // candidate lists per (row, segment): one per column half (pair kernel) / warp set
   struct Chunk {   // a range of pairs with its work decomposition and its slice of the candidate / plan buffers
     int b0, nb, splits;
     TcPlan plan;
@@ -1316,7 +1334,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   };
   Chunk all;
   all.b0 = 0, all.nb = B;
-  build_tc_plan(meta, rb_per_pair, h->sm_count, plan_kind, &all.plan);
+  build_tc_plan(meta, rb_per_pair, use_pair ? h->sm_count / 2 : h->sm_count, plan_kind, &all.plan, tile_n);
   all.splits = std::max(all.plan.splits, 1);
   all.slot_base = 0, all.slots = (size_t)B * all.splits * halves * npad_a;
   all.off_begin = 0;
@@ -1348,8 +1366,19 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     CUtensorMap tma, tmq;
     int r;
     if ((r = make_rows_tensor_map(h, &tma, h->rows16_a.as<__half>() + (size_t)k.b0 * npad_a * Dpad, k.nb * npad_a, Dpad, kb_elems, kTileM))) return r;
-    if ((r = make_rows_tensor_map(h, &tmq, h->rows16_q.as<__half>() + (size_t)k.b0 * npad_q * Dpad, k.nb * npad_q, Dpad, kb_elems, kTileN))) return r;
-    if (sw64) {
+    if ((r = make_rows_tensor_map(h, &tmq, h->rows16_q.as<__half>() + (size_t)k.b0 * npad_q * Dpad, k.nb * npad_q, Dpad, kb_elems, kTileM))) return r;   // 128 query rows per TMA box: a whole tile (single CTA) / this CTA's half (pair)
+    if (use_pair) {
+      if (sw64) {
+        r = launch_tc2<32, 1, 8>(h, tma, tmq, ta, k.plan.grid, stream);
+      } else {
+        switch (num_kb) {
+          case 1: r = launch_tc2<64, 1, 8>(h, tma, tmq, ta, k.plan.grid, stream); break;
+          case 2: r = launch_tc2<64, 2, 8>(h, tma, tmq, ta, k.plan.grid, stream); break;
+          case 3: r = launch_tc2<64, 3, 6>(h, tma, tmq, ta, k.plan.grid, stream); break;
+          default: r = launch_tc2<64, 4, 5>(h, tma, tmq, ta, k.plan.grid, stream); break;
+        }
+      }
+    } else if (sw64) {
       r = launch_tc<32, 1, 8>(h, tma, tmq, ta, k.plan.grid, stream);
     } else {
       switch (num_kb) {
@@ -1371,6 +1400,7 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     ra.cand_m = cand_m + k.slot_base, ra.cand_cnt = cand_cnt + k.slot_base, ra.cand_chunk = cand_chunk + k.slot_base * kCandCap;
     ra.nseg = reinterpret_cast<const uint8_t*>(h->match_plan.as<char>() + k.off_nseg);
     ra.B = k.nb, ra.npad_a = npad_a, ra.npad_q = npad_q, ra.D4 = D4, ra.splits = k.splits * halves, ra.cap_a = cap_a;
+    ra.halves = halves;
     ra.item_base = k.b0 * npad_a;
     ra.ambiguity = kAmbiguity;
     ra.out_idx = out_idx + (size_t)k.b0 * cap_a, ra.out_dist = out_dist + (size_t)k.b0 * cap_a;
@@ -1406,14 +1436,16 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
 
 int plan_debug(const int32_t* n_a, const int32_t* n_q, int B, int sm_count, int kind, int32_t* segs_out, int seg_cap,
                int32_t* begin_out, int32_t* info_out) {
+  const bool pair = (kind & 0x100) != 0;   // the plan of the CTA-pair kernel: 256-column tiles over sm_count / 2 pairs
+  kind &= 0xFF;
   ORYON_REQUIRE(n_a && n_q && B > 0 && B < (1 << 24) && sm_count > 0 && begin_out && info_out && (segs_out || seg_cap == 0) &&
-                    kind >= kPlanHybrid && kind <= kPlanWholeTasks,
+                    kind >= kPlanHybrid && kind <= kPlanWholeTasks && (!pair || sm_count >= 2),
                 "oryon_match_plan: bad argument");
   std::vector<PairMeta> meta(B);
   int max_a = 0;
   for (int b = 0; b < B; ++b) meta[b].n_a = n_a[b], meta[b].n_q = n_q[b], max_a = std::max(max_a, n_a[b]);
   TcPlan plan;
-  build_tc_plan(meta, std::max(1, round_up(max_a, kCtaRows) / kCtaRows), sm_count, kind, &plan);
+  build_tc_plan(meta, std::max(1, round_up(max_a, kCtaRows) / kCtaRows), pair ? sm_count / 2 : sm_count, kind, &plan, pair ? kTileN2 : kTileN);
   info_out[0] = plan.grid, info_out[1] = plan.splits, info_out[2] = (int32_t)plan.segs.size();
   for (int c = 0; c <= plan.grid; ++c) begin_out[c] = plan.begin[c];
   ORYON_REQUIRE((int)plan.segs.size() <= seg_cap || seg_cap == 0, "oryon_match_plan: %zu segments, capacity %d", plan.segs.size(), seg_cap);

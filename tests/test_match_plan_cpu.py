@@ -1,7 +1,8 @@
 """CPU: the host-side work decomposition of the matcher's tensor-core pass (oryon_match_plan, match.cu: build_tc_plan).
 
-The units (pair, 256-row anchor block, 128-column query tile) of a batch are distributed over the CTAs of the persistent
-kernel: whole row blocks round robin for the full waves, the remaining row blocks cut into per-CTA tile quotas.  The
+The units (pair, 256-row anchor block, query tile) of a batch are distributed over the workers of the persistent kernel -- the
+CTAs of the single-CTA kernel (128-column tiles) or the CTA pairs of the default cta_group::2 kernel (256-column tiles, kind |
+0x100): whole row blocks round robin for the full waves, the remaining row blocks cut into per-CTA tile quotas.  The
 properties checked here are the ones the kernel and the refine pass rely on: every unit is covered exactly once, the
 segments of a row block carry consecutive slots below the reported list count, no row block is shared by more than 8 CTAs,
 and the per-CTA loads are level (to one unit when the pairs are uniform)."""
@@ -33,8 +34,13 @@ def plan(n_a, n_q, sm_count=148, kind=HYBRID):
     return grid, lists, np.frombuffer(segs, dtype=np.int32)[:5 * nseg].reshape(nseg, 5).copy(), np.array(begin[:grid + 1])
 
 
+PAIR = 0x100
+
+
 def check(n_a, n_q, sm_count=148, kind=HYBRID):
     grid, lists, segs, begin = plan(n_a, n_q, sm_count, kind)
+    COLS = 256 if kind & PAIR else 128
+    sm_count = sm_count // 2 if kind & PAIR else sm_count
     units = {}
     for b, (a, q) in enumerate(zip(n_a, n_q)):
         if a > 0 and q > 0:
@@ -103,3 +109,24 @@ def test_ragged_random_batches(seed, kind):
         tiles_max = max(-(-q // COLS) for a, q in zip(n_a, n_q) if a > 0 and q > 0)
         # level to within one task / one minimum quota of the ideal share
         assert max(per_cta) <= -(-sum(per_cta) // sm) + tiles_max + -(-tiles_max // 7)
+
+
+def test_pair_kernel_plan_config2_config5_and_reference_shape():
+    """The default kernel works in CTA pairs on 256-column tiles: 74 workers on a B200."""
+    grid, lists, per = check([19200] * 32, [19200] * 32, kind=HYBRID | PAIR)
+    assert grid == 74 and lists <= MAX_LISTS and max(per) - min(per) <= 1        # 2 400 row blocks x 75 tiles over 74 pairs
+    grid, lists, per = check([76800] * 8, [76800] * 8, kind=HYBRID | PAIR)
+    assert grid == 74 and max(per) - min(per) <= 1
+    grid, lists, per = check([5000], [36864], kind=HYBRID | PAIR)                 # 20 row blocks x 144 tiles
+    assert grid >= 60 and lists <= MAX_LISTS
+    assert check([1], [1], kind=HYBRID | PAIR)[:2] == (1, 1)
+    assert check([0, 3], [5, 0], kind=HYBRID | PAIR)[0] == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pair_kernel_plan_ragged(seed):
+    rng = random.Random(100 + seed)
+    B = rng.randint(1, 40)
+    n_a = [rng.choice([0, 1, 255, 256, 257, rng.randint(1, 20000)]) for _ in range(B)]
+    n_q = [rng.choice([0, 1, 255, 256, 257, rng.randint(1, 40000)]) for _ in range(B)]
+    check(n_a, n_q, sm_count=rng.choice([2, 8, 132, 148]), kind=HYBRID | PAIR)
