@@ -118,9 +118,9 @@ int oryon_match_list_hist(oryon_handle* h, int64_t hist[26], void* stream);
  * over the CTAs of the persistent kernel as lists of segments: whole row blocks round robin for the full waves, the rest cut
  * into per-CTA tile quotas that level the finishing times (kind 0, the default; 1 = one contiguous range per CTA, 2 = whole
  * row blocks only; the environment variable ORYON_MATCH_PLAN=contiguous|whole selects 1 / 2 inside oryon_match_nn).
- * kind | 0x100: the decomposition of the default CTA-PAIR kernel (tcgen05 cta_group::2): units are (pair, 256-row anchor block,
- * 256-column query tile) distributed over sm_count / 2 CTA pairs; begin_out then has sm_count / 2 + 1 entries.  Without the
- * flag: the single-CTA kernel (ORYON_MATCH_1CTA=1), 128-column tiles over sm_count CTAs.
+ * kind | 0x100: the decomposition of the CTA-PAIR kernel (tcgen05 cta_group::2, selected by ORYON_MATCH_PAIR=1): units are
+ * (pair, 256-row anchor block, 256-column query tile) distributed over sm_count / 2 CTA pairs; begin_out then has
+ * sm_count / 2 + 1 entries.  Without the flag: the default single-CTA kernel, 128-column tiles over sm_count CTAs.
  *   n_a, n_q   HOST int32 [B] list lengths          seg_cap   capacity of segs_out in segments (0: only count)
  *   segs_out   HOST int32 [seg_cap][5]: pair, row block, first tile, end tile, candidate-list slot of the row block
  *   begin_out  HOST int32 [sm_count + 1]: first segment of CTA c in [c], total in [grid]

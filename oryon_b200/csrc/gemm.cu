@@ -429,6 +429,275 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// gemm_tc2_kernel<NPASS>: the same GEMM on CTA PAIRS (cluster of 2, tcgen05 cta_group::2) for the large, N % 256 == 0 products
+// (every CLIP linear layer: 27 of the 33 ms of GEMM time per 16 pairs).
+//
+// Why: in gemm_tc_kernel a stage feeds 24 UMMAs of 128x128x16 (two row blocks x three products x four K steps = 1 536 tensor
+// cycles) that read 8 KB of shared memory each (128 B/clk, all an SM delivers) while TMA writes the next 96 KB stage (64 B/clk):
+// 192 B/clk of demand against 128 -> the 69-75 % tensor-pipe ceiling ncu shows (profiles/r01_gemm_tc_ncu_v4.md).  A pair works on a
+// 256 x 256 output tile: each CTA stages ITS 128 rows of A and HALF (128 rows) of the W tile, hi and lo = 64 KB per stage, and one
+// tcgen05.mma.cta_group::2 of M = 256, N = 256, K = 16 (128 tensor cycles on both SMs) reads 4 KB of A + 4 KB of own W per SM, the
+// other W half coming from the peer: 64 B/clk of operand reads + 43 B/clk of refill = 107 B/clk, under the limit.
+// Each CTA gets 128 rows x 256 columns of D in its own tensor memory (x2 buffers = 512 columns) and its 8 epilogue warps (4 lane
+// quarters x 2 column halves) run the same fused epilogue as the single-CTA kernel.  Barriers as in match_tc2_kernel: both
+// producers report to the leader's `full`; tcgen05.commit multicasts `empty` / `t_full`; 16 epilogue warps arrive on the leader's
+// `t_empty`.
+constexpr int kPairTN = 256;
+
+template <int NPASS>
+struct Cfg2 {
+  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kABlock = kTileM * kKB * 2;                    // 16 KB: 128 rows x 64 K of one half (hi or lo)
+  static constexpr int kABytes = kABlock * kHalves;                   // this CTA's 128 rows of A
+  static constexpr int kWBytes = kABlock * kHalves;                   // this CTA's 128 rows (half) of the W tile
+  static constexpr int kStage = kABytes + kWBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStage;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kBarBytes = (8 * (2 * kStages + 4) + 16 + 15) / 16 * 16;
+  static constexpr int kEpiBytes = 8 * kEpiWarpFloats * 4;
+  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes + kEpiBytes;
+  static_assert(kStages >= 2, "pipeline depth");
+};
+
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int NPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const __grid_constant__ KArgs args) {
+  using L = Cfg2<NPASS>;
+  constexpr int STAGES = L::kStages;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kTileM, kPairTN, /*fp16*/ 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kStage * STAGES);
+  uint64_t* full = bars;               // leader's copy is the live one
+  uint64_t* empty = bars + STAGES;     // multicast
+  uint64_t* t_full = empty + STAGES;   // [2] multicast
+  uint64_t* t_empty = t_full + 2;      // [2] leader's copy, 16 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a_hi);
+    ptx::prefetch_tensormap(&tm_w_hi);
+    if (NPASS == 3) ptx::prefetch_tensormap(&tm_a_lo), ptx::prefetch_tensormap(&tm_w_lo);
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 16);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tasks_per_mat = args.tiles_m * args.tiles_n;      // tiles_m: 256-row blocks, tiles_n: 256-column blocks
+  const int total_tasks = tasks_per_mat * args.nb0 * args.nb1;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = pair_id; t < total_tasks; t += n_pairs) {
+        const int nt = t % args.tiles_n, mt = (t / args.tiles_n) % args.tiles_m;
+        const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
+        const int arow = mt * kCtaRows + (int)rank * kTileM, wrow = nt * kPairTN + (int)rank * kTileM;
+        for (int kb = 0; kb < args.KB; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * L::kStage);
+          const uint32_t bar = ptx::mapa_shared(ptx::smem_u32(&full[stage]), 0);
+          uint8_t* sa = smem + stage * L::kStage;
+          uint8_t* sw = sa + L::kABytes;
+          tma_load_4d_pair(sa, &tm_a_hi, bar, kb * kKB, arow, b0, b1);
+          if (NPASS == 3) tma_load_4d_pair(sa + L::kABlock, &tm_a_lo, bar, kb * kKB, arow, b0, b1);
+          tma_load_4d_pair(sw, &tm_w_hi, bar, kb * kKB, wrow, b0, b1);
+          if (NPASS == 3) tma_load_4d_pair(sw + L::kABlock, &tm_w_lo, bar, kb * kKB, wrow, b0, b1);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      uint32_t stage = 0, phase = 0, tile_iter = 0;
+      for (int t = pair_id; t < total_tasks; t += n_pairs) {
+        const uint32_t buf = tile_iter & 1;
+        ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kPairTN;
+        for (int kb = 0; kb < args.KB; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
+          const uint32_t sw = sa + L::kABytes;
+          const uint64_t da_hi = ptx::make_smem_desc_kmajor(sa, 128), da_lo = ptx::make_smem_desc_kmajor(sa + (NPASS == 3 ? L::kABlock : 0), 128);
+          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS == 3 ? L::kABlock : 0), 128);
+          const bool leader = ptx::elect_one();
+#pragma unroll
+          for (int pass = 0; pass < NPASS; ++pass) {
+            // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
+            const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
+#pragma unroll
+            for (int k = 0; k < kKB / 16; ++k)
+              if (leader) ptx::umma_f16_pair(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);
+          }
+          if (leader) {
+            ptx::umma_commit_pair(&empty[stage], 3);
+            if (kb == args.KB - 1) ptx::umma_commit_pair(&t_full[buf], 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        ++tile_iter;
+      }
+    }
+  } else {
+    // ============================ epilogue (8 warps: 4 lane quarters x 2 column halves of the CTA's 128 x 256 block) ============================
+    const int ew = warp - 2, half = ew >> 2, quarter = warp & 3;
+    const int row_in_tile = (int)rank * kTileM + quarter * 32 + lane;
+    const Epilogue& ep = args.ep;
+    const uint32_t stage_f = ptx::smem_u32(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats * 4;   // [32][kEpiLd] floats
+    const uint32_t bias_s = stage_f + 32 * kEpiLd * 4;                                                             // [128] floats
+    const uint32_t t_empty_leader0 = ptx::mapa_shared(ptx::smem_u32(&t_empty[0]), 0), t_empty_leader1 = ptx::mapa_shared(ptx::smem_u32(&t_empty[1]), 0);
+    const int sub_row = lane >> 2, cg = lane & 3;
+    uint32_t tile_iter = 0;
+    for (int t = pair_id; t < total_tasks; t += n_pairs) {
+      const int nt = t % args.tiles_n, mt = (t / args.tiles_n) % args.tiles_m;
+      const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
+      const uint32_t buf = tile_iter & 1;
+      const int row = mt * kCtaRows + row_in_tile;
+      int drow = row < args.M ? row : -1;
+      if (drow >= 0 && ep.row_map) drow = ep.row_map[row];
+      const int64_t base32 = (int64_t)b1 * ep.out_b1 + (int64_t)b0 * ep.out_b0;
+      const int64_t baseh = (int64_t)b1 * ep.outh_b1 + (int64_t)b0 * ep.outh_b0;
+      const int ncol0 = nt * kPairTN + half * (kPairTN / 2);     // first column of this warp's 128-column slice
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kPairTN / 64; ++j) {
+        const int col = ncol0 + j * 32 + lane;
+        ptx::st_shared_f1(bias_s + (j * 32 + lane) * 4, (ep.bias && col < args.N) ? __ldg(ep.bias + col) : 0.f);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kPairTN + half * (kPairTN / 2);
+#pragma unroll 1
+      for (int g = 0; g < kPairTN / 32; ++g) {
+        const int col0 = ncol0 + g * 16;
+        if (col0 >= args.N) break;   // warp-uniform
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(taddr + g * 16, v);
+        ptx::tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bq = ptx::ld_shared_f4(bias_s + (g * 16 + 4 * i) * 4);
+          x[4 * i] = fmaf(__uint_as_float(v[4 * i]), ep.alpha, bq.x), x[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), ep.alpha, bq.y);
+          x[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), ep.alpha, bq.z), x[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), ep.alpha, bq.w);
+        }
+        switch (ep.act) {
+          case ACT_QUICKGELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.f + expf(-1.702f * x[i]));
+            break;
+          case ACT_GELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = 0.5f * x[i] * (1.f + erff(x[i] * 0.70710678118654752440f));
+            break;
+          case ACT_RELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+            break;
+          default: break;
+        }
+        if (ep.transpose_h) {
+          if (drow >= 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < args.N) {
+                __half hh, ll;
+                split_half(x[i], hh, ll);
+                const int64_t o = baseh + (int64_t)(col0 + i) * ep.ldh + drow;
+                ep.out_hi[o] = hh;
+                if (ep.out_lo) ep.out_lo[o] = ll;
+              }
+          }
+          if (!ep.out32) continue;
+        }
+        __syncwarp();  // previous chunk's readers are done with the staging tile
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ptx::st_shared_f4(stage_f + (lane * kEpiLd + 4 * i) * 4, make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
+        __syncwarp();
+        const int col = col0 + cg * 4;
+        const bool vec_ok = col + 3 < args.N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = k * 8 + sub_row;
+          const int dr = __shfl_sync(0xffffffffu, drow, r);
+          if (dr < 0 || col >= args.N) continue;
+          float4 y = ptx::ld_shared_f4(stage_f + (r * kEpiLd + cg * 4) * 4);
+          const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
+          if (vec_ok && (ep.ld32 & 3) == 0) {
+            if (ep.residual) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(ep.residual + o32));
+              y.x += q.x, y.y += q.y, y.z += q.z, y.w += q.w;
+            }
+            if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o32) = y;
+          } else {
+            float* yy = reinterpret_cast<float*>(&y);
+            for (int i = 0; i < 4; ++i)
+              if (col + i < args.N) {
+                if (ep.residual) yy[i] += ep.residual[o32 + i];
+                if (ep.out32) ep.out32[o32 + i] = yy[i];
+              }
+          }
+          if (ep.out_hi && !ep.transpose_h) {
+            const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
+            __half hh[4], ll[4];
+            split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
+            if (vec_ok && (ep.ldh & 3) == 0) {
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
+            } else {
+              for (int i = 0; i < 4; ++i)
+                if (col + i < args.N) {
+                  ep.out_hi[oh + i] = hh[i];
+                  if (ep.out_lo) ep.out_lo[oh + i] = ll[i];
+                }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(buf ? t_empty_leader1 : t_empty_leader0);
+      ++tile_iter;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 static int make_map(oryon_handle* h, CUtensorMap* tm, const __half* base, int kpad, int rows, int nb0, int nb1, int64_t ld,
                     int64_t sb0, int64_t sb1, int box_rows) {
   const cuuint64_t gdim[4] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
@@ -502,6 +771,63 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
   return ORYON_OK;
 }
 
+template <int NPASS>
+static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
+  using L = Cfg2<NPASS>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  const int kpad = round_up(p.K, kKB);
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  int rc;
+  if ((rc = make_map(h, &tw_hi, p.W.hi, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
+  tw_lo = tw_hi;
+  if (NPASS == 3 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
+  if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+  ta_lo = ta_hi;
+  if (NPASS == 3 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+  KArgs ka;
+  ka.K = p.K;
+  ka.M = p.M, ka.N = p.N, ka.KB = kpad / kKB;
+  ka.nb0 = p.nb0, ka.nb1 = p.nb1;
+  ka.tiles_m = (p.M + kCtaRows - 1) / kCtaRows;
+  ka.tiles_n = (p.N + kPairTN - 1) / kPairTN;
+  ka.ep = p.ep;
+  const long long tasks = (long long)ka.tiles_m * ka.tiles_n * p.nb0 * p.nb1;
+  const int pairs = (int)std::min<long long>(h->sm_count / 2, tasks);
+  auto kern = gemm_tc2_kernel<NPASS>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  static const bool log_shapes = getenv("ORYON_GEMM_LOG") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (log_shapes) cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventRecord(e0, st);
+  h->span_begin(KID_GEMM, st);
+  kern<<<2 * pairs, kThreads, L::kTotal, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, ka);   // __cluster_dims__(2,1,1)
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  if (log_shapes) {
+    cudaEventRecord(e1, st), cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "gemm(pair) M=%d N=%d K=%d batch=%dx%d npass=%d tasks=%lld  %.1f us  %.0f TFLOP/s (algorithmic)\n", p.M, p.N, p.K, p.nb0,
+            p.nb1, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  }
+  ++h->gemm_launches;
+  h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  return ORYON_OK;
+}
+
+// The pair kernel pays off where a 256 x 256 tile is full and there are enough tiles to fill the 74 pairs.
+static bool use_pair_kernel(const oryon_handle* h, const Problem& p) {
+  static const bool off = getenv("ORYON_GEMM_1CTA") != nullptr;   // A/B switch
+  if (off || p.gather || h->sm_count < 2) return false;
+  if (p.N % kPairTN != 0) return false;
+  const long long tasks = (long long)((p.M + kCtaRows - 1) / kCtaRows) * (p.N / kPairTN) * p.nb0 * p.nb1;
+  return tasks >= h->sm_count / 2;
+}
+
 int launch(oryon_handle* h, const Problem& p, cudaStream_t st) {
   ORYON_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.nb0 > 0 && p.nb1 > 0, "gemm: empty problem (M=%d N=%d K=%d)", p.M, p.N, p.K);
   ORYON_REQUIRE(p.precision == 1 || p.precision == 3, "gemm: precision must be 1 or 3");
@@ -535,6 +861,7 @@ int launch(oryon_handle* h, const Problem& p, cudaStream_t st) {
                 "gemm: operand strides must be multiples of 8 elements (16 bytes)");
   ORYON_REQUIRE(p.A.ld >= round_up(p.K, kKB) || p.A.ld >= p.K, "gemm: A row stride shorter than K");
   ORYON_REQUIRE(!p.ep.row_map || (p.nb0 == 1 && p.nb1 == 1), "gemm: row_map needs an unbatched problem");
+  if (use_pair_kernel(h, p)) return p.precision == 3 ? launch_pair<3>(h, p, st) : launch_pair<1>(h, p, st);
   if (p.precision == 3) {
     switch (tn) {
       case 32: return launch_t<32, 3>(h, p, st);

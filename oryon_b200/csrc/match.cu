@@ -741,7 +741,7 @@ match_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int half = ew >> 2;              // columns [128 * half, +128) of every 256-column tile
     const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
     const int row_in_block = (int)rank * kTileM + quarter * 32 + lane;
-    const uint32_t t_empty_leader[2] = {ptx::mapa_shared(ptx::smem_u32(&t_empty[0]), 0), ptx::mapa_shared(ptx::smem_u32(&t_empty[1]), 0)};
+    const uint32_t t_empty_leader0 = ptx::mapa_shared(ptx::smem_u32(&t_empty[0]), 0), t_empty_leader1 = ptx::mapa_shared(ptx::smem_u32(&t_empty[1]), 0);
     uint32_t tile_iter = 0;
     for (int si = seg_lo; si < seg_hi; ++si) {
       const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);
@@ -805,7 +805,7 @@ match_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader[buf]);
+        if (lane == 0) ptx::mbar_arrive_cluster(buf ? t_empty_leader1 : t_empty_leader0);
         ++tile_iter;
       }
       if (row_ok) args.cand_m[slot] = m_run, args.cand_cnt[slot] = cnt;
@@ -1244,10 +1244,16 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
   const int kb_elems = sw64 ? 32 : 64;
   const int Dpad = round_up(D, kb_elems);
   const int num_kb = Dpad / kb_elems;
-  // tensor-core pass: CTA pairs (tcgen05 cta_group::2, 256-column query tiles) unless ORYON_MATCH_1CTA is set (A/B switch: the
-  // single-CTA kernel of round 1)
-  static const bool force_1cta = std::getenv("ORYON_MATCH_1CTA") != nullptr;
-  const bool use_pair = !force_1cta && h->sm_count >= 2;
+  // tensor-core pass: the single-CTA kernel, or -- ORYON_MATCH_PAIR=1, read per call so that one process can run both -- CTA
+  // pairs (tcgen05 cta_group::2, 256-column query tiles).  Measured on B200 at config 2 (profiles/r02_match_pair_vs_1cta.md):
+  // pair 2.74 ms / 59 % tensor-pipe active, single CTA 2.53 ms / 68.5 %.  Warp-state sampling shows why neither is limited by
+  // operand bandwidth: the MMA warp spends ~3/4 of its time waiting for a drained accumulator (t_empty) while the epilogue warps
+  // wait a third of theirs for a filled one -- at D = 128 a 128 x 256 fp32 accumulator (128 KB of tensor memory) must be read
+  // out every 1 024 tensor cycles, and that read-out plus the two barrier round trips takes ~2 000 cycles per buffer; with only
+  // 512 tensor-memory columns there is no room for a third buffer.  The pair kernel's buffers are twice as wide per barrier
+  // round trip, hence slower.  At D = 256 (config 5) the same single-CTA kernel is MMA-paced (0.98 of the sustained peak).
+  const char* pair_env = std::getenv("ORYON_MATCH_PAIR");
+  const bool use_pair = pair_env && pair_env[0] == '1' && h->sm_count >= 2;
   const int tile_n = use_pair ? kTileN2 : kTileN;
   const int npad_a = round_up(max_a, kCtaRows), npad_q = round_up(std::max(max_q, 1), tile_n);
 

@@ -152,6 +152,30 @@ def test_corrs_device_cuda_branch():
     _check_corr_rows_are_nn_pairs(corrs.cpu(), fa, fq, ma, mq, th)
 
 
+@pytest.mark.parametrize("case", ["m0_d32_48x48", "m2_d128_40x40_full", "m5_d17_24x40_ragged", "m6_d32_96x96_refsize"])
+def test_cta_pair_kernel_matches_reference_golden(golden_dir, case, monkeypatch):
+    """The cta_group::2 variant of the tensor-core pass (ORYON_MATCH_PAIR=1; slower than the default at config 2, kept as a
+    measured alternative) against the same reference goldens, plus a ragged dense batch against the oracle."""
+    need_gpu()
+    monkeypatch.setenv("ORYON_MATCH_PAIR", "1")
+    g = np.load(os.path.join(golden_dir, f"match_{case}.npz"))
+    fa, fq, ma, mq, th, max_corrs, sub, seed = synth.match_inputs(case)
+    roi1, f1 = _roi_feats(fa, ma)
+    roi2, f2 = _roi_feats(fq, mq)
+    pix1 = (roi1[:, 0] * fa.shape[2] + roi1[:, 1]).int().cuda()
+    pix2 = (roi2[:, 0] * fq.shape[2] + roi2[:, 1]).int().cuda()
+    idx, dist = pcd.match_nn(fa[None].cuda(), fq[None].cuda(), pix1[None], pix2[None], [pix1.numel()], [pix2.numel()])
+    torch.cuda.synchronize()
+    _check_rows(idx[0], dist[0], torch.from_numpy(g["nn_idx"]).long(), torch.from_numpy(g["min_dist"]), f1, f2, torch.from_numpy(g["margin"]))
+    fa, fq, perm = synth.permuted_feature_batch(77, 3, 64, 30, 34, noise=0.3)
+    idx, dist = pcd.match_nn(fa.cuda(), fq.cuda())
+    torch.cuda.synchronize()
+    for b in range(3):
+        a, q = fa[b].reshape(64, -1).T.contiguous(), fq[b].reshape(64, -1).T.contiguous()
+        rd, ri = oracle.match_rows(a, q)
+        _check_rows(idx[b], dist[b], ri, rd, a, q)
+
+
 def test_host_tensors_are_accepted_and_result_returns_to_host():
     need_gpu()
     fa, fq, ma, mq, th, max_corrs, sub, seed = synth.match_inputs("m0_d32_48x48")

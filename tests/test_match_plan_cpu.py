@@ -1,8 +1,8 @@
 """CPU: the host-side work decomposition of the matcher's tensor-core pass (oryon_match_plan, match.cu: build_tc_plan).
 
 The units (pair, 256-row anchor block, query tile) of a batch are distributed over the workers of the persistent kernel -- the
-CTAs of the single-CTA kernel (128-column tiles) or the CTA pairs of the default cta_group::2 kernel (256-column tiles, kind |
-0x100): whole row blocks round robin for the full waves, the remaining row blocks cut into per-CTA tile quotas.  The
+CTAs of the default single-CTA kernel (128-column tiles) or the CTA pairs of the cta_group::2 kernel (ORYON_MATCH_PAIR=1;
+256-column tiles, kind | 0x100): whole row blocks round robin for the full waves, the remaining row blocks cut into per-CTA tile quotas.  The
 properties checked here are the ones the kernel and the refine pass rely on: every unit is covered exactly once, the
 segments of a row block carry consecutive slots below the reported list count, no row block is shared by more than 8 CTAs,
 and the per-CTA loads are level (to one unit when the pairs are uniform)."""
@@ -112,7 +112,7 @@ def test_ragged_random_batches(seed, kind):
 
 
 def test_pair_kernel_plan_config2_config5_and_reference_shape():
-    """The default kernel works in CTA pairs on 256-column tiles: 74 workers on a B200."""
+    """The cta_group::2 kernel works in CTA pairs on 256-column tiles: 74 workers on a B200."""
     grid, lists, per = check([19200] * 32, [19200] * 32, kind=HYBRID | PAIR)
     assert grid == 74 and lists <= MAX_LISTS and max(per) - min(per) <= 1        # 2 400 row blocks x 75 tiles over 74 pairs
     grid, lists, per = check([76800] * 8, [76800] * 8, kind=HYBRID | PAIR)
