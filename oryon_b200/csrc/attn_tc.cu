@@ -6,7 +6,7 @@
 //                              a single V^T stage exposed one full TMA latency per key tile, 37k -> cycles per CTA)
 //   warp 1      MMA issuer     S = Q K^T (M=128, N=128, K=64) into a double-buffered TMEM accumulator;
 //                              O += P V (M=128, N=64, K=128) into a third TMEM region
-//   warps 2..9  softmax        thread <-> query row (TMEM lane); two warps per lane quarter, each owning 64 of the 128
+//   warps 2..17 softmax        thread <-> query row (TMEM lane); four warps per lane quarter, each owning 32 of the 128
 //                              key columns of a tile.  Pass 1 over the key tiles: row maximum (a single hi*hi product
 //                              is enough: softmax is invariant to the subtracted constant).  Pass 2: S is recomputed
 //                              (K = 64: cheap), p = exp2((s - max) * scale * log2 e), the row sum accumulates in a
@@ -18,6 +18,7 @@
 // extra Q K^T costs little tensor work on a kernel that is bound by the exp / convert work of the softmax warps.
 // Operands are fp16 split pairs; NPASS = 3 evaluates hi*hi + lo*hi + hi*lo (see gemm.cuh).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -29,7 +30,14 @@ namespace attn {
 constexpr int kQ = 128;      // queries per CTA
 constexpr int kKT = 128;     // keys per tile
 constexpr int kD = 64;       // head dim
-constexpr int kThreads = 320;   // TMA, MMA, 8 softmax warps
+// Softmax warps: 16 = four per TMEM lane quarter, each owning 32 of the 128 key columns of a tile.  Round 1 ran 8 (64 columns per
+// thread): ncu showed the kernel bound by the softmax warps with the issue slots 32 % used -- two warps per scheduler cannot hide
+// the tensor-memory loads, MUFU latency and barrier waits of one another.  With four per scheduler (and half the registers per
+// thread) the same instruction stream overlaps better; see profiles/r02_attn_tc.md for the measured effect.
+constexpr int kSmWarps = 16;
+constexpr int kParts = kSmWarps / 4;            // column groups per tile
+constexpr int kPartCols = 128 / kParts;         // 32 key columns per thread and tile
+constexpr int kThreads = 64 + 32 * kSmWarps;    // TMA, MMA, softmax warps
 constexpr int kTileBytes = 128 * 64 * 2;   // one [128][64] fp16 tile, 128-byte rows, SWIZZLE_128B
 
 template <int NPASS>
@@ -43,8 +51,9 @@ struct Cfg {
   static constexpr int kOffV = kOffK + 2 * kKStage;
   static constexpr int kOffP = kOffV + 2 * kVBytes;
   static constexpr int kOffBar = kOffP + kPBytes;
-  static constexpr int kOffRed = kOffBar + 256;               // [2][128] floats: cross-warp max / sum exchange
-  static constexpr int kTotal = 1024 + kOffRed + 2 * 128 * 4;
+  // the cross-warp max / sum exchanges ([kParts][128] floats) borrow operand tiles that are dead at that moment: the P buffer
+  // before pass 2 writes it, the Q tile after the last Q K^T has completed (there is no room for a separate 2 KB)
+  static constexpr int kTotal = 1024 + kOffBar + 256;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
@@ -104,10 +113,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     if (!VMN) ptx::prefetch_tensormap(&tm_vt_hi);
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], 8);
+      ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], kSmWarps);
       ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
     }
-    ptx::mbar_init(p_full, 8), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(p_full, kSmWarps), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -222,74 +231,76 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     __syncwarp();
   } else {
     const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
-    const int half = (warp - 2) >> 2;                   // which 64 key columns of every tile this warp owns
+    const int part = (warp - 2) >> 2;                   // which kPartCols key columns of every tile this warp owns
     const int r = quarter * 32 + lane;                  // row of the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    float* red = reinterpret_cast<float*>(smem + L::kOffRed);   // [2][128]
+    float* red = reinterpret_cast<float*>(sP);          // [kParts][128]: the P buffer is not written before pass 2
     float m = -INFINITY;
     const bool dbg2 = dbg && warp == 2;
+    static_assert(kPartCols == 32, "one 32-column tensor-memory load per thread and tile");
     // ---- pass 1: row maximum ----
     for (int i = 0; i < T; ++i) {
       const int st = i & 1;
       ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
       if (dbg2 && lane == 0) a.dbg[70 + i] = clock64();
       ptx::tc_fence_after();
-      const int key0 = i * kKT + half * 64;
-#pragma unroll 1
-      for (int g = 0; g < 2; ++g) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + half * 64 + g * 32, v);
-        ptx::tmem_ld_wait();
-        if (key0 + g * 32 + 32 <= a.S) {
+      const int key0 = i * kKT + part * kPartCols;
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + part * kPartCols, v);
+      ptx::tmem_ld_wait();
+      if (key0 + 32 <= a.S) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
-        } else {
+        for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+      } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (key0 + g * 32 + c < a.S) m = fmaxf(m, __uint_as_float(v[c]));
-        }
+        for (int c = 0; c < 32; ++c)
+          if (key0 + c < a.S) m = fmaxf(m, __uint_as_float(v[c]));
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[st]);
     }
-    red[half * 128 + r] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(red[r], red[128 + r]);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    red[part * 128 + r] = m;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSmWarps) : "memory");
+#pragma unroll
+    for (int pp = 0; pp < kParts; ++pp) m = fmaxf(m, red[pp * 128 + r]);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSmWarps) : "memory");
     // ---- pass 2: probabilities -> registers -> shared memory (swizzled K-major), row sum ----
     float l = 0.f;
     const float ms = m * a.scale_log2e;
-    const uint32_t prow = ptx::smem_u32(sP) + half * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;   // this row inside sub-tile `half`
+    // this row inside the 64-key sub-tile (part >> 1); the thread's 32 columns are the 64-byte half (part & 1) of the 128-byte row
+    const uint32_t prow = ptx::smem_u32(sP) + (part >> 1) * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;
     for (int j = 0; j < T; ++j) {
       const int i = T + j, st = i & 1;
       ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
       if (dbg2 && lane == 0) a.dbg[70 + i] = clock64();
       ptx::tc_fence_after();
-      const int key0 = j * kKT + half * 64;
-      uint32_t ph[32], pl[32];   // packed half2: element 2c, 2c+1 of this warp's 64 columns
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      const int key0 = j * kKT + part * kPartCols;
+      uint32_t ph[16], pl[16];   // packed half2: element 2c, 2c+1 of this thread's 32 columns
+      {
         uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + half * 64 + g * 32, v);
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + st * 128 + part * kPartCols, v);
         ptx::tmem_ld_wait();
-        const bool full = key0 + g * 32 + 32 <= a.S;
+        auto convert = [&](auto masked) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float p0, p1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[2 * c]), a.scale_log2e, -ms)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[2 * c + 1]), a.scale_log2e, -ms)));
-          if (!full) {
-            if (key0 + g * 32 + 2 * c >= a.S) p0 = 0.f;
-            if (key0 + g * 32 + 2 * c + 1 >= a.S) p1 = 0.f;
+          for (int c = 0; c < 16; ++c) {
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[2 * c]), a.scale_log2e, -ms)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[2 * c + 1]), a.scale_log2e, -ms)));
+            if (decltype(masked)::value) {   // only the tile that straddles the end of the sequence pays for the masking
+              if (key0 + 2 * c >= a.S) p0 = 0.f;
+              if (key0 + 2 * c + 1 >= a.S) p1 = 0.f;
+            }
+            l += p0 + p1;
+            const __half2 h2 = __floats2half2_rn(p0, p1);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(p0 - back.x, p1 - back.y);
+            ph[c] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[c] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          l += p0 + p1;
-          const __half2 h2 = __floats2half2_rn(p0, p1);
-          const float2 back = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn(p0 - back.x, p1 - back.y);
-          ph[g * 16 + c] = *reinterpret_cast<const uint32_t*>(&h2);
-          pl[g * 16 + c] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
+        };
+        if (key0 + 32 <= a.S) convert(std::false_type{});
+        else convert(std::true_type{});
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -298,8 +309,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       if (j > 0) ptx::mbar_wait(p_empty, (j - 1) & 1);             // P V of the previous tile has consumed the buffer
       if (dbg2 && lane == 0) a.dbg[100 + j] = clock64();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                                // 8 chunks of 16 bytes = this warp's 64 columns
-        const int chunk = c ^ (r & 7);
+      for (int c = 0; c < 4; ++c) {                                // 4 chunks of 16 bytes = this thread's 32 columns
+        const int chunk = ((part & 1) * 4 + c) ^ (r & 7);
         ptx::st_shared_v4(prow + chunk * 16, ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
         if (NPASS == 3) ptx::st_shared_v4(prow + 2 * kTileBytes + chunk * 16, pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
       }
@@ -307,32 +318,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    red[half * 128 + r] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l = red[r] + red[128 + r];
-    // ---- output: O / l -> split pair, concatenated heads; this warp stores columns half*32 .. +31 ----
+    red = reinterpret_cast<float*>(sQ);                 // every Q K^T has completed (all s_full phases were waited for): Q is dead
+    red[part * 128 + r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSmWarps) : "memory");
+    l = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < kParts; ++pp) l += red[pp * 128 + r];
+    // ---- output: O / l -> split pair, concatenated heads; this warp stores columns part*16 .. +15 ----
     ptx::mbar_wait(o_full, 0);
     if (dbg2 && lane == 0) a.dbg[110] = clock64();
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     const int q = q0 + r;
     {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_o + lane_addr + half * 32, v);
+      constexpr int kOutCols = kD / kParts;   // 16
+      static_assert(kOutCols == 16, "one 16-column tensor-memory load per thread");
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(tmem_o + lane_addr + part * kOutCols, v);
       ptx::tmem_ld_wait();
       if (q < a.S) {
-        uint32_t oh[16], ol[16];
+        uint32_t oh[8], ol[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 8; ++c) {
           const float x0 = __uint_as_float(v[2 * c]) * inv, x1 = __uint_as_float(v[2 * c + 1]) * inv;
           const __half2 h2 = __floats2half2_rn(x0, x1);
           const float2 back = __half22float2(h2);
           const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
           oh[c] = *reinterpret_cast<const uint32_t*>(&h2), ol[c] = *reinterpret_cast<const uint32_t*>(&l2);
         }
-        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + half * 32;
+        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + part * kOutCols;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
           if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
         }

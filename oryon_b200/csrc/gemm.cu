@@ -828,7 +828,30 @@ static bool use_pair_kernel(const oryon_handle* h, const Problem& p) {
   return tasks >= h->sm_count / 2;
 }
 
-int launch(oryon_handle* h, const Problem& p, cudaStream_t st) {
+// Experiment switch (tools/gemm_precision_sweep.py): ORYON_GEMM_P1_SHAPES="N:K,N:K,..." demotes the GEMMs of
+// these (N, K) classes from three products to one; a leading '!' demotes every class EXCEPT the listed ones.  Read per call.
+static bool demoted_by_env(const Problem& p) {
+  const char* e = getenv("ORYON_GEMM_P1_SHAPES");
+  if (!e || !*e) return false;
+  const bool invert = *e == '!';
+  if (invert) ++e;
+  bool listed = false;
+  while (*e) {
+    char* end = nullptr;
+    const long n = strtol(e, &end, 10);
+    if (end == e || *end != ':') break;
+    e = end + 1;
+    const long k = strtol(e, &end, 10);
+    if (end == e) break;
+    if (n == p.N && k == p.K) listed = true;
+    e = *end == ',' ? end + 1 : end;
+  }
+  return listed != invert;
+}
+
+int launch(oryon_handle* h, const Problem& p_in, cudaStream_t st) {
+  Problem p = p_in;
+  if (p.precision == 3 && demoted_by_env(p)) p.precision = 1;
   ORYON_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.nb0 > 0 && p.nb1 > 0, "gemm: empty problem (M=%d N=%d K=%d)", p.M, p.N, p.K);
   ORYON_REQUIRE(p.precision == 1 || p.precision == 3, "gemm: precision must be 1 or 3");
   const int tn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
