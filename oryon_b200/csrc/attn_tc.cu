@@ -11,9 +11,13 @@
 //                              is enough: softmax is invariant to the subtracted constant).  Pass 2: S is recomputed
 //                              (K = 64: cheap), p = exp2((s - max) * scale * log2 e), the row sum accumulates in a
 //                              register, p is held in registers as packed fp16 split pairs until the P V MMA of the
-//                              previous tile has released the buffer, then written straight into the 128B-swizzled
-//                              K-major shared-memory layout the P V MMA consumes.  Finally O / sum is stored as a
-//                              split pair into the concatenated-heads activation.
+//                              previous tile has released the buffer, then written with tcgen05.st into TENSOR MEMORY:
+//                              P is the A operand of the P V MMA and tcgen05.mma takes A from tensor memory (the ".ts"
+//                              form: lane = query row, two fp16 per 32-bit column).  Round 1 wrote P into a swizzled
+//                              shared-memory tile instead: 16 st.shared.v4 per thread and tile plus a fence.proxy.async,
+//                              ~1 000-1 500 of the ~2 900 cycles a key tile took (profiles/r02_attn_tc.md); the 64 KB that
+//                              buffer occupied now hold a third K stage.  Finally O / sum is stored as a split pair into
+//                              the concatenated-heads activation.
 // Two passes instead of an online rescale keep a max-subtracted softmax and need no TMEM read-modify-write of O; the
 // extra Q K^T costs little tensor work on a kernel that is bound by the exp / convert work of the softmax warps.
 // Operands are fp16 split pairs; NPASS = 3 evaluates hi*hi + lo*hi + hi*lo (see gemm.cuh).
@@ -40,22 +44,24 @@ constexpr int kPartCols = 128 / kParts;         // 32 key columns per thread and
 constexpr int kThreads = 64 + 32 * kSmWarps;    // TMA, MMA, softmax warps
 constexpr int kTileBytes = 128 * 64 * 2;   // one [128][64] fp16 tile, 128-byte rows, SWIZZLE_128B
 
+constexpr int kNK = 3;       // K stages (ring); S accumulators and V stages stay double buffered
+
 template <int NPASS>
 struct Cfg {
   static constexpr int kHalves = NPASS == 3 ? 2 : 1;
   static constexpr int kQBytes = kHalves * kTileBytes;
   static constexpr int kKStage = kHalves * kTileBytes;
   static constexpr int kVBytes = kHalves * kTileBytes;        // [64 d][128 keys] = two [64][64] sub-tiles per half
-  static constexpr int kPBytes = kHalves * 2 * kTileBytes;    // [128 q][128 keys] = two [128][64] sub-tiles per half
   static constexpr int kOffK = kQBytes;
-  static constexpr int kOffV = kOffK + 2 * kKStage;
-  static constexpr int kOffP = kOffV + 2 * kVBytes;
-  static constexpr int kOffBar = kOffP + kPBytes;
-  // the cross-warp max / sum exchanges ([kParts][128] floats) borrow operand tiles that are dead at that moment: the P buffer
-  // before pass 2 writes it, the Q tile after the last Q K^T has completed (there is no room for a separate 2 KB)
-  static constexpr int kTotal = 1024 + kOffBar + 256;
+  static constexpr int kOffV = kOffK + kNK * kKStage;
+  static constexpr int kOffBar = kOffV + 2 * kVBytes;
+  static constexpr int kOffRed = kOffBar + 256;               // [kParts][128] floats: cross-warp max / sum exchange
+  static constexpr int kTotal = 1024 + kOffRed + kParts * 128 * 4;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
+
+// tensor-memory columns (512 allocated): S accumulators [0,256), O [256,320), P hi [320,384), P lo [384,448)
+constexpr uint32_t kTmemO = 256, kTmemPhi = 320, kTmemPlo = 384;
 
 struct Args {
   int S, heads, T;            // T = key tiles
@@ -87,19 +93,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
   uint8_t* sQ = smem;
   uint8_t* sK = smem + L::kOffK;
   uint8_t* sV = smem + L::kOffV;
-  uint8_t* sP = smem + L::kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* s_empty = bars + 11;  // [2]
-  uint64_t* p_full = bars + 13;
-  uint64_t* p_empty = bars + 14;
-  uint64_t* o_full = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* k_full = bars + 1;             // [kNK]
+  uint64_t* k_empty = k_full + kNK;        // [kNK]
+  uint64_t* v_full = k_empty + kNK;        // [2]
+  uint64_t* v_empty = v_full + 2;          // [2]
+  uint64_t* s_full = v_empty + 2;          // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  static_assert(8 * (4 + 2 * kNK + 8) + 4 <= 256, "barrier block");
 
   const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQ, head = blockIdx.y, seq = blockIdx.z;
@@ -112,8 +118,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     ptx::prefetch_tensormap(&tm_qkv_hi);
     if (!VMN) ptx::prefetch_tensormap(&tm_vt_hi);
     ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kNK; ++i) ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1), ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], kSmWarps);
+      ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], kSmWarps);
       ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
     }
     ptx::mbar_init(p_full, kSmWarps), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
@@ -127,7 +134,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = tmem_base + kTmemO;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -136,8 +143,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       tma_load_2d_(sQ, &tm_qkv_hi, q_full, head * kD, row0 + q0);
       if (NPASS == 3) tma_load_2d_(sQ + kTileBytes, &tm_qkv_lo, q_full, head * kD, row0 + q0);
       for (int i = 0; i < 2 * T; ++i) {
-        const int st = i & 1, kt = i % T;
-        ptx::mbar_wait(&k_empty[st], ((i >> 1) & 1) ^ 1);
+        const int st = i % kNK, kt = i % T;
+        ptx::mbar_wait(&k_empty[st], ((i / kNK) & 1) ^ 1);
         const bool need_lo = NPASS == 3 && i >= T;   // pass 1 (row maximum) multiplies the hi halves only
         ptx::mbar_arrive_expect_tx(&k_full[st], need_lo ? L::kKStage : kTileBytes);
         tma_load_2d_(sK + st * L::kKStage, &tm_qkv_hi, &k_full[st], width + head * kD, row0 + kt * kKT);
@@ -169,24 +176,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       STAMP(60 + j);
       ptx::tc_fence_after();
       {
-        // warp-uniform descriptors, one elected lane issues (see gemm.cu): the 8 * NPASS MMAs go out back to back
-        const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV + (j & 1) * L::kVBytes);
+        // warp-uniform descriptors, one elected lane issues (see gemm.cu): the 8 * NPASS MMAs go out back to back.
+        // A = P from tensor memory: [128 query lanes][128 keys] fp16, two keys per 32-bit column -> 8 columns per 16-key MMA.
+        const uint32_t v_addr = ptx::smem_u32(sV + (j & 1) * L::kVBytes);
         const bool leader = ptx::elect_one();
 #pragma unroll
         for (int pass = 0; pass < NPASS; ++pass) {
           // pass 0: P_hi V_hi   pass 1: P_lo V_hi   pass 2: P_hi V_lo
-          const uint64_t dp0 = ptx::make_smem_desc_kmajor(p_addr + (pass == 1 ? 2 * kTileBytes : 0), 128);
+          const uint32_t tp = tmem_base + (pass == 1 ? kTmemPlo : kTmemPhi);
           const uint32_t va = v_addr + (pass == 2 ? kTileBytes : 0);
           const uint64_t dv0 = VMN ? ptx::make_smem_desc_mnmajor_sw128(va, 0, 1024) : ptx::make_smem_desc_kmajor(va, 128);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              // descriptor start-address field is (bytes >> 4).  P: 16 KB per 64-key sub-tile, 32 bytes per 16 keys.
               // 16 keys per MMA: MN-major V advances two 8-key groups (2 KB); K-major V^T 32 bytes inside the swizzled row.
-              const uint64_t dp = dp0 + (sub * (kTileBytes >> 4) + 2 * k);
               const uint64_t dv = dv0 + (VMN ? (sub * 4 + k) * (2048 >> 4) : sub * (kTileBytes >> 5) + 2 * k);
-              if (leader) ptx::umma_f16(tmem_o, dp, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
+              if (leader) ptx::umma_f16_ts(tmem_o, tp + (sub * 4 + k) * 8, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
             }
         }
         if (leader) {
@@ -199,14 +205,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     ptx::mbar_wait(q_full, 0);
     STAMP(1);
     for (int i = 0; i < 2 * T; ++i) {
-      const int st = i & 1;
-      ptx::mbar_wait(&k_full[st], (i >> 1) & 1);
+      const int st = i & 1, ks = i % kNK;   // S accumulator / K stage
+      ptx::mbar_wait(&k_full[ks], (i / kNK) & 1);
       STAMP(10 + i);
       ptx::mbar_wait(&s_empty[st], ((i >> 1) & 1) ^ 1);
       STAMP(30 + i);
       ptx::tc_fence_after();
       {
-        const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + st * L::kKStage);
+        const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + ks * L::kKStage);
         const int npass = i < T ? 1 : NPASS;   // pass 1 only needs an approximate maximum
         const bool leader = ptx::elect_one();
 #pragma unroll
@@ -219,7 +225,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
             if (leader) ptx::umma_f16(tmem_base + st * 128, dq0 + 2 * k, dk0 + 2 * k, kIdescS, (pass | k) != 0 ? 1u : 0u);
         }
         if (leader) {
-          ptx::umma_commit(&k_empty[st]);
+          ptx::umma_commit(&k_empty[ks]);
           ptx::umma_commit(&s_full[st]);
         }
       }
@@ -234,7 +240,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     const int part = (warp - 2) >> 2;                   // which kPartCols key columns of every tile this warp owns
     const int r = quarter * 32 + lane;                  // row of the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    float* red = reinterpret_cast<float*>(sP);          // [kParts][128]: the P buffer is not written before pass 2
+    float* red = reinterpret_cast<float*>(smem + L::kOffRed);   // [kParts][128]
     float m = -INFINITY;
     const bool dbg2 = dbg && warp == 2;
     static_assert(kPartCols == 32, "one 32-column tensor-memory load per thread and tile");
@@ -268,8 +274,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
     // ---- pass 2: probabilities -> registers -> shared memory (swizzled K-major), row sum ----
     float l = 0.f;
     const float ms = m * a.scale_log2e;
-    // this row inside the 64-key sub-tile (part >> 1); the thread's 32 columns are the 64-byte half (part & 1) of the 128-byte row
-    const uint32_t prow = ptx::smem_u32(sP) + (part >> 1) * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;
+    // P in tensor memory: this thread's row is lane r; its 32 keys are the 16 packed columns [part * 16, +16) of the tile
+    const uint32_t tp_hi = tmem_base + lane_addr + kTmemPhi + part * (kPartCols / 2);
+    const uint32_t tp_lo = tmem_base + lane_addr + kTmemPlo + part * (kPartCols / 2);
     for (int j = 0; j < T; ++j) {
       const int i = T + j, st = i & 1;
       ptx::mbar_wait(&s_full[st], (i >> 1) & 1);
@@ -308,17 +315,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
       if (dbg2 && lane == 0) a.dbg[90 + j] = clock64();
       if (j > 0) ptx::mbar_wait(p_empty, (j - 1) & 1);             // P V of the previous tile has consumed the buffer
       if (dbg2 && lane == 0) a.dbg[100 + j] = clock64();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {                                // 4 chunks of 16 bytes = this thread's 32 columns
-        const int chunk = ((part & 1) * 4 + c) ^ (r & 7);
-        ptx::st_shared_v4(prow + chunk * 16, ph[4 * c], ph[4 * c + 1], ph[4 * c + 2], ph[4 * c + 3]);
-        if (NPASS == 3) ptx::st_shared_v4(prow + 2 * kTileBytes + chunk * 16, pl[4 * c], pl[4 * c + 1], pl[4 * c + 2], pl[4 * c + 3]);
-      }
-      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x32b_x16(tp_hi, ph);
+      if (NPASS == 3) ptx::tmem_st_32x32b_x16(tp_lo, pl);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    red = reinterpret_cast<float*>(sQ);                 // every Q K^T has completed (all s_full phases were waited for): Q is dead
     red[part * 128 + r] = l;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSmWarps) : "memory");
     l = 0.f;
