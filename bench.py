@@ -210,7 +210,7 @@ def prompt_lists(n=FULL["distinct_prompts"]):
     return [[f"object{i}"] + [f"a photo number {t} of a object{i}." for t in range(80)] for i in range(n)]
 
 
-def build_full_path(local, precision, mask_mode, pipelined=True):
+def build_full_path(local, precision, mask_mode, pipelined=True, pairs_per_pass=16):
     from oryon_b200 import synth
     from oryon_b200.models.tokenizer import SimpleTokenizer
     from oryon_b200.net import Oryon
@@ -218,7 +218,8 @@ def build_full_path(local, precision, mask_mode, pipelined=True):
     from oryon_b200.utils.pointdsc.init import PointDSCSolver
     cfg = synth.POINTDSC_DEFAULT_CFG
     dev = f"cuda:{local}"
-    model = Oryon(None, dev, state_dict=full_path_weights(), precision=precision, tokenizer=SimpleTokenizer(BPE_SYNTH))
+    model = Oryon(None, dev, state_dict=full_path_weights(), precision=precision, tokenizer=SimpleTokenizer(BPE_SYNTH),
+                  max_pairs_per_pass=pairs_per_pass)
     solver = PointDSCSolver(synth.pointdsc_state_dict(300), in_dim=cfg["in_dim"], num_layers=cfg["num_layers"],
                             num_channels=cfg["num_channels"], num_iterations=cfg["num_iterations"], ratio=cfg["ratio"],
                             sigma_d=cfg["sigma_d"], k=cfg["k"], nms_radius=cfg["inlier_threshold"], device=dev)
@@ -550,6 +551,7 @@ def main():
     ap.add_argument("--matcher-only", action="store_true", help="only the config-2 matcher region (used by tools/ncu_traffic.py)")
     ap.add_argument("--matcher-seconds", type=float, default=2.0, help="minimum length of the config-2 roofline region")
     ap.add_argument("--eager-baseline", action="store_true", help="also time the reference's matcher formulation as PyTorch eager ops on the GPU")
+    ap.add_argument("--pairs-per-pass", type=int, default=16, help="pairs per network pass inside a step (activation arena size; A/B)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: run each batch's post-network tail before the next network pass instead of under it")
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's CPU set (A/B for the e2e scaling)")
     args = ap.parse_args()
@@ -595,7 +597,7 @@ def main():
 
     # ---- the full path -----------------------------------------------------------------------------------------------
     B, K, W = FULL["B"], args.steps, args.warmup
-    pipe, model = build_full_path(local, args.precision, args.mask, pipelined=not args.no_pipeline)
+    pipe, model = build_full_path(local, args.precision, args.mask, pipelined=not args.no_pipeline, pairs_per_pass=args.pairs_per_pass)
     prompts = prompt_lists()
     hb = host_batches(FULL["distinct_batches"], B)
     db = [to_device_batch(b, dev) for b in hb]

@@ -247,6 +247,95 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(LnArgs a) {
   }
 }
 
+// Narrow rows (C = 128 * NQ, NQ <= 2: the swin / fusion stages, 300 000 rows of 512 bytes per launch): one row per warp iteration
+// keeps a single 16-byte load per lane in flight and the kernel ran at 23 % of the HBM peak (ncu launch list, round 2: ~208 us for
+// 314 MB).  Here a warp works on ROWS rows at a time -- all their loads (and the row_map lookups) are issued before the first
+// reduction -- with the same per-row arithmetic and summation order as layernorm_vec_kernel (bit-identical results).
+template <int NQ, int ROWS>
+__global__ void __launch_bounds__(256) layernorm_vec_rows_kernel(LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  for (int r0 = wid * ROWS; r0 < a.rows; r0 += nw * ROWS) {
+    int src[ROWS];
+    float4 v[ROWS][NQ];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int r = r0 + j;
+      src[j] = r < a.rows ? (a.row_map ? a.row_map[r] : r) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      if (src[j] >= 0) {
+        const float4* xr = reinterpret_cast<const float4*>(a.x + (int64_t)src[j] * a.ldx) + lane;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) v[j][i] = xr[32 * i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) v[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 g[NQ], b[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      g[i] = __ldg(reinterpret_cast<const float4*>(a.gamma) + 32 * i + lane);
+      b[i] = __ldg(reinterpret_cast<const float4*>(a.beta) + 32 * i + lane);
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int r = r0 + j;
+      if (r >= a.rows) break;
+      if (src[j] >= 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) s += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+        const float mean = warp_sum(s) / (float)a.C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          const float d0 = v[j][i].x - mean, d1 = v[j][i].y - mean, d2 = v[j][i].z - mean, d3 = v[j][i].w - mean;
+          q = fmaf(d0, d0, q), q = fmaf(d1, d1, q), q = fmaf(d2, d2, q), q = fmaf(d3, d3, q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)a.C + a.eps);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          v[j][i].x = (v[j][i].x - mean) * rstd * g[i].x + b[i].x, v[j][i].y = (v[j][i].y - mean) * rstd * g[i].y + b[i].y;
+          v[j][i].z = (v[j][i].z - mean) * rstd * g[i].z + b[i].z, v[j][i].w = (v[j][i].w - mean) * rstd * g[i].w + b[i].w;
+        }
+      }
+      if (a.out32) {
+        float4* o = reinterpret_cast<float4*>(a.out32 + (int64_t)r * a.ld32) + lane;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) o[32 * i] = v[j][i];
+      }
+      if (a.out_hi) {
+        const int64_t o = (int64_t)r * a.ldh;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+          __half h0, h1, h2, h3, l0, l1, l2, l3;
+          split_half(v[j][i].x, h0, l0), split_half(v[j][i].y, h1, l1), split_half(v[j][i].z, h2, l2), split_half(v[j][i].w, h3, l3);
+          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned*>(&ha), pk.y = *reinterpret_cast<const unsigned*>(&hb);
+          *reinterpret_cast<uint2*>(a.out_hi + o + 128 * i + 4 * lane) = pk;
+          if (a.out_lo) {
+            const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+            pk.x = *reinterpret_cast<const unsigned*>(&la), pk.y = *reinterpret_cast<const unsigned*>(&lb);
+            *reinterpret_cast<uint2*>(a.out_lo + o + 128 * i + 4 * lane) = pk;
+          }
+        }
+        for (int c = a.C + lane; c < a.ldh; c += 32) {
+          float x = 0.f;
+          if (c < a.C + a.cat_C && src[j] >= 0) x = a.cat[(int64_t)src[j] * a.cat_C + (c - a.C)];
+          __half hh, ll;
+          split_half(x, hh, ll);
+          a.out_hi[o + c] = hh;
+          if (a.out_lo) a.out_lo[o + c] = ll;
+        }
+      }
+    }
+  }
+}
+
 int layernorm(oryon_handle* h, const LnArgs& a, cudaStream_t st) {
   ORYON_REQUIRE(a.C > 0 && a.C % 32 == 0 && a.C <= 1024, "layernorm: C=%d unsupported", a.C);
   if (a.rows <= 0) return ORYON_OK;
@@ -256,7 +345,10 @@ int layernorm(oryon_handle* h, const LnArgs& a, cudaStream_t st) {
                    (!a.out32 || (al(a.out32, 16) && a.ld32 % 4 == 0)) &&
                    (!a.out_hi || (al(a.out_hi, 8) && a.ldh % 4 == 0 && (!a.out_lo || al(a.out_lo, 8))));
   const int grid = std::min((a.rows + 7) / 8, h->sm_count * 16);
-  if (vec) layernorm_vec_kernel<<<grid, 256, 0, st>>>(a);
+  static const bool rows_v1 = getenv("ORYON_LN_V1") != nullptr;   // A/B switch: one row per warp iteration for every width
+  if (vec && !rows_v1 && a.C == 128) layernorm_vec_rows_kernel<1, 4><<<std::min((a.rows + 31) / 32, h->sm_count * 16), 256, 0, st>>>(a);
+  else if (vec && !rows_v1 && a.C == 256) layernorm_vec_rows_kernel<2, 4><<<std::min((a.rows + 31) / 32, h->sm_count * 16), 256, 0, st>>>(a);
+  else if (vec) layernorm_vec_kernel<<<grid, 256, 0, st>>>(a);
   else layernorm_kernel<<<grid, 256, 0, st>>>(a);
   h->span_end(st);
   ORYON_CUDA_CHECK(cudaGetLastError());
