@@ -210,7 +210,7 @@ def prompt_lists(n=FULL["distinct_prompts"]):
     return [[f"object{i}"] + [f"a photo number {t} of a object{i}." for t in range(80)] for i in range(n)]
 
 
-def build_full_path(local, precision, mask_mode, pipelined=True, pairs_per_pass=16):
+def build_full_path(local, precision, mask_mode, pipelined=True, pairs_per_pass=32):
     from oryon_b200 import synth
     from oryon_b200.models.tokenizer import SimpleTokenizer
     from oryon_b200.net import Oryon
@@ -551,7 +551,8 @@ def main():
     ap.add_argument("--matcher-only", action="store_true", help="only the config-2 matcher region (used by tools/ncu_traffic.py)")
     ap.add_argument("--matcher-seconds", type=float, default=2.0, help="minimum length of the config-2 roofline region")
     ap.add_argument("--eager-baseline", action="store_true", help="also time the reference's matcher formulation as PyTorch eager ops on the GPU")
-    ap.add_argument("--pairs-per-pass", type=int, default=16, help="pairs per network pass inside a step (activation arena size; A/B)")
+    ap.add_argument("--pairs-per-pass", type=int, default=32, help="pairs per network pass inside a step (activation arena size; 16 = round 1's "
+                                                                     "setting: twice the launches, 2 %% slower, profiles/r02_bench_run_h_*.json)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: run each batch's post-network tail before the next network pass instead of under it")
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's CPU set (A/B for the e2e scaling)")
     args = ap.parse_args()

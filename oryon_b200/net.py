@@ -28,7 +28,7 @@ class Oryon:
     with ``model.`` stripped."""
 
     def __init__(self, args=None, device="cuda", *, state_dict: Optional[Dict[str, Tensor]] = None, vis_layers: int = 24,
-                 txt_layers: int = 12, precision: int = 3, max_pairs_per_pass: int = 16, tokenizer=None):
+                 txt_layers: int = 12, precision: int = 3, max_pairs_per_pass: int = 32, tokenizer=None):
         self.args = getattr(args, "model", args)
         dev = torch.device(device)
         if dev.type != "cuda":
