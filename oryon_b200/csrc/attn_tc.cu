@@ -66,6 +66,7 @@ constexpr uint32_t kTmemO = 256, kTmemPhi = 320, kTmemPlo = 384;
 struct Args {
   int S, heads, T;            // T = key tiles
   float scale_log2e;          // head_dim^-0.5 * log2(e)
+  float tau;                  // online kernel: the reference maximum of a row is renewed when a tile exceeds it by more than 2^tau
   __half* out_hi;
   __half* out_lo;
   int64_t ldh;
@@ -368,6 +369,312 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// attn_online_kernel: the same attention in ONE pass over the key tiles (online softmax with a lazily renewed reference maximum).
+// ------------------------------------------------------------------------------------------------
+// The two-pass kernel above spends ~3 k of its ~19 k cycles per CTA on pass 1 (row maxima from an extra hi*hi Q K^T per tile, an
+// extra read-out of S, an extra K stream through L2).  Here every key tile is visited once: S = Q K^T in three products, the four
+// column warps of a row exchange the tile's row maximum through shared memory (one named barrier per lane quarter and tile), and
+// p = 2^(s*c - m_ref) is taken against a REFERENCE maximum m_ref that is only renewed when a tile exceeds it by more than tau (2^8):
+// softmax is invariant to the subtracted constant, p <= 2^tau keeps the fp16 split pair exact to 2^-21, and the accumulated O and
+// row sum need a correction (x 2^(m_old - m_new)) only on a renewal -- after the first tile that is rare.  The correction of O
+// (tcgen05.ld, multiply, tcgen05.st of this warp's 32 rows x 16 columns) happens between the wait for the previous P V product and
+// the store of the new P, when no MMA touches O.  Same operands, same three-product P V through tensor memory as above.
+constexpr int kRedFloats = 3 * kParts * 128;   // two alternating row-maximum exchange buffers + one for the row sums
+
+template <int NPASS>
+struct CfgOnline {
+  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kQBytes = kHalves * kTileBytes;
+  static constexpr int kKStage = kHalves * kTileBytes;
+  static constexpr int kVBytes = kHalves * kTileBytes;
+  static constexpr int kOffK = kQBytes;
+  static constexpr int kOffV = kOffK + kNK * kKStage;
+  static constexpr int kOffBar = kOffV + 2 * kVBytes;
+  static constexpr int kOffRed = kOffBar + 256;
+  static constexpr int kTotal = 1024 + kOffRed + kRedFloats * 4;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+template <int NPASS, bool VMN>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_online_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_constant__ CUtensorMap tm_qkv_lo,
+                   const __grid_constant__ CUtensorMap tm_vt_hi, const __grid_constant__ CUtensorMap tm_vt_lo, Args a, int width) {
+  using L = CfgOnline<NPASS>;
+  constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0);
+  constexpr uint32_t kIdescO = ptx::make_idesc_f16(128, 64, 0, VMN ? 1 : 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + L::kOffK;
+  uint8_t* sV = smem + L::kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;             // [kNK]
+  uint64_t* k_empty = k_full + kNK;        // [kNK]
+  uint64_t* v_full = k_empty + kNK;        // [2]
+  uint64_t* v_empty = v_full + 2;          // [2]
+  uint64_t* s_full = v_empty + 2;          // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQ, head = blockIdx.y, seq = blockIdx.z;
+  const int T = a.T;
+  const bool dbg = a.dbg && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 5;
+  if (dbg && threadIdx.x == 0) a.dbg[0] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_qkv_hi);
+    if (!VMN) ptx::prefetch_tensormap(&tm_vt_hi);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kNK; ++i) ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&s_empty[i], kSmWarps);
+      ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
+    }
+    ptx::mbar_init(p_full, kSmWarps), ptx::mbar_init(p_empty, 1), ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + kTmemO;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int row0 = seq * a.S;
+      ptx::mbar_arrive_expect_tx(q_full, L::kQBytes);
+      tma_load_2d_(sQ, &tm_qkv_hi, q_full, head * kD, row0 + q0);
+      if (NPASS == 3) tma_load_2d_(sQ + kTileBytes, &tm_qkv_lo, q_full, head * kD, row0 + q0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % kNK, vs = j & 1;
+        ptx::mbar_wait(&k_empty[st], ((j / kNK) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[st], L::kKStage);
+        tma_load_2d_(sK + st * L::kKStage, &tm_qkv_hi, &k_full[st], width + head * kD, row0 + j * kKT);
+        if (NPASS == 3) tma_load_2d_(sK + st * L::kKStage + kTileBytes, &tm_qkv_lo, &k_full[st], width + head * kD, row0 + j * kKT);
+        ptx::mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[vs], L::kVBytes);
+        uint8_t* dst = sV + vs * L::kVBytes;
+        if (VMN) {   // rows past S belong to the next sequence (or are zero-filled past the end): their probabilities are exactly 0
+          tma_load_2d_(dst, &tm_qkv_hi, &v_full[vs], 2 * width + head * kD, row0 + j * kKT);
+          if (NPASS == 3) tma_load_2d_(dst + kTileBytes, &tm_qkv_lo, &v_full[vs], 2 * width + head * kD, row0 + j * kKT);
+        } else {
+          const int vrow = (seq * a.heads + head) * kD;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            tma_load_2d_(dst + sub * (kTileBytes / 2), &tm_vt_hi, &v_full[vs], j * kKT + sub * 64, vrow);
+            if (NPASS == 3) tma_load_2d_(dst + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, &v_full[vs], j * kKT + sub * 64, vrow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    auto issue_pv = [&](int j) {
+      ptx::mbar_wait(p_full, j & 1);
+      if (dbg && lane == 0) a.dbg[50 + j] = clock64();
+      ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      {
+        const uint32_t v_addr = ptx::smem_u32(sV + (j & 1) * L::kVBytes);
+        const bool leader = ptx::elect_one();
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+          // pass 0: P_hi V_hi   pass 1: P_lo V_hi   pass 2: P_hi V_lo
+          const uint32_t tp = tmem_base + (pass == 1 ? kTmemPlo : kTmemPhi);
+          const uint32_t va = v_addr + (pass == 2 ? kTileBytes : 0);
+          const uint64_t dv0 = VMN ? ptx::make_smem_desc_mnmajor_sw128(va, 0, 1024) : ptx::make_smem_desc_kmajor(va, 128);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dv = dv0 + (VMN ? (sub * 4 + k) * (2048 >> 4) : sub * (kTileBytes >> 5) + 2 * k);
+              if (leader) ptx::umma_f16_ts(tmem_o, tp + (sub * 4 + k) * 8, dv, kIdescO, (j | pass | sub | k) != 0 ? 1u : 0u);
+            }
+        }
+        if (leader) {
+          ptx::umma_commit(&v_empty[j & 1]);
+          ptx::umma_commit(p_empty);
+        }
+      }
+      __syncwarp();
+    };
+    ptx::mbar_wait(q_full, 0);
+    if (dbg && lane == 0) a.dbg[1] = clock64();
+    for (int j = 0; j < T; ++j) {
+      const int sb = j & 1, ks = j % kNK;
+      ptx::mbar_wait(&k_full[ks], (j / kNK) & 1);
+      if (dbg && lane == 0) a.dbg[10 + j] = clock64();
+      ptx::mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      {
+        const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + ks * L::kKStage);
+        const bool leader = ptx::elect_one();
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+          const uint64_t dq0 = ptx::make_smem_desc_kmajor(q_addr + (pass == 1 ? kTileBytes : 0), 128);
+          const uint64_t dk0 = ptx::make_smem_desc_kmajor(k_addr + (pass == 2 ? kTileBytes : 0), 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (leader) ptx::umma_f16(tmem_base + sb * 128, dq0 + 2 * k, dk0 + 2 * k, kIdescS, (pass | k) != 0 ? 1u : 0u);
+        }
+        if (leader) {
+          ptx::umma_commit(&k_empty[ks]);
+          ptx::umma_commit(&s_full[sb]);
+        }
+      }
+      __syncwarp();
+      if (j > 0) issue_pv(j - 1);
+    }
+    issue_pv(T - 1);
+    if (ptx::elect_one()) ptx::umma_commit(o_full);
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
+    const int part = (warp - 2) >> 2;                   // which 32 key columns of every tile this warp owns
+    const int r = quarter * 32 + lane;                  // row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float* red = reinterpret_cast<float*>(smem + L::kOffRed);   // [3][kParts][128]
+    const uint32_t tp_hi = tmem_base + lane_addr + kTmemPhi + part * (kPartCols / 2);
+    const uint32_t tp_lo = tmem_base + lane_addr + kTmemPlo + part * (kPartCols / 2);
+    const uint32_t to = tmem_o + lane_addr + part * (kD / kParts);
+    const bool dbg2 = dbg && warp == 2;
+    float m_ref = -INFINITY;   // reference maximum of this row, in the scaled log2 domain (s * scale_log2e)
+    float l = 0.f;             // this thread's share of the row sum, relative to m_ref
+    for (int j = 0; j < T; ++j) {
+      const int sb = j & 1;
+      ptx::mbar_wait(&s_full[sb], (j >> 1) & 1);
+      if (dbg2 && lane == 0) a.dbg[70 + j] = clock64();
+      ptx::tc_fence_after();
+      const int key0 = j * kKT + part * kPartCols;
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * 128 + part * kPartCols, v);
+      ptx::tmem_ld_wait();
+      const bool full = key0 + 32 <= a.S;
+      float m_loc = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) m_loc = fmaxf(m_loc, __uint_as_float(v[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (key0 + c < a.S) m_loc = fmaxf(m_loc, __uint_as_float(v[c]));
+      }
+      // the tile's row maximum over the four column warps of this lane quarter (alternating buffers: no second barrier)
+      float* ex = red + (j & 1) * (kParts * 128);
+      ex[part * 128 + r] = m_loc;
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory");
+      float m_tile = ex[r];
+#pragma unroll
+      for (int pp = 1; pp < kParts; ++pp) m_tile = fmaxf(m_tile, ex[pp * 128 + r]);
+      const float mt = m_tile * a.scale_log2e;
+      const bool grow = mt > m_ref + a.tau;     // always on the first tile (m_ref = -inf); the same decision in all four warps of the row
+      float alpha = 1.f;
+      if (grow) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(m_ref - mt));   // 0 on the first tile
+        m_ref = mt;
+        l *= alpha;
+      }
+      uint32_t ph[16], pl[16];   // packed half2: element 2c, 2c+1 of this thread's 32 columns
+      {
+        auto convert = [&](auto masked) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[2 * c]), a.scale_log2e, -m_ref)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[2 * c + 1]), a.scale_log2e, -m_ref)));
+            if (decltype(masked)::value) {
+              if (key0 + 2 * c >= a.S) p0 = 0.f;
+              if (key0 + 2 * c + 1 >= a.S) p1 = 0.f;
+            }
+            l += p0 + p1;
+            const __half2 h2 = __floats2half2_rn(p0, p1);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(p0 - back.x, p1 - back.y);
+            ph[c] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[c] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+        };
+        if (full) convert(std::false_type{});
+        else convert(std::true_type{});
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);              // S buffer drained: the Q K^T after next may overwrite it
+      if (dbg2 && lane == 0) a.dbg[90 + j] = clock64();
+      if (j > 0) {
+        ptx::mbar_wait(p_empty, (j - 1) & 1);                      // P V of the previous tile is complete: P is free, O is at rest
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {                       // renew the reference of O: this warp's 32 rows x 16 columns
+          uint32_t o[16];
+          ptx::tmem_ld_32x32b_x16(to, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          ptx::tmem_st_32x32b_x16(to, o);
+        }
+      }
+      if (dbg2 && lane == 0) a.dbg[100 + j] = clock64();
+      ptx::tmem_st_32x32b_x16(tp_hi, ph);
+      if (NPASS == 3) ptx::tmem_st_32x32b_x16(tp_lo, pl);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+    float* exl = red + 2 * (kParts * 128);
+    exl[part * 128 + r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSmWarps) : "memory");
+    l = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < kParts; ++pp) l += exl[pp * 128 + r];
+    // ---- output: O / l -> split pair, concatenated heads; this warp stores columns part*16 .. +15 ----
+    ptx::mbar_wait(o_full, 0);
+    if (dbg2 && lane == 0) a.dbg[110] = clock64();
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    const int q = q0 + r;
+    {
+      constexpr int kOutCols = kD / kParts;   // 16
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(to, v);
+      ptx::tmem_ld_wait();
+      if (q < a.S) {
+        uint32_t oh[8], ol[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float x0 = __uint_as_float(v[2 * c]) * inv, x1 = __uint_as_float(v[2 * c + 1]) * inv;
+          const __half2 h2 = __floats2half2_rn(x0, x1);
+          const float2 back = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(x0 - back.x, x1 - back.y);
+          oh[c] = *reinterpret_cast<const uint32_t*>(&h2), ol[c] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + part * kOutCols;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
+          if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) a.dbg[111] = clock64();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int make_map_2d(oryon_handle* h, CUtensorMap* tm, const __half* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
@@ -412,6 +719,9 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
   Args a;
   a.S = S, a.heads = heads, a.T = T;
   a.scale_log2e = (1.f / sqrtf((float)kD)) * 1.4426950408889634f;
+  static const bool two_pass = getenv("ORYON_ATTN_TWOPASS") != nullptr;     // A/B switch: the two-pass kernel
+  const char* tau_env = getenv("ORYON_ATTN_TAU");                           // test switch: 0 renews the reference maximum at every increase
+  a.tau = tau_env ? (float)atof(tau_env) : 8.f;
   a.out_hi = out_hi, a.out_lo = precision == 3 ? out_lo : nullptr, a.ldh = ldh;
   a.dbg = nullptr;
   static const bool want_dbg = getenv("ORYON_ATTN_DEBUG") != nullptr;
@@ -429,8 +739,13 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
     kernel<<<grid, kThreads, smem, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
     return ORYON_OK;
   };
-  if (precision == 3) rc = vmn ? run(attn_tc_kernel<3, true>, Cfg<3>::kTotal) : run(attn_tc_kernel<3, false>, Cfg<3>::kTotal);
-  else rc = vmn ? run(attn_tc_kernel<1, true>, Cfg<1>::kTotal) : run(attn_tc_kernel<1, false>, Cfg<1>::kTotal);
+  if (two_pass) {
+    if (precision == 3) rc = vmn ? run(attn_tc_kernel<3, true>, Cfg<3>::kTotal) : run(attn_tc_kernel<3, false>, Cfg<3>::kTotal);
+    else rc = vmn ? run(attn_tc_kernel<1, true>, Cfg<1>::kTotal) : run(attn_tc_kernel<1, false>, Cfg<1>::kTotal);
+  } else {
+    if (precision == 3) rc = vmn ? run(attn_online_kernel<3, true>, CfgOnline<3>::kTotal) : run(attn_online_kernel<3, false>, CfgOnline<3>::kTotal);
+    else rc = vmn ? run(attn_online_kernel<1, true>, CfgOnline<1>::kTotal) : run(attn_online_kernel<1, false>, CfgOnline<1>::kTotal);
+  }
   h->span_end(st);
   if (rc) return rc;
   ORYON_CUDA_CHECK(cudaGetLastError());
