@@ -585,26 +585,38 @@ attn_online_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_c
       }
       uint32_t ph[16], pl[16];   // packed half2: element 2c, 2c+1 of this thread's 32 columns
       {
+        // packed fp32x2 arithmetic (FFMA2 / FADD2): one instruction for the scale-and-shift of two scores, one for the two row-sum
+        // additions, one for the two fp16 residuals -- 9 instead of 12 issue slots per pair of scores on warps that are issue-bound
+        const uint64_t c2 = ptx::pack_f32x2(a.scale_log2e, a.scale_log2e), nm2 = ptx::pack_f32x2(-m_ref, -m_ref);
+        const uint64_t neg1 = ptx::pack_f32x2(-1.f, -1.f);
+        uint64_t l2 = ptx::pack_f32x2(l, 0.f);
         auto convert = [&](auto masked) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            float p0, p1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(v[2 * c]), a.scale_log2e, -m_ref)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(v[2 * c + 1]), a.scale_log2e, -m_ref)));
+            float x0, x1, p0, p1;
+            ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), c2, nm2), x0, x1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
             if (decltype(masked)::value) {
               if (key0 + 2 * c >= a.S) p0 = 0.f;
               if (key0 + 2 * c + 1 >= a.S) p1 = 0.f;
             }
-            l += p0 + p1;
+            const uint64_t pp = ptx::pack_f32x2(p0, p1);
+            l2 = ptx::add_f32x2(l2, pp);
             const __half2 h2 = __floats2half2_rn(p0, p1);
             const float2 back = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(p0 - back.x, p1 - back.y);
+            float r0, r1;
+            ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(back.x, back.y), neg1, pp), r0, r1);   // p - fp16(p), exact
+            const __half2 lo2 = __floats2half2_rn(r0, r1);
             ph[c] = *reinterpret_cast<const uint32_t*>(&h2);
-            pl[c] = *reinterpret_cast<const uint32_t*>(&l2);
+            pl[c] = *reinterpret_cast<const uint32_t*>(&lo2);
           }
         };
         if (full) convert(std::false_type{});
         else convert(std::true_type{});
+        float la, lb;
+        ptx::unpack_f32x2(l2, la, lb);
+        l = la + lb;
       }
       ptx::tc_fence_before();
       __syncwarp();
