@@ -698,6 +698,301 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// gemm_tc4_kernel<NPASS>: two CTA pairs per cluster (cluster of 4) that share their A tiles through TMA multicast.
+//
+// Measured on B200 (profiles/r02_gemm_pair.md, r02_gemm_l2_bound.md): the pair kernel moves 128 KB of operands from L2 per
+// 256 x 256 x 64 unit and streams 8.4-8.7 TB/s on EVERY CLIP shape -- at three products AND at one product, where the tensor pipe is
+// only half busy.  The GEMMs are bound by L2 -> SM operand traffic, not by the tensor pipe.  Here the two pairs of a cluster work
+// on the same 256-row block and two neighbouring 256-column tiles: every A box (128 rows x 64 K of one half) is fetched from L2 ONCE
+// and written by TMA multicast into the CTA of each pair that needs it (rank h of pair 0 fetches the hi halves, rank h of pair 1
+// the lo halves, for the 128 rows both own), W boxes stay private: 96 KB per 256 x 256 x 64 unit instead of 128.
+// Barriers: every CTA owns a `full[stage]` for the 64 KB that land in ITS shared memory (own W boxes, one own and one multicast A
+// box); warp 1 of the non-leader CTA forwards its completions to the leader's `peer_full[stage]`; the MMA warp of a leader waits
+// for both.  A stage slot is written by this CTA and by its partner in the other pair, so `empty[stage]` counts the commits of BOTH
+// leaders (tcgen05.commit multicast to all four CTAs).  Accumulators, epilogue and `t_full` / `t_empty` are per pair as in
+// gemm_tc2_kernel.
+template <int NPASS>
+struct Cfg4 {
+  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kABlock = kTileM * kKB * 2;
+  static constexpr int kABytes = kABlock * kHalves;
+  static constexpr int kWBytes = kABlock * kHalves;
+  static constexpr int kStage = kABytes + kWBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStage;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kBarBytes = (8 * (3 * kStages + 4) + 16 + 15) / 16 * 16;
+  static constexpr int kEpiBytes = 8 * kEpiWarpFloats * 4;
+  static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes + kEpiBytes;
+  static_assert(kStages >= 2, "pipeline depth");
+};
+
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, uint16_t cta_mask, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int NPASS>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc4_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const __grid_constant__ KArgs args) {
+  using L = Cfg4<NPASS>;
+  constexpr int STAGES = L::kStages;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kTileM, kPairTN, /*fp16*/ 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kStage * STAGES);
+  uint64_t* full = bars;                    // [STAGES] the 64 KB that land in THIS CTA's stage
+  uint64_t* peer_full = bars + STAGES;      // [STAGES] leader only: the peer CTA's stage has landed (forwarded)
+  uint64_t* empty = bars + 2 * STAGES;      // [STAGES] both pairs' MMAs of the stage have retired (2 commits)
+  uint64_t* t_full = empty + STAGES;        // [2] pair-wide multicast
+  uint64_t* t_empty = t_full + 2;           // [2] leader's copy, 16 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();     // 0..3
+  const uint32_t pair = rank >> 1, half = rank & 1; // pair 0 = ranks {0,1}, pair 1 = ranks {2,3}; even rank = leader of its pair
+  const uint32_t leader_rank = rank & ~1u;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a_hi);
+    ptx::prefetch_tensormap(&tm_w_hi);
+    if (NPASS == 3) ptx::prefetch_tensormap(&tm_a_lo), ptx::prefetch_tensormap(&tm_w_lo);
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&peer_full[s], 1), ptx::mbar_init(&empty[s], 2);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 16);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // a task = one 256-row block x TWO neighbouring 256-column tiles (one per pair)
+  const int tiles_n2 = args.tiles_n >> 1;
+  const int tasks_per_mat = args.tiles_m * tiles_n2;
+  const int total_tasks = tasks_per_mat * args.nb0 * args.nb1;
+  const int cluster_id = blockIdx.x >> 2, n_clusters = gridDim.x >> 2;
+  const uint16_t a_mask = static_cast<uint16_t>((1u << half) | (1u << (half + 2)));   // the two CTAs that own these 128 rows of A
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = cluster_id; t < total_tasks; t += n_clusters) {
+        const int nt = 2 * (t % tiles_n2) + (int)pair, mt = (t / tiles_n2) % args.tiles_m;
+        const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
+        const int arow = mt * kCtaRows + (int)half * kTileM, wrow = nt * kPairTN + (int)half * kTileM;
+        for (int kb = 0; kb < args.KB; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], L::kStage);
+          uint8_t* sa = smem + stage * L::kStage;
+          uint8_t* sw = sa + L::kABytes;
+          // A: pair 0 fetches the hi box of these rows, pair 1 the lo box, each for both CTAs that own the rows
+          if (NPASS == 3) {
+            if (pair == 0) tma_load_4d_mc(sa, &tm_a_hi, &full[stage], a_mask, kb * kKB, arow, b0, b1);
+            else tma_load_4d_mc(sa + L::kABlock, &tm_a_lo, &full[stage], a_mask, kb * kKB, arow, b0, b1);
+          } else {
+            // one half only: split the box by rows (64 each)
+            tma_load_4d_mc(sa + pair * (L::kABlock / 2), &tm_a_hi, &full[stage], a_mask, kb * kKB, arow + (int)pair * (kTileM / 2), b0, b1);
+          }
+          tma_load_4d(sw, &tm_w_hi, &full[stage], kb * kKB, wrow, b0, b1);
+          if (NPASS == 3) tma_load_4d(sw + L::kABlock, &tm_w_lo, &full[stage], kb * kKB, wrow, b0, b1);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (half == 0) {
+      // ============================ MMA issuer (leader of the pair) ============================
+      uint32_t stage = 0, phase = 0, tile_iter = 0;
+      const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
+      for (int t = cluster_id; t < total_tasks; t += n_clusters) {
+        const uint32_t buf = tile_iter & 1;
+        ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kPairTN;
+        for (int kb = 0; kb < args.KB; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::mbar_wait(&peer_full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
+          const uint32_t sw = sa + L::kABytes;
+          const uint64_t da_hi = ptx::make_smem_desc_kmajor(sa, 128), da_lo = ptx::make_smem_desc_kmajor(sa + (NPASS == 3 ? L::kABlock : 0), 128);
+          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS == 3 ? L::kABlock : 0), 128);
+          const bool leader = ptx::elect_one();
+#pragma unroll
+          for (int pass = 0; pass < NPASS; ++pass) {
+            const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
+#pragma unroll
+            for (int k = 0; k < kKB / 16; ++k)
+              if (leader) ptx::umma_f16_pair(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);
+          }
+          if (leader) {
+            ptx::umma_commit_pair(&empty[stage], 0xF);                           // all four CTAs: the slots are written across pairs
+            if (kb == args.KB - 1) ptx::umma_commit_pair(&t_full[buf], pair_mask);
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        ++tile_iter;
+      }
+    } else {
+      // ============================ forwarder (non-leader CTA): my stage has landed -> the leader's peer_full ============================
+      if (lane == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int t = cluster_id; t < total_tasks; t += n_clusters) {
+          for (int kb = 0; kb < args.KB; ++kb) {
+            ptx::mbar_wait(&full[stage], phase);
+            mbar_arrive_cluster_release(ptx::mapa_shared(ptx::smem_u32(&peer_full[stage]), leader_rank));
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue (as gemm_tc2_kernel) ============================
+    const int ew = warp - 2, chalf = ew >> 2, quarter = warp & 3;
+    const int row_in_tile = (int)half * kTileM + quarter * 32 + lane;
+    const Epilogue& ep = args.ep;
+    const uint32_t stage_f = ptx::smem_u32(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats * 4;
+    const uint32_t bias_s = stage_f + 32 * kEpiLd * 4;
+    const uint32_t t_empty_leader0 = ptx::mapa_shared(ptx::smem_u32(&t_empty[0]), leader_rank), t_empty_leader1 = ptx::mapa_shared(ptx::smem_u32(&t_empty[1]), leader_rank);
+    const int sub_row = lane >> 2, cg = lane & 3;
+    uint32_t tile_iter = 0;
+    for (int t = cluster_id; t < total_tasks; t += n_clusters) {
+      const int nt = 2 * (t % tiles_n2) + (int)pair, mt = (t / tiles_n2) % args.tiles_m;
+      const int bb = t / tasks_per_mat, b0 = bb % args.nb0, b1 = bb / args.nb0;
+      const uint32_t buf = tile_iter & 1;
+      const int row = mt * kCtaRows + row_in_tile;
+      int drow = row < args.M ? row : -1;
+      if (drow >= 0 && ep.row_map) drow = ep.row_map[row];
+      const int64_t base32 = (int64_t)b1 * ep.out_b1 + (int64_t)b0 * ep.out_b0;
+      const int64_t baseh = (int64_t)b1 * ep.outh_b1 + (int64_t)b0 * ep.outh_b0;
+      const int ncol0 = nt * kPairTN + chalf * (kPairTN / 2);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kPairTN / 64; ++j) {
+        const int col = ncol0 + j * 32 + lane;
+        ptx::st_shared_f1(bias_s + (j * 32 + lane) * 4, (ep.bias && col < args.N) ? __ldg(ep.bias + col) : 0.f);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kPairTN + chalf * (kPairTN / 2);
+#pragma unroll 1
+      for (int g = 0; g < kPairTN / 32; ++g) {
+        const int col0 = ncol0 + g * 16;
+        if (col0 >= args.N) break;
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(taddr + g * 16, v);
+        ptx::tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bq = ptx::ld_shared_f4(bias_s + (g * 16 + 4 * i) * 4);
+          x[4 * i] = fmaf(__uint_as_float(v[4 * i]), ep.alpha, bq.x), x[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), ep.alpha, bq.y);
+          x[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), ep.alpha, bq.z), x[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), ep.alpha, bq.w);
+        }
+        switch (ep.act) {
+          case ACT_QUICKGELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.f + expf(-1.702f * x[i]));
+            break;
+          case ACT_GELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = 0.5f * x[i] * (1.f + erff(x[i] * 0.70710678118654752440f));
+            break;
+          case ACT_RELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+            break;
+          default: break;
+        }
+        if (ep.transpose_h) {
+          if (drow >= 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < args.N) {
+                __half hh, ll;
+                split_half(x[i], hh, ll);
+                const int64_t o = baseh + (int64_t)(col0 + i) * ep.ldh + drow;
+                ep.out_hi[o] = hh;
+                if (ep.out_lo) ep.out_lo[o] = ll;
+              }
+          }
+          if (!ep.out32) continue;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ptx::st_shared_f4(stage_f + (lane * kEpiLd + 4 * i) * 4, make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]));
+        __syncwarp();
+        const int col = col0 + cg * 4;
+        const bool vec_ok = col + 3 < args.N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = k * 8 + sub_row;
+          const int dr = __shfl_sync(0xffffffffu, drow, r);
+          if (dr < 0 || col >= args.N) continue;
+          float4 y = ptx::ld_shared_f4(stage_f + (r * kEpiLd + cg * 4) * 4);
+          const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
+          if (vec_ok && (ep.ld32 & 3) == 0) {
+            if (ep.residual) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(ep.residual + o32));
+              y.x += q.x, y.y += q.y, y.z += q.z, y.w += q.w;
+            }
+            if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o32) = y;
+          } else {
+            float* yy = reinterpret_cast<float*>(&y);
+            for (int i = 0; i < 4; ++i)
+              if (col + i < args.N) {
+                if (ep.residual) yy[i] += ep.residual[o32 + i];
+                if (ep.out32) ep.out32[o32 + i] = yy[i];
+              }
+          }
+          if (ep.out_hi && !ep.transpose_h) {
+            const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
+            __half hh[4], ll[4];
+            split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
+            if (vec_ok && (ep.ldh & 3) == 0) {
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
+            } else {
+              for (int i = 0; i < 4; ++i)
+                if (col + i < args.N) {
+                  ep.out_hi[oh + i] = hh[i];
+                  if (ep.out_lo) ep.out_lo[oh + i] = ll[i];
+                }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(buf ? t_empty_leader1 : t_empty_leader0);
+      ++tile_iter;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 static int make_map(oryon_handle* h, CUtensorMap* tm, const __half* base, int kpad, int rows, int nb0, int nb1, int64_t ld,
                     int64_t sb0, int64_t sb1, int box_rows) {
   const cuuint64_t gdim[4] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
@@ -819,6 +1114,73 @@ static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
   return ORYON_OK;
 }
 
+template <int NPASS>
+static int launch_quad(oryon_handle* h, const Problem& p, cudaStream_t st) {
+  using L = Cfg4<NPASS>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
+  const int kpad = round_up(p.K, kKB);
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  int rc;
+  const int a_box = NPASS == 3 ? kTileM : kTileM / 2;   // one product: the two pairs fetch 64 rows each of the single half
+  if ((rc = make_map(h, &tw_hi, p.W.hi, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
+  tw_lo = tw_hi;
+  if (NPASS == 3 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
+  if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, a_box))) return rc;
+  ta_lo = ta_hi;
+  if (NPASS == 3 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, a_box))) return rc;
+  KArgs ka;
+  ka.K = p.K;
+  ka.M = p.M, ka.N = p.N, ka.KB = kpad / kKB;
+  ka.nb0 = p.nb0, ka.nb1 = p.nb1;
+  ka.tiles_m = (p.M + kCtaRows - 1) / kCtaRows;
+  ka.tiles_n = p.N / kPairTN;   // even (N % 512 == 0)
+  ka.ep = p.ep;
+  const long long tasks = (long long)ka.tiles_m * (ka.tiles_n / 2) * p.nb0 * p.nb1;
+  auto kern = gemm_tc4_kernel<NPASS>;
+  static int max_clusters = 0;  // per instantiation
+  if (max_clusters == 0) {
+    ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * (h->sm_count / 4)), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = L::kTotal;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 4, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+    cfg.attrs = &at, cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = h->sm_count / 4, cudaGetLastError();
+    max_clusters = n;
+    if (getenv("ORYON_GEMM_LOG")) fprintf(stderr, "gemm(quad): %d clusters of 4 CTAs can be co-resident on %d SMs\n", n, h->sm_count);
+  }
+  const int clusters = (int)std::min<long long>(max_clusters, tasks);
+  static const bool log_shapes = getenv("ORYON_GEMM_LOG") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (log_shapes) cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventRecord(e0, st);
+  h->span_begin(KID_GEMM, st);
+  kern<<<4 * clusters, kThreads, L::kTotal, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, ka);   // __cluster_dims__(4,1,1)
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  if (log_shapes) {
+    cudaEventRecord(e1, st), cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "gemm(quad) M=%d N=%d K=%d batch=%dx%d npass=%d tasks=%lld clusters=%d  %.1f us  %.0f TFLOP/s (algorithmic)\n", p.M, p.N, p.K,
+            p.nb0, p.nb1, NPASS, tasks, clusters, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  }
+  ++h->gemm_launches;
+  h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  return ORYON_OK;
+}
+
+// Two pairs sharing A through multicast: N must split into pairs of 256-column tiles and there must be work for every cluster.
+static bool use_quad_kernel(const oryon_handle* h, const Problem& p) {
+  const char* e = getenv("ORYON_GEMM_QUAD");   // A/B switch, read per call: "0" = CTA pairs only
+  if (e && e[0] == '0') return false;
+  if (p.gather || h->sm_count < 4 || p.N % (2 * kPairTN) != 0) return false;
+  const long long tasks = (long long)((p.M + kCtaRows - 1) / kCtaRows) * (p.N / (2 * kPairTN)) * p.nb0 * p.nb1;
+  return tasks >= h->sm_count / 4;
+}
+
 // The pair kernel pays off where a 256 x 256 tile is full and there are enough tiles to fill the 74 pairs.
 static bool use_pair_kernel(const oryon_handle* h, const Problem& p) {
   static const bool off = getenv("ORYON_GEMM_1CTA") != nullptr;   // A/B switch
@@ -884,6 +1246,8 @@ int launch(oryon_handle* h, const Problem& p_in, cudaStream_t st) {
                 "gemm: operand strides must be multiples of 8 elements (16 bytes)");
   ORYON_REQUIRE(p.A.ld >= round_up(p.K, kKB) || p.A.ld >= p.K, "gemm: A row stride shorter than K");
   ORYON_REQUIRE(!p.ep.row_map || (p.nb0 == 1 && p.nb1 == 1), "gemm: row_map needs an unbatched problem");
+  static const bool pairs_off = getenv("ORYON_GEMM_1CTA") != nullptr;
+  if (!pairs_off && use_quad_kernel(h, p)) return p.precision == 3 ? launch_quad<3>(h, p, st) : launch_quad<1>(h, p, st);
   if (use_pair_kernel(h, p)) return p.precision == 3 ? launch_pair<3>(h, p, st) : launch_pair<1>(h, p, st);
   if (p.precision == 3) {
     switch (tn) {

@@ -43,13 +43,16 @@ CASES = [
     (9216, 16, 1152, 1, "relu", True, False),     # TN = 32, N = 16
     (100, 33, 48, 2, "gelu", True, True),         # everything ragged
     (1, 7, 5, 1, "none", True, False),
-    # large, N % 256 == 0: these run on the CTA-pair kernel (gemm_tc2_kernel, tcgen05 cta_group::2; >= 74 tiles of 256 x 256)
+    # large, N % 512 == 0: two CTA pairs per cluster sharing A through TMA multicast (gemm_tc4_kernel; >= 37 units of 256 x 512);
+    # N % 256 == 0 otherwise: CTA pairs (gemm_tc2_kernel, tcgen05 cta_group::2; >= 74 tiles of 256 x 256)
     (4800, 1024, 1024, 1, "none", True, True),        # out-projection shape, ragged last row block (4800 = 18.75 x 256)
     (4737, 3072, 1024, 1, "none", True, False),       # QKV shape, one row in the last block
     (5000, 4096, 1024, 1, "quickgelu", True, False),  # MLP up-projection
     (4864, 1024, 4096, 1, "none", True, True),        # MLP down-projection, deep K
     (2500, 512, 320, 2, "gelu", True, True),          # batched, K not a multiple of 64
-    (19000, 256, 64, 1, "relu", False, False),        # one k-block, one column tile
+    (19000, 256, 64, 1, "relu", False, False),        # one k-block, one column tile (pair kernel)
+    (10000, 768, 256, 1, "none", True, True),         # N % 512 != 0: pair kernel, three column tiles
+    (9700, 512, 128, 1, "gelu", True, False),         # exactly one unit per row block (quad kernel), ragged rows
 ]
 
 
