@@ -1174,8 +1174,12 @@ static int launch_quad(oryon_handle* h, const Problem& p, cudaStream_t st) {
 
 // Two pairs sharing A through multicast: N must split into pairs of 256-column tiles and there must be work for every cluster.
 static bool use_quad_kernel(const oryon_handle* h, const Problem& p) {
-  const char* e = getenv("ORYON_GEMM_QUAD");   // A/B switch, read per call: "0" = CTA pairs only
-  if (e && e[0] == '0') return false;
+  // Opt-in (ORYON_GEMM_QUAD=1, read per call).  Measured on B200 (profiles/r02_gemm_quad.md): bit-identical outputs, 25 % less L2
+  // traffic per flop -- and SLOWER than the pair kernel: only 33 clusters of 4 CTAs are co-resident on the 148 SMs (132 SMs, the GPCs
+  // do not divide into fours), 438 units on 33 clusters are 13.3 waves, and the per-stage round trip did not get shorter (3.6 vs 3.4 us):
+  // QKV 0.249 vs 0.213 ms.  The pair kernel is bound by that round trip with three 64 KB stages in flight, not by L2 bandwidth.
+  const char* e = getenv("ORYON_GEMM_QUAD");
+  if (!e || e[0] != '1') return false;
   if (p.gather || h->sm_count < 4 || p.N % (2 * kPairTN) != 0) return false;
   const long long tasks = (long long)((p.M + kCtaRows - 1) / kCtaRows) * (p.N / (2 * kPairTN)) * p.nb0 * p.nb1;
   return tasks >= h->sm_count / 4;

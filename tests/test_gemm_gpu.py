@@ -43,8 +43,8 @@ CASES = [
     (9216, 16, 1152, 1, "relu", True, False),     # TN = 32, N = 16
     (100, 33, 48, 2, "gelu", True, True),         # everything ragged
     (1, 7, 5, 1, "none", True, False),
-    # large, N % 512 == 0: two CTA pairs per cluster sharing A through TMA multicast (gemm_tc4_kernel; >= 37 units of 256 x 512);
-    # N % 256 == 0 otherwise: CTA pairs (gemm_tc2_kernel, tcgen05 cta_group::2; >= 74 tiles of 256 x 256)
+    # large, N % 256 == 0: CTA pairs (gemm_tc2_kernel, tcgen05 cta_group::2; >= 74 tiles of 256 x 256); with ORYON_GEMM_QUAD=1 and
+    # N % 512 == 0: two CTA pairs per cluster sharing A through TMA multicast (gemm_tc4_kernel), see test_quad_kernel_... below
     (4800, 1024, 1024, 1, "none", True, True),        # out-projection shape, ragged last row block (4800 = 18.75 x 256)
     (4737, 3072, 1024, 1, "none", True, False),       # QKV shape, one row in the last block
     (5000, 4096, 1024, 1, "quickgelu", True, False),  # MLP up-projection
@@ -84,3 +84,12 @@ def test_gemm_large_values_saturate_not_nan():
     W = torch.full((128, 64), 300.0)
     out = ops.linear(A.cuda(), W.cuda()).cpu()
     assert torch.isfinite(out).all() and torch.allclose(out, torch.full_like(out, 300.0 * 300.0 * 64), rtol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,K,batch,act,use_bias,use_res", [c for c in CASES if c[1] % 512 == 0 and c[0] >= 4000])
+def test_quad_kernel_matches_float64(M, N, K, batch, act, use_bias, use_res, monkeypatch):
+    """gemm_tc4_kernel (two CTA pairs per cluster, A through TMA multicast; opt-in because it is slower on the B200's 148 SMs) is
+    held to the same tolerance as the default kernels."""
+    monkeypatch.setenv("ORYON_GEMM_QUAD", "1")
+    test_gemm_matches_float64(M, N, K, batch, act, use_bias, use_res, 3)
+    test_gemm_matches_float64(M, N, K, batch, act, use_bias, use_res, 1)
