@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "net_kernels.cuh"
+#include "ptx_sm100.cuh"
 
 namespace oryon {
 namespace net {
@@ -531,12 +532,16 @@ __global__ void __launch_bounds__(160) window_attention_kernel(AttnArgs a, int s
   }
   auto score = [&](int j) {
     const float4* kp = reinterpret_cast<const float4*>(Ks + j * kWinD);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    // packed FFMA2 (fma.rn.f32x2): the same four IEEE accumulation chains, half the issue slots
+    uint64_t s01 = ptx::pack_f32x2(0.f, 0.f), s23 = s01;
 #pragma unroll
     for (int i = 0; i < kWinD / 4; ++i) {
       const float4 k = kp[i];
-      s0 = fmaf(q[4 * i], k.x, s0), s1 = fmaf(q[4 * i + 1], k.y, s1), s2 = fmaf(q[4 * i + 2], k.z, s2), s3 = fmaf(q[4 * i + 3], k.w, s3);
+      s01 = ptx::fma_f32x2(ptx::pack_f32x2(q[4 * i], q[4 * i + 1]), ptx::pack_f32x2(k.x, k.y), s01);
+      s23 = ptx::fma_f32x2(ptx::pack_f32x2(q[4 * i + 2], q[4 * i + 3]), ptx::pack_f32x2(k.z, k.w), s23);
     }
+    float s0, s1, s2, s3;
+    ptx::unpack_f32x2(s01, s0, s1), ptx::unpack_f32x2(s23, s2, s3);
     float sc = (s0 + s1) + (s2 + s3);
     if (bias) sc += __ldg(bias + j * bstride);
     if (mask) sc += __ldg(mask + j * S);
@@ -548,21 +553,25 @@ __global__ void __launch_bounds__(160) window_attention_kernel(AttnArgs a, int s
     if (KEEP) my[j] = sc;
     m = fmaxf(m, sc);
   }
-  float acc[kWinD];
+  uint64_t acc2[kWinD / 2];
 #pragma unroll
-  for (int i = 0; i < kWinD; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kWinD / 2; ++i) acc2[i] = ptx::pack_f32x2(0.f, 0.f);
   float l = 0.f;
   for (int j = 0; j < S; ++j) {
     const float p = expf((KEEP ? my[j] : score(j)) - m);
     l += p;
+    const uint64_t pp = ptx::pack_f32x2(p, p);
     const float4* vp = reinterpret_cast<const float4*>(Vs + j * kWinD);
 #pragma unroll
     for (int i = 0; i < kWinD / 4; ++i) {
       const float4 v = vp[i];
-      acc[4 * i] = fmaf(p, v.x, acc[4 * i]), acc[4 * i + 1] = fmaf(p, v.y, acc[4 * i + 1]);
-      acc[4 * i + 2] = fmaf(p, v.z, acc[4 * i + 2]), acc[4 * i + 3] = fmaf(p, v.w, acc[4 * i + 3]);
+      acc2[2 * i] = ptx::fma_f32x2(pp, ptx::pack_f32x2(v.x, v.y), acc2[2 * i]);
+      acc2[2 * i + 1] = ptx::fma_f32x2(pp, ptx::pack_f32x2(v.z, v.w), acc2[2 * i + 1]);
     }
   }
+  float acc[kWinD];
+#pragma unroll
+  for (int i = 0; i < kWinD / 2; ++i) ptx::unpack_f32x2(acc2[i], acc[2 * i], acc[2 * i + 1]);
   if (ok) {
     const int64_t o = ((int64_t)seq * S + qi) * a.ldh + hh * kWinD;
 #pragma unroll

@@ -25,6 +25,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace oryon {
 namespace pdsc {
@@ -34,6 +35,12 @@ constexpr int TP = 16;       // points per tile
 constexpr int TPS = 20;      // padded shared-memory row stride (floats; keeps float4 alignment, spreads banks)
 constexpr int NT = 256;      // threads per CTA of the per-point kernels
 constexpr int kMaxK = 64;    // neighbourhood size limit (release: 40)
+
+// (a0, a1) += (x0, x1) * (y, y) as ONE packed FFMA2 (sm_100 fma.rn.f32x2): the same two IEEE fused multiply-adds, half the issue
+// slots.  The per-point layers and the attention of the NonLocal blocks are issue-bound fp32 FMA loops.
+__device__ __forceinline__ void fma2(float& a0, float& a1, float x0, float x1, float y) {
+  ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(x0, x1), ptx::pack_f32x2(y, y), ptx::pack_f32x2(a0, a1)), a0, a1);
+}
 
 struct LayerW {
   const float *pcn_w, *pcn_b;            // [C][C], [C]      PointCN conv + BN folded
@@ -77,15 +84,13 @@ __device__ __forceinline__ void point_linear(const float* __restrict__ Wt, const
     const float w = __ldg(Wt + ci * COUT + co);
     if constexpr (PPT == 2) {
       const float2 x = *reinterpret_cast<const float2*>(xs + ci * TPS);
-      acc[0] = fmaf(w, x.x, acc[0]), acc[1] = fmaf(w, x.y, acc[1]);
+      fma2(acc[0], acc[1], x.x, x.y, w);
     } else {
 #pragma unroll
       for (int v = 0; v < PPT / 4; ++v) {
         const float4 x = *reinterpret_cast<const float4*>(xs + ci * TPS + v * 4);
-        acc[v * 4 + 0] = fmaf(w, x.x, acc[v * 4 + 0]);
-        acc[v * 4 + 1] = fmaf(w, x.y, acc[v * 4 + 1]);
-        acc[v * 4 + 2] = fmaf(w, x.z, acc[v * 4 + 2]);
-        acc[v * 4 + 3] = fmaf(w, x.w, acc[v * 4 + 3]);
+        fma2(acc[v * 4 + 0], acc[v * 4 + 1], x.x, x.y, w);
+        fma2(acc[v * 4 + 2], acc[v * 4 + 3], x.z, x.w, w);
       }
     }
   }
@@ -275,10 +280,8 @@ __global__ void __launch_bounds__(NT) pdsc_layer_kernel(Args a, int layer, int l
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         const float4 q = *reinterpret_cast<const float4*>(Qs + c * TPS + v * 4);
-        acc[v * 4 + 0] = fmaf(q.x, kv, acc[v * 4 + 0]);
-        acc[v * 4 + 1] = fmaf(q.y, kv, acc[v * 4 + 1]);
-        acc[v * 4 + 2] = fmaf(q.z, kv, acc[v * 4 + 2]);
-        acc[v * 4 + 3] = fmaf(q.w, kv, acc[v * 4 + 3]);
+        fma2(acc[v * 4 + 0], acc[v * 4 + 1], q.x, q.y, kv);
+        fma2(acc[v * 4 + 2], acc[v * 4 + 3], q.z, q.w, kv);
       }
     }
 #pragma unroll
@@ -319,8 +322,8 @@ __global__ void __launch_bounds__(NT) pdsc_layer_kernel(Args a, int layer, int l
       const float v = __ldg(Vg + (size_t)i * C + c);
       const float4 w0 = *reinterpret_cast<const float4*>(St + i * TPS + og * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(St + i * TPS + og * 8 + 4);
-      acc[0] = fmaf(w0.x, v, acc[0]), acc[1] = fmaf(w0.y, v, acc[1]), acc[2] = fmaf(w0.z, v, acc[2]), acc[3] = fmaf(w0.w, v, acc[3]);
-      acc[4] = fmaf(w1.x, v, acc[4]), acc[5] = fmaf(w1.y, v, acc[5]), acc[6] = fmaf(w1.z, v, acc[6]), acc[7] = fmaf(w1.w, v, acc[7]);
+      fma2(acc[0], acc[1], w0.x, w0.y, v), fma2(acc[2], acc[3], w0.z, w0.w, v);
+      fma2(acc[4], acc[5], w1.x, w1.y, v), fma2(acc[6], acc[7], w1.z, w1.w, v);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) bufA[c * TPS + og * 8 + j] = __fdiv_rn(acc[j], row_inv[og * 8 + j]);
