@@ -379,7 +379,7 @@ struct TcSmem {
   static constexpr int kABytes = kABlock * NUM_KB * kRowBlocks;
   static constexpr int kQStage = kTileN * kRowBytes;            // one k-block of a query tile
   static constexpr int kQBytes = kQStage * STAGES;
-  static constexpr int kBarBytes = 8 * (2 * STAGES + 2 + 4) + 16;
+  static constexpr int kBarBytes = 8 * (2 * STAGES + 2 + 8) + 16;
   static constexpr int kTotal = 1024 /*align slack*/ + kABytes + kQBytes + kBarBytes;
 };
 
@@ -407,9 +407,15 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* a_full = bars + 2 * STAGES;  // A tile landed
   uint64_t* a_empty = a_full + 1;        // all MMAs of the task retired: A may be overwritten
-  uint64_t* t_full = a_empty + 1;        // [2] accumulator ready
-  uint64_t* t_empty = t_full + 2;        // [2] accumulator drained
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  // Accumulators are handed over per (buffer, ROW BLOCK): 4 units of 128 lanes x 128 columns.  Round 1 handed over whole buffers (both
+  // row blocks at once): at D = 128 the MMAs of a buffer take 1 024 cycles, its read-out by the 8 epilogue warps plus the two barrier
+  // hops ~2 000, and the MMA warp waited for a drained buffer 3/4 of the time (profiles/r02_match_pair_vs_1cta.md).  With the
+  // row blocks issued one after the other (all k-blocks of row block 0, then of row block 1) and their own full / empty barriers,
+  // a unit is filled in 512 cycles and has the 1 536 cycles of the other three units' MMAs to be read out.
+  uint64_t* t_full = a_empty + 1;        // [2 buffers][kRowBlocks] accumulator unit ready
+  uint64_t* t_empty = t_full + 4;        // [2 buffers][kRowBlocks] accumulator unit drained (4 warps)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
+  static_assert(kRowBlocks == 2 && NUM_KB < STAGES, "unit hand-off assumes two row blocks and a ring deeper than one query tile");
 
   const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
 
@@ -419,7 +425,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 8);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 4 * kEpiSets);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -470,27 +476,33 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       ptx::mbar_wait(a_full, task_iter & 1);
       for (int j = j0; j < j1; ++j) {
         const uint32_t buf = tile_iter & 1;
-        ptx::mbar_wait(&t_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t dq0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_q + stage * L::kQStage), kRowBytes);
-          const bool leader = ptx::elect_one();
+        // row-block-major issue: the NUM_KB stages of this query tile are consumed twice (row block 0, then 1) and released after
+        // the second use
 #pragma unroll
-          for (int r = 0; r < kRowBlocks; ++r) {
+        for (int r = 0; r < kRowBlocks; ++r) {
+          ptx::mbar_wait(&t_empty[buf * kRowBlocks + r], ((tile_iter >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * kTileN) + r * kTileN;
+          uint32_t st = stage, ph = phase;
+          for (int kb = 0; kb < NUM_KB; ++kb) {
+            if (r == 0) {
+              ptx::mbar_wait(&full[st], ph);
+              ptx::tc_fence_after();
+            }
+            const uint64_t dq0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_q + st * L::kQStage), kRowBytes);
             const uint64_t da0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_a + (kb * kRowBlocks + r) * L::kABlock), kRowBytes);
-            const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * kTileN) + r * kTileN;
+            const bool leader = ptx::elect_one();
 #pragma unroll
             for (int k = 0; k < kKSteps; ++k)
               if (leader) ptx::umma_f16(d_tmem, da0 + 2 * k, dq0 + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            if (leader) {
+              if (r == kRowBlocks - 1) ptx::umma_commit(&empty[st]);                      // smem slot reusable when these MMAs retire
+              if (kb == NUM_KB - 1) ptx::umma_commit(&t_full[buf * kRowBlocks + r]);      // this row block's accumulator complete
+            }
+            __syncwarp();
+            if (++st == STAGES) st = 0, ph ^= 1;
           }
-          if (leader) {
-            ptx::umma_commit(&empty[stage]);                       // smem slot reusable when these MMAs retire
-            if (kb == NUM_KB - 1) ptx::umma_commit(&t_full[buf]);  // accumulator complete
-          }
-          __syncwarp();
-          if (++stage == STAGES) stage = 0, phase ^= 1;
+          if (r == kRowBlocks - 1) stage = st, phase = ph;
         }
         ++tile_iter;
       }
@@ -527,7 +539,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           ++tile_iter;
           continue;
         }
-        ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
+        ptx::mbar_wait(&t_full[buf * kRowBlocks + rblk], (tile_iter >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * kTileN) + rblk * kTileN;
         const int col_base = j * kTileN;
@@ -581,7 +593,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+        if (lane == 0) ptx::mbar_arrive(&t_empty[buf * kRowBlocks + rblk]);
         ++tile_iter;
       }
       if (row_ok) args.cand_m[slot] = m_run, args.cand_cnt[slot] = cnt;
