@@ -79,7 +79,7 @@ __device__ __forceinline__ void point_linear(const float* __restrict__ Wt, const
 #pragma unroll
   for (int p = 0; p < PPT; ++p) acc[p] = b;
   const float* xs = Xs + pg * PPT;
-#pragma unroll 8
+#pragma unroll 16
   for (int ci = 0; ci < CIN; ++ci) {
     const float w = __ldg(Wt + ci * COUT + co);
     if constexpr (PPT == 2) {
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NT) pdsc_layer_kernel(Args a, int layer, int l
     float acc[TP];
 #pragma unroll
     for (int o = 0; o < TP; ++o) acc[o] = 0.f;
-#pragma unroll 4
+#pragma unroll 16
     for (int c = 0; c < C; ++c) {
       const float kv = __ldg(Kt + (size_t)c * a.npad + i);
 #pragma unroll
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(NT) pdsc_layer_kernel(Args a, int layer, int l
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {
       const float v = __ldg(Vg + (size_t)i * C + c);
       const float4 w0 = *reinterpret_cast<const float4*>(St + i * TPS + og * 8);

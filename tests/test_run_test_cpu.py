@@ -210,3 +210,27 @@ def test_dataset_mode_glue_on_cpu(monkeypatch, tmp_path):
     assert invalid_by_dataset <= sum(metrics["Missing segm"]) <= invalid_by_dataset + n_failed_in_loop
     missing = {i for i, m in zip(ids, metrics["Missing segm"]) if m}
     assert scored["failed"] <= missing
+
+
+@pytest.mark.parametrize("n_pairs,batch", [(23, 4), (8, 32), (4, 4)])
+def test_sharded_loop_with_a_pipelined_step(tmp_path, n_pairs, batch):
+    """A pipelined step (``test.pipelined``) hands back the records of the batch BEFORE the one it was given and ``flush`` the last
+    ones: the loop must still attribute every record to its own pair and write the same CSV as the direct loop; without a flush
+    function the loop refuses to drop a batch."""
+    direct = tmp_path / "direct.csv"
+    run_test.run_sharded(n_pairs, batch, _fake_rows, out_path=str(direct))
+    held = []
+
+    def step(idx):
+        held.append(_fake_rows(idx))
+        return held.pop(0) if len(held) > 1 else []
+
+    def flush():
+        return held.pop(0) if held else []
+
+    piped = tmp_path / "piped.csv"
+    res = run_test.run_sharded(n_pairs, batch, step, out_path=str(piped), flush_fn=flush)
+    assert piped.read_bytes() == direct.read_bytes() and [r["pair_index"] for r in res["records"]] == list(range(n_pairs))
+    held.clear()
+    with pytest.raises(RuntimeError, match="never returned"):
+        run_test.run_sharded(n_pairs, batch, step, out_path=str(piped))
