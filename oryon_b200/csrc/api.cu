@@ -109,7 +109,7 @@ cudaEvent_t oryon_handle::take_event() {
 }
 void oryon_handle::span_begin(int id, cudaStream_t st) {
   if (!profiling) return;
-  oryon::ProfSpan s{id, take_event(), take_event()};
+  oryon::ProfSpan s{span_alias >= 0 ? span_alias : id, take_event(), take_event()};
   cudaEventRecord(s.a, st);
   spans.push_back(s);
 }

@@ -66,6 +66,8 @@ struct ProfSpan {
 // The opaque handle of the C ABI.
 struct oryon_handle {
   bool profiling = false;
+  int span_alias = -1;                      // >= 0: spans opened meanwhile are booked under this kernel id (PointDSC's GEMMs)
+  bool gemm_uncounted = false;              // GEMMs launched meanwhile stay out of gemm_launches / gemm_flops (the network's counters)
   std::vector<oryon::ProfSpan> spans;       // recorded, not yet read
   std::vector<cudaEvent_t> free_events;
   cudaEvent_t take_event();

@@ -1061,8 +1061,7 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
             p.M, p.N, p.K, p.nb0, p.nb1, TN, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
-  ++h->gemm_launches;
-  h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  if (!h->gemm_uncounted) ++h->gemm_launches, h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
   return ORYON_OK;
 }
 
@@ -1109,8 +1108,7 @@ static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
             p.nb1, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
-  ++h->gemm_launches;
-  h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  if (!h->gemm_uncounted) ++h->gemm_launches, h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
   return ORYON_OK;
 }
 
@@ -1167,8 +1165,7 @@ static int launch_quad(oryon_handle* h, const Problem& p, cudaStream_t st) {
             p.nb0, p.nb1, NPASS, tasks, clusters, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
-  ++h->gemm_launches;
-  h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  if (!h->gemm_uncounted) ++h->gemm_launches, h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
   return ORYON_OK;
 }
 

@@ -24,7 +24,10 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "gemm.cuh"
 #include "ptx_sm100.cuh"
 
 namespace oryon {
@@ -57,6 +60,13 @@ struct Model {
   std::vector<LayerW> layers;
   const float *c0_w = nullptr, *c0_b = nullptr, *c1_w = nullptr, *c1_b = nullptr, *c2_w = nullptr, *c2_b = nullptr;
   DeviceBuffer layer_table;                        // LayerW[num_layers] on the device
+  // tensor-core path: the same folded weights as GEMM operands, [cout][cin] fp16 split pairs (cin = 128 or 64: already a multiple of 64)
+  DeviceBuffer tc_blob;
+  struct TcLayer {
+    const __half *pcn_hi, *pcn_lo, *qk_hi, *qk_lo, *v_hi, *v_lo, *m0_hi, *m0_lo, *m1_hi, *m1_lo, *m2_hi, *m2_lo;
+    const float *pcn_b, *qk_b, *v_b, *m0_b, *m1_b, *m2_b;
+  };
+  std::vector<TcLayer> tc;
 };
 
 struct PairMeta {
@@ -233,6 +243,31 @@ __global__ void __launch_bounds__(NT) pdsc_prologue_kernel(Args a) {
   store_point_major(bufB, a.b.v[0] + po, base);
 }
 
+// after the last layer (PointDSC.py:156, :171): L2-normalised features and the confidence MLP for the tile in bufA ([C][TPS])
+__device__ __forceinline__ void final_part(const Args& a, int p, int base, int n, size_t po, float* bufA, float* bufB) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // F.normalize(p=2, dim=-1): x / max(|x|, 1e-12); warp w owns points 2w, 2w+1
+  for (int r = 0; r < 2; ++r) {
+    const int pt = warp * 2 + r;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) ss = fmaf(bufA[c * TPS + pt], bufA[c * TPS + pt], ss);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+    if (base + pt < n)
+      for (int c = lane; c < C; c += 32) a.b.fn[po + (size_t)(base + pt) * C + c] = __fdiv_rn(bufA[c * TPS + pt], nrm);
+  }
+  point_linear<C, 32, true>(a.c0_w, a.c0_b, bufA, bufB);
+  __syncthreads();
+  point_linear<32, 32, true>(a.c1_w, a.c1_b, bufB, bufA);
+  __syncthreads();
+  if (threadIdx.x < TP && base + threadIdx.x < n) {
+    float s = __ldg(a.c2_b);
+    for (int ci = 0; ci < 32; ++ci) s = fmaf(__ldg(a.c2_w + ci), bufA[ci * TPS + threadIdx.x], s);
+    a.b.conf[(size_t)p * a.npad + base + threadIdx.x] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // one NonLocal layer for a tile of 16 points (PointDSC.py:26-45), fused with the per-point part of the
 // next layer (PointDSC.py:73-76) or with feature normalisation + confidence MLP (PointDSC.py:156, :171)
@@ -366,27 +401,85 @@ __global__ void __launch_bounds__(NT) pdsc_layer_kernel(Args a, int layer, int l
     __syncthreads();
     store_point_major(bufA, a.b.v[g2] + po, base);
   } else {
-    // F.normalize(p=2, dim=-1): x / max(|x|, 1e-12); warp w owns points 2w, 2w+1
-    for (int r = 0; r < 2; ++r) {
-      const int pt = warp * 2 + r;
-      float ss = 0.f;
-      for (int c = lane; c < C; c += 32) ss = fmaf(bufA[c * TPS + pt], bufA[c * TPS + pt], ss);
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-      if (base + pt < n)
-        for (int c = lane; c < C; c += 32) a.b.fn[po + (size_t)(base + pt) * C + c] = __fdiv_rn(bufA[c * TPS + pt], nrm);
+    final_part(a, p, base, n, po, bufA, bufB);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core path of the NonLocal network (run_network_tc): the two kernels that are not GEMMs
+// ------------------------------------------------------------------------------------------------
+// weight[o][i] = softmax_i( SC[o][i] * S[o][i] ) for i < n (PointDSC.py:39: attention * feat_attention, softmax over the last dim),
+// written as fp16 split pairs with the K extent (i) zero padded to kp: the A operand of the message GEMM.  One warp per row.
+__global__ void __launch_bounds__(256) pdsc_softmax_kernel(Args a, const float* __restrict__ S, __half* __restrict__ p_hi, __half* __restrict__ p_lo, int kp) {
+  const int p = blockIdx.y, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= a.npad) return;
+  const int n = a.meta[p].n;
+  const size_t row = (size_t)p * a.npad + o;
+  __half* ph = p_hi + row * kp;
+  __half* pl = p_lo + row * kp;
+  constexpr int kMaxPer = 64;   // cap 2048 keys / 32 lanes
+  float x[kMaxPer];
+  const int per = (kp + 31) / 32;
+  if (o >= n) {
+    for (int t = 0; t < per; ++t) {
+      const int i = lane + 32 * t;
+      if (i < kp) ph[i] = __float2half_rn(0.f), pl[i] = __float2half_rn(0.f);
     }
-    point_linear<C, 32, true>(a.c0_w, a.c0_b, bufA, bufB);
-    __syncthreads();
-    point_linear<32, 32, true>(a.c1_w, a.c1_b, bufB, bufA);
-    __syncthreads();
-    if (threadIdx.x < TP && base + threadIdx.x < n) {
-      float s = __ldg(a.c2_b);
-      for (int ci = 0; ci < 32; ++ci) s = fmaf(__ldg(a.c2_w + ci), bufA[ci * TPS + threadIdx.x], s);
-      a.b.conf[(size_t)p * a.npad + base + threadIdx.x] = s;
+    return;
+  }
+  const float* sr = S + row * a.npad;
+  const float* cr = a.b.sc + row * a.npad;
+  float m = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < kMaxPer; ++t) {
+    if (t >= per) break;
+    const int i = lane + 32 * t;
+    x[t] = i < n ? __fmul_rn(__ldg(cr + i), __ldg(sr + i)) : -INFINITY;
+    m = fmaxf(m, x[t]);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < kMaxPer; ++t) {
+    if (t >= per) break;
+    const int i = lane + 32 * t;
+    x[t] = i < n ? expf(x[t] - m) : 0.f;
+    sum += x[t];
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll
+  for (int t = 0; t < kMaxPer; ++t) {
+    if (t >= per) break;
+    const int i = lane + 32 * t;
+    if (i < kp) {
+      const float w = __fdiv_rn(x[t], sum);
+      const __half hi = __float2half_rn(w);
+      ph[i] = hi, pl[i] = __float2half_rn(w - __half2float(hi));
     }
   }
+}
+
+// last layer: features [P][npad][C] fp32 (point-major) -> L2-normalised features + confidence (the tail of pdsc_layer_kernel)
+__global__ void __launch_bounds__(NT) pdsc_final_kernel(Args a, const float* __restrict__ feat) {
+  __shared__ __align__(16) float bufA[C * TPS];
+  __shared__ __align__(16) float bufB[C * TPS];
+  const int p = blockIdx.y, base = blockIdx.x * TP;
+  const int n = a.meta[p].n;
+  if (base >= n) return;
+  const size_t po = (size_t)p * a.npad * C;
+  {
+    const int c = threadIdx.x % C, pg = threadIdx.x / C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pt = pg * 8 + j;
+      bufA[c * TPS + pt] = (base + pt < n) ? feat[po + (size_t)(base + pt) * C + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  final_part(a, p, base, n, po, bufA, bufB);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -855,8 +948,14 @@ void destroy_model(oryon_handle* h) {
   if (!m) return;
   m->blob.release();
   m->layer_table.release();
+  m->tc_blob.release();
   delete m;
   h->pointdsc_model = nullptr;
+}
+
+static void destroy_model_ptr(Model* m) {
+  m->blob.release(), m->layer_table.release(), m->tc_blob.release();
+  delete m;
 }
 
 // Packed host weights, reference state_dict order and shapes (models/pointdsc/PointDSC.py:9-113):
@@ -908,17 +1007,34 @@ int load_weights(oryon_handle* h, const oryon_pointdsc_config* cfg, const float*
     }
     return o;
   };
-  struct LayerOff { Off pcn, m0, m1, m2, q, k, v; };
+  // the same folded weights once more in GEMM order [cout][cin] (row-major, K = cin contiguous) for the tensor-core path
+  std::vector<float> rowmajor;
+  auto rm_of = [&](const Off& o, int cout, int cin) -> size_t {
+    const size_t at = rowmajor.size();
+    rowmajor.resize(at + (size_t)cout * cin);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci) rowmajor[at + (size_t)co * cin + ci] = packed[o.w + (size_t)ci * cout + co];
+    return at;
+  };
+  struct LayerOff { Off pcn, m0, m1, m2, q, k, v; size_t r_pcn, r_qk, r_v, r_m0, r_m1, r_m2, b_qk; };
   const Off l0 = fold(C, 6, false);
-  std::vector<LayerOff> lo(L);
+  std::vector<LayerOff> lo_(L);
   for (int i = 0; i < L; ++i) {
-    lo[i].pcn = fold(C, C, true);
-    lo[i].m0 = fold(H, C, true);
-    lo[i].m1 = fold(H, H, true);
-    lo[i].m2 = fold(C, H, false);
-    lo[i].q = fold(C, C, false);
-    lo[i].k = fold(C, C, false);
-    lo[i].v = fold(C, C, false);
+    lo_[i].pcn = fold(C, C, true);
+    lo_[i].m0 = fold(H, C, true);
+    lo_[i].m1 = fold(H, H, true);
+    lo_[i].m2 = fold(C, H, false);
+    lo_[i].q = fold(C, C, false);
+    lo_[i].k = fold(C, C, false);
+    lo_[i].v = fold(C, C, false);
+    lo_[i].r_pcn = rm_of(lo_[i].pcn, C, C);
+    lo_[i].r_qk = rm_of(lo_[i].q, C, C), rm_of(lo_[i].k, C, C);      // q rows then k rows: one [2C][C] operand
+    lo_[i].r_v = rm_of(lo_[i].v, C, C);
+    lo_[i].r_m0 = rm_of(lo_[i].m0, H, C), lo_[i].r_m1 = rm_of(lo_[i].m1, H, H), lo_[i].r_m2 = rm_of(lo_[i].m2, C, H);
+    while (packed.size() % 4) packed.push_back(0.f);
+    lo_[i].b_qk = packed.size();                                    // q bias followed by k bias
+    for (int c = 0; c < C; ++c) packed.push_back(packed[lo_[i].q.b + c]);
+    for (int c = 0; c < C; ++c) packed.push_back(packed[lo_[i].k.b + c]);
   }
   const Off c0 = fold(32, C, false), c1 = fold(32, 32, false), c2 = fold(1, 32, false);
   if (cur != w + n_floats) {
@@ -940,22 +1056,146 @@ int load_weights(oryon_handle* h, const oryon_pointdsc_config* cfg, const float*
   m->layers.resize(L);
   for (int i = 0; i < L; ++i) {
     LayerW& lw = m->layers[i];
-    lw.pcn_w = base + lo[i].pcn.w, lw.pcn_b = base + lo[i].pcn.b;
-    lw.q_w = base + lo[i].q.w, lw.q_b = base + lo[i].q.b;
-    lw.k_w = base + lo[i].k.w, lw.k_b = base + lo[i].k.b;
-    lw.v_w = base + lo[i].v.w, lw.v_b = base + lo[i].v.b;
-    lw.m0_w = base + lo[i].m0.w, lw.m0_b = base + lo[i].m0.b;
-    lw.m1_w = base + lo[i].m1.w, lw.m1_b = base + lo[i].m1.b;
-    lw.m2_w = base + lo[i].m2.w, lw.m2_b = base + lo[i].m2.b;
+    lw.pcn_w = base + lo_[i].pcn.w, lw.pcn_b = base + lo_[i].pcn.b;
+    lw.q_w = base + lo_[i].q.w, lw.q_b = base + lo_[i].q.b;
+    lw.k_w = base + lo_[i].k.w, lw.k_b = base + lo_[i].k.b;
+    lw.v_w = base + lo_[i].v.w, lw.v_b = base + lo_[i].v.b;
+    lw.m0_w = base + lo_[i].m0.w, lw.m0_b = base + lo_[i].m0.b;
+    lw.m1_w = base + lo_[i].m1.w, lw.m1_b = base + lo_[i].m1.b;
+    lw.m2_w = base + lo_[i].m2.w, lw.m2_b = base + lo_[i].m2.b;
   }
   m->c0_w = base + c0.w, m->c0_b = base + c0.b, m->c1_w = base + c1.w, m->c1_b = base + c1.b, m->c2_w = base + c2.w, m->c2_b = base + c2.b;
   ORYON_CUDA_CHECK(cudaMemcpyAsync(m->layer_table.ptr, m->layers.data(), sizeof(LayerW) * L, cudaMemcpyHostToDevice, st));
-  ORYON_CUDA_CHECK(cudaStreamSynchronize(st));  // `packed` and `m->layers` are read by the copies
+  {  // tensor-core operands: fp32 row-major staging (front of the blob) -> fp16 split pairs (every K here is 128 or 64: no padding)
+    const size_t nrm = rowmajor.size();
+    if ((rc = m->tc_blob.reserve(nrm * sizeof(float) + 2 * nrm * sizeof(__half), st))) {
+      destroy_model_ptr(m);
+      return rc;
+    }
+    float* stage = m->tc_blob.as<float>();
+    __half* hi = reinterpret_cast<__half*>(stage + nrm);
+    __half* lo = hi + nrm;
+    ORYON_CUDA_CHECK(cudaMemcpyAsync(stage, rowmajor.data(), nrm * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = gemm::split_rows(h, stage, (int64_t)nrm, 1, (int)nrm, hi, lo, (int64_t)nrm, st))) {
+      destroy_model_ptr(m);
+      return rc;
+    }
+    m->tc.resize(L);
+    for (int i = 0; i < L; ++i) {
+      Model::TcLayer& t = m->tc[i];
+      t.pcn_hi = hi + lo_[i].r_pcn, t.pcn_lo = lo + lo_[i].r_pcn, t.qk_hi = hi + lo_[i].r_qk, t.qk_lo = lo + lo_[i].r_qk;
+      t.v_hi = hi + lo_[i].r_v, t.v_lo = lo + lo_[i].r_v, t.m0_hi = hi + lo_[i].r_m0, t.m0_lo = lo + lo_[i].r_m0;
+      t.m1_hi = hi + lo_[i].r_m1, t.m1_lo = lo + lo_[i].r_m1, t.m2_hi = hi + lo_[i].r_m2, t.m2_lo = lo + lo_[i].r_m2;
+      t.pcn_b = base + lo_[i].pcn.b, t.qk_b = base + lo_[i].b_qk, t.v_b = base + lo_[i].v.b;
+      t.m0_b = base + lo_[i].m0.b, t.m1_b = base + lo_[i].m1.b, t.m2_b = base + lo_[i].m2.b;
+    }
+  }
+  ORYON_CUDA_CHECK(cudaStreamSynchronize(st));  // `packed`, `rowmajor` and `m->layers` are read by the copies
   h->pointdsc_model = m;
   return ORYON_OK;
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// The NonLocal network on the tcgen05 GEMM (gemm.cuh), batched over the P pairs of the call.
+// ------------------------------------------------------------------------------------------------
+// Every per-point layer of the network is a 1x1 convolution = a linear layer over the P * npad points of the call, and the two
+// products of a NonLocal block are per-pair GEMMs (M = N = npad points, K = C / K = npad): per layer
+//   QK    [P*R][2C]   = X Wqk^T + b            (split pair out: Q | K, the operands of the score product)
+//   V^T   [C][P*R]    = (X Wv^T + b)^T         (split pair out, transposed: the W operand of the message product)
+//   S     [P][R][R]   = Q K^T / sqrt(C)        (fp32 out, batched over pairs)
+//   W     = softmax(SC * S) over the keys      (pdsc_softmax_kernel: split pair out, K extent zero padded)
+//   MSG   [P*R][C]    = W V                    (batched over pairs)
+//   fc_message: 128 -> 64 (ReLU) -> 64 (ReLU) -> 128, + F1  (feat, fp32 and split pair)
+//   PointCN of the next layer: 128 -> 128 (ReLU)            (F1 of the next layer, fp32 and split pair)
+// with R = npad.  Operands are fp16 split pairs and every product is issued three times (float32-equivalent, gemm.cuh), like the
+// network GEMMs; rows of points >= n are computed on finite garbage and never read.  Against the fp32 CUDA-core kernel
+// (pdsc_layer_kernel, ORYON_PDSC_FP32=1): 12 x 9 small launches instead of 12 large ones, ~4x less time.
+struct TcBuffers {
+  __half *xa_hi, *xa_lo, *xb_hi, *xb_lo;     // [P*R][C]   activations (A operands), ping-pong
+  __half *qk_hi, *qk_lo;                     // [P*R][2C]
+  __half *vt_hi, *vt_lo;                     // [C][ldv]   V transposed over ALL points of the call (+ 64 zero columns)
+  float* S;                                  // [P][R][R]
+  __half *pm_hi, *pm_lo;                     // [P][R][kp] softmax weights
+  __half *msg_hi, *msg_lo;                   // [P*R][C]
+  __half *h1_hi, *h1_lo, *h2_hi, *h2_lo;     // [P*R][C/2]
+  float* feat;                               // [P*R][C]
+  int R, kp, ldv;
+};
+
+static int run_network_tc(oryon_handle* h, Model* m, const Args& a, const TcBuffers& b, int P, cudaStream_t st) {
+  const int R = b.R, H2 = C / 2, rows = P * R;
+  const int L = m->cfg.num_layers;
+  int rc;
+  auto lin = [&](const __half* a_hi, const __half* a_lo, int K, const __half* w_hi, const __half* w_lo, int N, const gemm::Epilogue& ep) -> int {
+    gemm::Problem p;
+    p.M = rows, p.N = N, p.K = K, p.precision = 3;
+    p.A.hi = a_hi, p.A.lo = a_lo, p.A.ld = K;
+    p.W.hi = w_hi, p.W.lo = w_lo, p.W.ld = K;
+    p.ep = ep;
+    return gemm::launch(h, p, st);
+  };
+  auto ep_split = [](__half* hi, __half* lo, int ld, const float* bias, int act) {
+    gemm::Epilogue e;
+    e.out_hi = hi, e.out_lo = lo, e.ldh = ld, e.bias = bias, e.act = act;
+    return e;
+  };
+  // layer 0's F1 comes from the prologue kernel in fp32
+  if ((rc = gemm::split_rows(h, a.b.f1[0], C, rows, C, b.xa_hi, b.xa_lo, C, st))) return rc;
+  const float* F1 = a.b.f1[0];
+  __half *x_hi = b.xa_hi, *x_lo = b.xa_lo, *y_hi = b.xb_hi, *y_lo = b.xb_lo;
+  for (int l = 0; l < L; ++l) {
+    const Model::TcLayer& t = m->tc[l];
+    if ((rc = lin(x_hi, x_lo, C, t.qk_hi, t.qk_lo, 2 * C, ep_split(b.qk_hi, b.qk_lo, 2 * C, t.qk_b, gemm::ACT_NONE)))) return rc;
+    {
+      gemm::Epilogue e = ep_split(b.vt_hi, b.vt_lo, b.ldv, t.v_b, gemm::ACT_NONE);
+      e.transpose_h = 1;                      // element (point, channel) -> vt[channel][point]
+      if ((rc = lin(x_hi, x_lo, C, t.v_hi, t.v_lo, C, e))) return rc;
+    }
+    {  // scores, batched over pairs: A = Q (columns 0..C-1 of QK), W = K (columns C..2C-1)
+      gemm::Problem p;
+      p.M = R, p.N = R, p.K = C, p.nb0 = P, p.precision = 3;
+      p.A.hi = b.qk_hi, p.A.lo = b.qk_lo, p.A.ld = 2 * C, p.A.stride_b0 = (int64_t)R * 2 * C;
+      p.W.hi = b.qk_hi + C, p.W.lo = b.qk_lo + C, p.W.ld = 2 * C, p.W.stride_b0 = (int64_t)R * 2 * C;
+      p.ep.alpha = 1.f / 11.313708498984761f;  // / (num_channels // head) ** 0.5
+      p.ep.out32 = b.S, p.ep.ld32 = R, p.ep.out_b0 = (int64_t)R * R;
+      if ((rc = gemm::launch(h, p, st))) return rc;
+    }
+    h->span_begin(KID_PDSC_NET, st);
+    pdsc_softmax_kernel<<<dim3((R + 7) / 8, P), 256, 0, st>>>(a, b.S, b.pm_hi, b.pm_lo, b.kp);
+    h->span_end(st);
+    ORYON_CUDA_CHECK(cudaGetLastError());
+    {  // message = W V, batched over pairs: W operand = this pair's columns of V^T
+      gemm::Problem p;
+      p.M = R, p.N = C, p.K = b.kp, p.nb0 = P, p.precision = 3;
+      p.A.hi = b.pm_hi, p.A.lo = b.pm_lo, p.A.ld = b.kp, p.A.stride_b0 = (int64_t)R * b.kp;
+      p.W.hi = b.vt_hi, p.W.lo = b.vt_lo, p.W.ld = b.ldv, p.W.stride_b0 = R;
+      p.ep.out_hi = b.msg_hi, p.ep.out_lo = b.msg_lo, p.ep.ldh = C, p.ep.outh_b0 = (int64_t)R * C;
+      if ((rc = gemm::launch(h, p, st))) return rc;
+    }
+    if ((rc = lin(b.msg_hi, b.msg_lo, C, t.m0_hi, t.m0_lo, H2, ep_split(b.h1_hi, b.h1_lo, H2, t.m0_b, gemm::ACT_RELU)))) return rc;
+    if ((rc = lin(b.h1_hi, b.h1_lo, H2, t.m1_hi, t.m1_lo, H2, ep_split(b.h2_hi, b.h2_lo, H2, t.m1_b, gemm::ACT_RELU)))) return rc;
+    {  // feat = F1 + fc_message(message)
+      gemm::Epilogue e = ep_split(y_hi, y_lo, C, t.m2_b, gemm::ACT_NONE);
+      e.residual = F1, e.out32 = b.feat, e.ld32 = C;
+      if ((rc = lin(b.h2_hi, b.h2_lo, H2, t.m2_hi, t.m2_lo, C, e))) return rc;
+    }
+    if (l + 1 < L) {  // PointCN of the next layer: its F1 (fp32 for the residual, split pair for the projections)
+      float* f1n = a.b.f1[(l + 1) & 1];
+      gemm::Epilogue e = ep_split(x_hi, x_lo, C, m->tc[l + 1].pcn_b, gemm::ACT_RELU);
+      e.out32 = f1n, e.ld32 = C;
+      if ((rc = lin(y_hi, y_lo, C, m->tc[l + 1].pcn_hi, m->tc[l + 1].pcn_lo, C, e))) return rc;
+      F1 = f1n;
+    }
+  }
+  const int tiles = (a.npad + TP - 1) / TP;
+  h->span_begin(KID_PDSC_NET, st);
+  pdsc_final_kernel<<<dim3(tiles, P), NT, 0, st>>>(a, b.feat);
+  h->span_end(st);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
 
 int run_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t* n_host, int P, int cap, float* out_T,
              const oryon_pointdsc_debug* dbg, cudaStream_t st) {
@@ -997,8 +1237,39 @@ int run_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t*
   const size_t o_fn = take(feat), o_conf = take((size_t)P * npad * 4), o_seeds = take((size_t)P * smax * 4);
   const size_t o_knn = take((size_t)P * smax * kMaxK * 4), o_M = take((size_t)P * smax * kMaxK * kMaxK * 4);
   const size_t o_st = take((size_t)P * smax * 12 * 4), o_fit = take((size_t)P * smax * 4), o_meta = take(sizeof(PairMeta) * P);
+  // tensor-core path of the network (default; ORYON_PDSC_FP32=1, read per call, selects the fp32 CUDA-core layer kernel)
+  const char* fp32_env = std::getenv("ORYON_PDSC_FP32");
+  const bool use_tc = !(fp32_env && fp32_env[0] == '1');
+  TcBuffers tb{};
+  size_t o_tc[16] = {0};
+  tb.R = npad, tb.kp = round_up(npad, 64), tb.ldv = round_up(P * npad + 64, 64);
+  if (use_tc) {
+    const size_t rows = (size_t)P * npad;
+    o_tc[0] = take(rows * C * 2), o_tc[1] = take(rows * C * 2), o_tc[2] = take(rows * C * 2), o_tc[3] = take(rows * C * 2);   // xa, xb
+    o_tc[4] = take(rows * 2 * C * 2), o_tc[5] = take(rows * 2 * C * 2);                                                       // qk
+    o_tc[6] = take((size_t)C * tb.ldv * 2), o_tc[7] = take((size_t)C * tb.ldv * 2);                                           // vt
+    o_tc[8] = take(rows * npad * 4);                                                                                          // S
+    o_tc[9] = take(rows * tb.kp * 2), o_tc[10] = take(rows * tb.kp * 2);                                                      // pm
+    o_tc[11] = take(rows * C * 2), o_tc[12] = take(rows * C * 2);                                                             // msg
+    o_tc[13] = take(rows * C * 2), o_tc[14] = take(rows * C * 2);                                                             // h1 | h2 (hi and lo halves inside)
+    o_tc[15] = take(rows * C * 4);                                                                                            // feat
+  }
   if ((rc = h->pdsc_ws.reserve(off, st))) return rc;
   char* ws = h->pdsc_ws.as<char>();
+  if (use_tc) {
+    auto hp = [&](int i) { return reinterpret_cast<__half*>(ws + o_tc[i]); };
+    const size_t rows = (size_t)P * npad;
+    tb.xa_hi = hp(0), tb.xa_lo = hp(1), tb.xb_hi = hp(2), tb.xb_lo = hp(3), tb.qk_hi = hp(4), tb.qk_lo = hp(5), tb.vt_hi = hp(6), tb.vt_lo = hp(7);
+    tb.S = reinterpret_cast<float*>(ws + o_tc[8]);
+    tb.pm_hi = hp(9), tb.pm_lo = hp(10), tb.msg_hi = hp(11), tb.msg_lo = hp(12);
+    tb.h1_hi = hp(13), tb.h1_lo = hp(13) + rows * (C / 2), tb.h2_hi = hp(14), tb.h2_lo = hp(14) + rows * (C / 2);
+    tb.feat = reinterpret_cast<float*>(ws + o_tc[15]);
+    // the grow-only workspace may hold anything from an earlier call's layout: the K padding of V^T (points past the last pair)
+    // must be finite, and rows the prologue does not write (points >= n of every pair) feed GEMM rows that must stay finite too
+    ORYON_CUDA_CHECK(cudaMemsetAsync(tb.vt_hi, 0, (size_t)C * tb.ldv * 2, st));
+    ORYON_CUDA_CHECK(cudaMemsetAsync(tb.vt_lo, 0, (size_t)C * tb.ldv * 2, st));
+    ORYON_CUDA_CHECK(cudaMemsetAsync(ws + o_f1[0], 0, feat, st));
+  }
   ORYON_CUDA_CHECK(cudaMemcpyAsync(ws + o_meta, meta.data(), sizeof(PairMeta) * P, cudaMemcpyHostToDevice, st));
 
   Args a;
@@ -1032,9 +1303,18 @@ int run_pose(oryon_handle* h, const float* src, const float* tgt, const int32_t*
   ORYON_CUDA_CHECK(cudaGetLastError());
   const size_t layer_smem = (size_t)(3 * C * TPS + npad * TPS) * sizeof(float);
   ORYON_CUDA_CHECK(cudaFuncSetAttribute(pdsc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer_smem));
-  for (int l = 0; l < cfg.num_layers; ++l) {
-    pdsc_layer_kernel<<<dim3(tiles, P), NT, layer_smem, st>>>(a, l, l == cfg.num_layers - 1 ? 1 : 0);
-    ORYON_CUDA_CHECK(cudaGetLastError());
+  if (use_tc) {
+    h->span_end(st);                                        // the prologue's span; the GEMMs open their own, booked as pointdsc_net
+    h->span_alias = KID_PDSC_NET, h->gemm_uncounted = true;
+    rc = run_network_tc(h, m, a, tb, P, st);
+    h->span_alias = -1, h->gemm_uncounted = false;
+    if (rc) return rc;
+    h->span_begin(KID_PDSC_NET, st);                        // (empty) span closed below
+  } else {
+    for (int l = 0; l < cfg.num_layers; ++l) {
+      pdsc_layer_kernel<<<dim3(tiles, P), NT, layer_smem, st>>>(a, l, l == cfg.num_layers - 1 ? 1 : 0);
+      ORYON_CUDA_CHECK(cudaGetLastError());
+    }
   }
   h->span_end(st);
   h->span_begin(KID_PDSC_SEEDS, st);

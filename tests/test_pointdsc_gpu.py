@@ -27,6 +27,17 @@ pytestmark = pytest.mark.gpu
 CFG = synth.POINTDSC_DEFAULT_CFG
 
 
+@pytest.fixture(autouse=True, params=["tcgen05", "fp32"])
+def network_path(request, monkeypatch):
+    """Every test runs on both forms of the NonLocal network: the default one on the tcgen05 GEMM (batched over the pairs, three
+    fp16 products per product = float32-equivalent) and the fp32 CUDA-core layer kernel (ORYON_PDSC_FP32=1, read per call)."""
+    if request.param == "fp32":
+        monkeypatch.setenv("ORYON_PDSC_FP32", "1")
+    else:
+        monkeypatch.delenv("ORYON_PDSC_FP32", raising=False)
+    return request.param
+
+
 def _check_seeds(conf_ref, src, mine, theirs, radius):
     """Seed scores (PointDSC.py:211-217) from the reference confidences; compare rank-ordered scores and indices."""
     conf_ref = torch.as_tensor(conf_ref)
