@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ORYON_ABI_VERSION 2
+#define ORYON_ABI_VERSION 3
 
 typedef struct oryon_handle oryon_handle;
 
@@ -238,7 +238,10 @@ int oryon_pointdsc_pose(oryon_handle* h, const float* src, const float* tgt, con
  *   A DEVICE float32 [batch][M][K], W DEVICE float32 [batch][N][K], bias DEVICE float32 [N] or NULL,
  *   residual DEVICE float32 [batch][M][N] or NULL, out DEVICE float32 [batch][M][N]
  *   act: 0 none, 1 QuickGELU x*sigmoid(1.702x) (CLIP), 2 GELU(erf) (timm Mlp), 3 ReLU
- *   precision: 3 = fp16 split pairs, three tcgen05 products, float32-equivalent (default of the backbone);
+ *   precision: 3 = fp16 split pairs, three tcgen05 products, float32-equivalent;
+ *              2 = one fp16 product + both cross terms in one 8-bit (e5m2 x e4m3) product of the same depth, K % 64 == 0: two tensor-pipe
+ *                  units instead of three, ~1.7e-5 relative RMS error per product against 2.9e-4 for one product and 7e-8 for three
+ *                  (oryon_b200/csrc/gemm.cuh);
  *              1 = single fp16 product (run_test.py:14 'medium' precision class) */
 int oryon_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
                    int K, int batch, int act, float alpha, int precision, void* stream);
@@ -253,7 +256,9 @@ int oryon_gemm_f32(oryon_handle* h, const float* A, const float* W, const float*
 typedef struct {
   int32_t vis_layers;          /* CLIP vision transformer depth: 24 for ViT-L/14@336 (vlm.py:19) */
   int32_t txt_layers;          /* CLIP text transformer depth: 12; 0 = text tower not loaded */
-  int32_t precision;           /* GEMM precision, see oryon_gemm_f32: 3 (float32-equivalent, default) or 1 */
+  int32_t precision;           /* GEMM precision, see oryon_gemm_f32: 3 = three products in every GEMM; 2 (default of the Python mirror) = three
+                                * products everywhere except the four linear layers of every CLIP vision block, which run with fp8 cross terms;
+                                * 1 = one product everywhere (NOT a parity mode) */
   int32_t max_pairs_per_pass;  /* pairs processed per pass over the network (bounds activation memory); 0 = 16 */
 } oryon_backbone_config;
 
@@ -284,8 +289,9 @@ typedef struct {
 int oryon_backbone_forward(oryon_handle* h, const float* rgb_a, const float* rgb_q, int B, const float* text_emb, float* featmap_a,
                            float* featmap_q, float* mask_a, float* mask_q, const oryon_backbone_debug* debug, void* stream);
 
-/* GEMM accounting since the last call (launches, algorithmic FLOPs 2*M*N*K); resets the counters. */
-int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops);
+/* GEMM accounting since the last call: launches, algorithmic FLOPs 2*M*N*K, and (may be NULL) the tensor-pipe work actually issued in
+ * fp16-equivalent FLOPs -- 3x / 2x / 1x the algorithmic ones for a GEMM at precision 3 / 2 / 1.  Resets the counters. */
+int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops, double* tensor_flops);
 
 /* ---- a7: mask post-processing ----------------------------------------------------------------------
  * Replaces the no-grad part of FeatureLoss.mask_loss (losses.py:56-60: torch.where(sigmoid(logits) > mask_th, 1, 0)

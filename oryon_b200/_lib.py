@@ -14,7 +14,7 @@ from typing import Dict, Optional
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MATCH_TC_REFINED = 0
 MATCH_EXACT_FP32 = 1
@@ -78,7 +78,7 @@ SIGNATURES = {
     "oryon_text_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "oryon_backbone_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        POINTER(BackboneDebug), c_void_p]),
-    "oryon_gemm_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double)]),
+    "oryon_gemm_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_double), POINTER(c_double)]),
     "oryon_mask_postproc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "oryon_stage_inputs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

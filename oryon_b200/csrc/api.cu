@@ -276,10 +276,11 @@ int oryon_backbone_forward(oryon_handle* h, const float* rgb_a, const float* rgb
   return oryon::net::backbone_forward(h, rgb_a, rgb_q, B, text_emb, featmap_a, featmap_q, mask_a, mask_q, debug,
                                       static_cast<cudaStream_t>(stream));
 }
-int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops) {
+int oryon_gemm_counters(oryon_handle* h, int64_t* launches, double* flops, double* tensor_flops) {
   ORYON_REQUIRE(h && launches && flops, "oryon_gemm_counters: null argument");
   *launches = h->gemm_launches, *flops = h->gemm_flops;
-  h->gemm_launches = 0, h->gemm_flops = 0.0;
+  if (tensor_flops) *tensor_flops = h->gemm_tensor_flops;
+  h->gemm_launches = 0, h->gemm_flops = 0.0, h->gemm_tensor_flops = 0.0;
   return ORYON_OK;
 }
 

@@ -70,6 +70,7 @@ struct Args {
   __half* out_hi;
   __half* out_lo;
   int64_t ldh;
+  int lo_format;              // gemm::LO_F8X: out_lo receives the 8-bit cross-term blocks of the rows (the out-projection runs at precision 2)
   long long* dbg;             // optional per-phase clock64 stamps of CTA (0,0,0) (ORYON_ATTN_DEBUG)
 };
 
@@ -353,9 +354,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_const
         }
         const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + part * kOutCols;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
-          if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
+        for (int c = 0; c < 2; ++c) reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
+        if (a.lo_format == gemm::LO_F8X) {
+          // 16 consecutive columns of one 64-column head: 16 bytes in each half of the row's 128-byte cross-term block
+          uint32_t f[4], g[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            gemm::f8x_act4(__uint_as_float(v[4 * c]) * inv, __uint_as_float(v[4 * c + 1]) * inv, __uint_as_float(v[4 * c + 2]) * inv,
+                           __uint_as_float(v[4 * c + 3]) * inv, f[c], g[c]);
+          uint8_t* pb = reinterpret_cast<uint8_t*>(a.out_lo + ((int64_t)seq * a.S + q) * a.ldh) + gemm::f8x_off(head * kD + part * kOutCols);
+          *reinterpret_cast<uint4*>(pb) = make_uint4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<uint4*>(pb + 64) = make_uint4(g[0], g[1], g[2], g[3]);
+        } else if (a.out_lo) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
         }
       }
     }
@@ -671,9 +683,20 @@ attn_online_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_c
         }
         const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + part * kOutCols;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
-          if (a.out_lo) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
+        for (int c = 0; c < 2; ++c) reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
+        if (a.lo_format == gemm::LO_F8X) {
+          // 16 consecutive columns of one 64-column head: 16 bytes in each half of the row's 128-byte cross-term block
+          uint32_t f[4], g[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            gemm::f8x_act4(__uint_as_float(v[4 * c]) * inv, __uint_as_float(v[4 * c + 1]) * inv, __uint_as_float(v[4 * c + 2]) * inv,
+                           __uint_as_float(v[4 * c + 3]) * inv, f[c], g[c]);
+          uint8_t* pb = reinterpret_cast<uint8_t*>(a.out_lo + ((int64_t)seq * a.S + q) * a.ldh) + gemm::f8x_off(head * kD + part * kOutCols);
+          *reinterpret_cast<uint4*>(pb) = make_uint4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<uint4*>(pb + 64) = make_uint4(g[0], g[1], g[2], g[3]);
+        } else if (a.out_lo) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
         }
       }
     }
@@ -711,8 +734,9 @@ bool v_from_qkv() {
 // vt split pair [n_seq*heads*64][ld_vt] (V^T, zero padded for keys >= S up to a multiple of 128) is only read when
 // v_from_qkv() is false.
 int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
-           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st) {
+           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st, int out_lo_format) {
   ORYON_REQUIRE(width == heads * kD, "attn_tc: head dim must be 64");
+  ORYON_REQUIRE(out_lo_format == gemm::LO_F16 || (precision == 3 && out_lo && ldh == width), "attn_tc: the 8-bit cross-term output needs ldh == width");
   const int T = (S + kKT - 1) / kKT;
   const bool vmn = v_from_qkv();
   ORYON_REQUIRE(vmn || ld_vt >= T * kKT, "attn_tc: V^T rows must be padded to %d keys", T * kKT);
@@ -734,7 +758,7 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
   static const bool two_pass = getenv("ORYON_ATTN_TWOPASS") != nullptr;     // A/B switch: the two-pass kernel
   const char* tau_env = getenv("ORYON_ATTN_TAU");                           // test switch: 0 renews the reference maximum at every increase
   a.tau = tau_env ? (float)atof(tau_env) : 8.f;
-  a.out_hi = out_hi, a.out_lo = precision == 3 ? out_lo : nullptr, a.ldh = ldh;
+  a.out_hi = out_hi, a.out_lo = precision == 3 ? out_lo : nullptr, a.ldh = ldh, a.lo_format = out_lo_format;
   a.dbg = nullptr;
   static const bool want_dbg = getenv("ORYON_ATTN_DEBUG") != nullptr;
   static long long* dbg_dev = nullptr;

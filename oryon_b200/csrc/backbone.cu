@@ -21,7 +21,7 @@
 namespace oryon {
 namespace attn {
 int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
-           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st);
+           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st, int out_lo_format = 0);
 bool v_from_qkv();
 }
 namespace net {
@@ -32,6 +32,9 @@ struct SplitW {  // GEMM-ready weight: [N][ld] fp16 split pair, ld = round_up(K,
   __half* hi = nullptr;
   __half* lo = nullptr;
   int N = 0, K = 0, ld = 0;
+  // precision-2 form (gemm.cuh): hi / lo hold W * 2^k (fp16 / 8-bit cross-term blocks), unscale = 2^-k goes into the epilogue's alpha
+  int f8x = 0;
+  float unscale = 1.f;
 };
 
 struct ClipBlock {
@@ -139,10 +142,18 @@ struct Loader {
     auto* v = get(name, numel);
     return v ? f32(*v) : nullptr;
   }
-  // host matrix [N][K] (row-major) -> device split pair, K padded to 64
-  SplitW split(const float* w, int N, int K) {
+  // host matrix [N][K] (row-major) -> device split pair, K padded to 64.  f8x: the precision-2 form, for the layers that run with
+  // fp8 cross terms (K % 64 == 0)
+  SplitW split(const float* w, int N, int K, bool f8x = false) {
     SplitW s;
     s.N = N, s.K = K, s.ld = round_up(K, 64);
+    float scale = 1.f;
+    if (f8x && K % 64 == 0) {
+      float amax = 0.f;
+      for (size_t i = 0; i < (size_t)N * K; ++i) amax = std::max(amax, std::fabs(w[i]));
+      scale = gemm::weight_scale(amax);
+      s.f8x = 1, s.unscale = 1.f / scale;
+    }
     float* tmp = nullptr;
     if (cudaMalloc(&tmp, (size_t)N * K * 4) != cudaSuccess) {
       if (rc == ORYON_OK) rc = ORYON_ERR_OUT_OF_MEMORY, missing = "cudaMalloc";
@@ -152,16 +163,17 @@ struct Loader {
     s.lo = static_cast<__half*>(dmalloc((size_t)N * s.ld * 2));
     if (s.hi && s.lo) {
       cudaMemcpyAsync(tmp, w, (size_t)N * K * 4, cudaMemcpyHostToDevice, st);
-      const int r = gemm::split_rows(h, tmp, K, N, K, s.hi, s.lo, s.ld, st);
+      const int r = s.f8x ? gemm::split_rows_f8x(h, tmp, K, N, K, s.hi, s.lo, s.ld, true, scale, st)
+                          : gemm::split_rows(h, tmp, K, N, K, s.hi, s.lo, s.ld, st);
       if (r && rc == ORYON_OK) rc = r;
       cudaStreamSynchronize(st);
     }
     cudaFree(tmp);
     return s;
   }
-  SplitW split(const std::string& name, int N, int K) {
+  SplitW split(const std::string& name, int N, int K, bool f8x = false) {
     auto* v = get(name, (size_t)N * K);
-    return v ? split(v->data(), N, K) : SplitW();
+    return v ? split(v->data(), N, K, f8x) : SplitW();
   }
   // conv weight [Cout][Cin][k][k] -> [Cout][(ky*k+kx)*Cin + ci]
   SplitW conv(const std::string& name, int cout, int cin, int k) {
@@ -257,17 +269,17 @@ int set_weight(oryon_handle* h, const char* name, const float* data, int64_t num
   return ORYON_OK;
 }
 
-static void load_clip_blocks(Loader& L, const std::string& prefix, int width, int layers, std::vector<ClipBlock>& out) {
+static void load_clip_blocks(Loader& L, const std::string& prefix, int width, int layers, std::vector<ClipBlock>& out, bool f8x) {
   out.resize(layers);
   for (int i = 0; i < layers; ++i) {
     const std::string p = prefix + ".resblocks." + std::to_string(i);
     ClipBlock& b = out[i];
     b.ln1_g = L.f32(p + ".ln_1.weight", width), b.ln1_b = L.f32(p + ".ln_1.bias", width);
     b.ln2_g = L.f32(p + ".ln_2.weight", width), b.ln2_b = L.f32(p + ".ln_2.bias", width);
-    b.qkv = L.split(p + ".attn.in_proj_weight", 3 * width, width), b.qkv_b = L.f32(p + ".attn.in_proj_bias", 3 * width);
-    b.out = L.split(p + ".attn.out_proj.weight", width, width), b.out_b = L.f32(p + ".attn.out_proj.bias", width);
-    b.fc = L.split(p + ".mlp.c_fc.weight", 4 * width, width), b.fc_b = L.f32(p + ".mlp.c_fc.bias", 4 * width);
-    b.proj = L.split(p + ".mlp.c_proj.weight", width, 4 * width), b.proj_b = L.f32(p + ".mlp.c_proj.bias", width);
+    b.qkv = L.split(p + ".attn.in_proj_weight", 3 * width, width, f8x), b.qkv_b = L.f32(p + ".attn.in_proj_bias", 3 * width);
+    b.out = L.split(p + ".attn.out_proj.weight", width, width, f8x), b.out_b = L.f32(p + ".attn.out_proj.bias", width);
+    b.fc = L.split(p + ".mlp.c_fc.weight", 4 * width, width, f8x), b.fc_b = L.f32(p + ".mlp.c_fc.bias", 4 * width);
+    b.proj = L.split(p + ".mlp.c_proj.weight", width, 4 * width, f8x), b.proj_b = L.f32(p + ".mlp.c_proj.bias", width);
   }
 }
 
@@ -286,8 +298,7 @@ int finalize(oryon_handle* h, const oryon_backbone_config* cfg, cudaStream_t st)
     return ORYON_ERR_NOT_LOADED;
   }
   ORYON_REQUIRE(!m->finalized, "oryon_backbone_finalize: already finalized");
-  ORYON_REQUIRE(cfg->vis_layers >= 1 && cfg->txt_layers >= 0 && (cfg->precision == 1 || cfg->precision == 3),
-                "oryon_backbone_finalize: bad config");
+  ORYON_REQUIRE(cfg->vis_layers >= 1 && cfg->txt_layers >= 0 && cfg->precision >= 1 && cfg->precision <= 3, "oryon_backbone_finalize: bad config");
   ORYON_CUDA_CHECK(cudaSetDevice(h->device));
   m->cfg = *cfg;
   Loader L{h, m, st};
@@ -299,14 +310,15 @@ int finalize(oryon_handle* h, const oryon_backbone_config* cfg, cudaStream_t st)
     m->v_pos = L.f32(p + ".positional_embedding", (size_t)(kVisTok + 1) * kVisW);
     m->v_lnpre_g = L.f32(p + ".ln_pre.weight", kVisW), m->v_lnpre_b = L.f32(p + ".ln_pre.bias", kVisW);
     m->v_lnpost_g = L.f32(p + ".ln_post.weight", kVisW), m->v_lnpost_b = L.f32(p + ".ln_post.bias", kVisW);
-    load_clip_blocks(L, p + ".transformer", kVisW, cfg->vis_layers, m->v_blocks);
+    // precision 2: the four linear layers of every vision block (96 of the 148 GEMMs, 9/10 of the GEMM time) run with fp8 cross terms
+    load_clip_blocks(L, p + ".transformer", kVisW, cfg->vis_layers, m->v_blocks, cfg->precision == 2);
   }
   if (cfg->txt_layers > 0) {  // CLIP text
     const std::string p = "vlm.clip_model";
     m->t_tok = L.f32(p + ".token_embedding.weight", (size_t)kVocab * kTxtW);
     m->t_pos = L.f32(p + ".positional_embedding", (size_t)kTxtL * kTxtW);
     m->t_lnf_g = L.f32(p + ".ln_final.weight", kTxtW), m->t_lnf_b = L.f32(p + ".ln_final.bias", kTxtW);
-    load_clip_blocks(L, p + ".transformer", kTxtW, cfg->txt_layers, m->t_blocks);
+    load_clip_blocks(L, p + ".transformer", kTxtW, cfg->txt_layers, m->t_blocks, false);
     if (auto* v = L.get(p + ".text_projection", (size_t)kTxtW * kTxtW)) {  // x @ P  ==  linear(x, P^T)
       const std::vector<float> t = transpose(*v, kTxtW, kTxtW);
       m->t_proj = L.split(t.data(), kTxtW, kTxtW);
@@ -457,10 +469,11 @@ struct Ctx {
   void gemm(const SplitA& A, int M, const SplitW& W, gemm::Epilogue ep, int nb0 = 1, int64_t a_b0 = 0, int64_t w_b0 = 0) {
     if (dry || rc) return;
     gemm::Problem p;
-    p.M = M, p.N = W.N, p.K = W.K, p.nb0 = nb0, p.precision = prec;
+    p.M = M, p.N = W.N, p.K = W.K, p.nb0 = nb0, p.precision = W.f8x ? 2 : prec;   // f8x: A.lo was written in the LO_F8X form by its producer
     p.A.hi = A.hi, p.A.lo = A.lo, p.A.ld = A.ld, p.A.stride_b0 = a_b0;
     p.W.hi = W.hi, p.W.lo = W.lo, p.W.ld = W.ld, p.W.stride_b0 = w_b0;
     p.ep = ep;
+    p.ep.alpha *= W.unscale;
     rc = gemm::launch(h, p, st);
   }
   void ln(const LnArgs& a) {
@@ -479,9 +492,9 @@ gemm::Epilogue ep_f32(float* out, int ld, const float* bias, int act = gemm::ACT
   e.out32 = out, e.ld32 = ld, e.bias = bias, e.act = act, e.residual = residual, e.row_map = row_map;
   return e;
 }
-gemm::Epilogue ep_split(const SplitA& o, const float* bias, int act) {
+gemm::Epilogue ep_split(const SplitA& o, const float* bias, int act, int lo_format = gemm::LO_F16) {
   gemm::Epilogue e;
-  e.out_hi = o.hi, e.out_lo = o.lo, e.ldh = o.ld, e.bias = bias, e.act = act;
+  e.out_hi = o.hi, e.out_lo = o.lo, e.ldh = o.ld, e.bias = bias, e.act = act, e.lo_format = lo_format;
   return e;
 }
 
@@ -493,6 +506,11 @@ gemm::Epilogue ep_split(const SplitA& o, const float* bias, int act) {
 void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool causal, const std::vector<ClipBlock>& blocks) {
   const int M = n_seq * S, d = width / heads;
   const bool tc_attn = S >= 256 && !causal && d == 64;
+  if (!tc_attn && !blocks.empty() && blocks[0].out.f8x && !c.rc) {
+    set_error("clip_blocks: fp8 cross-term weights need the tensor-core attention path (S >= 256, head dim 64)");
+    c.rc = ORYON_ERR_INVALID_ARGUMENT;
+    return;
+  }
   const size_t mark = c.ar.off;
   SplitA hsp = c.split(M, width);
   SplitA att = c.split(M, width);
@@ -517,13 +535,14 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
   for (const ClipBlock& b : blocks) {
     LnArgs l;
     l.x = x, l.ldx = width, l.C = width, l.gamma = b.ln1_g, l.beta = b.ln1_b, l.rows = M, l.out_hi = hsp.hi, l.out_lo = hsp.lo, l.ldh = width;
+    l.lo_format = b.qkv.f8x;   // each producer writes the `lo` form its consumer's weights were packed for
     c.ln(l);
     if (tc_attn) {
       c.gemm(hsp, M, b.qkv, ep_split(qkvh, b.qkv_b, gemm::ACT_NONE));
       if (need_vt && !c.dry && !c.rc) c.rc = transpose_v(c.h, qkvh.hi, qkvh.lo, 3 * width, 2 * width, n_seq, S, heads, d, vt.hi, vt.lo, ldP, c.st);
       if (!materialized) {
         if (!c.dry && !c.rc)
-          c.rc = attn::launch(c.h, qkvh.hi, qkvh.lo, vt.hi, vt.lo, ldP, n_seq, S, heads, width, c.prec, att.hi, att.lo, width, c.st);
+          c.rc = attn::launch(c.h, qkvh.hi, qkvh.lo, vt.hi, vt.lo, ldP, n_seq, S, heads, width, c.prec, att.hi, att.lo, width, c.st, b.out.f8x);
       } else {
       if (!c.dry && !c.rc) {  // scores[seq][head] = scale * Q K^T
         gemm::Problem p;
@@ -540,6 +559,7 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
         p.A.hi = P.hi, p.A.lo = P.lo, p.A.ld = ldP, p.A.stride_b0 = (int64_t)S * ldP, p.A.stride_b1 = (int64_t)heads * S * ldP;
         p.W.hi = vt.hi, p.W.lo = vt.lo, p.W.ld = ldP, p.W.stride_b0 = (int64_t)d * ldP, p.W.stride_b1 = (int64_t)heads * d * ldP;
         p.ep.out_hi = att.hi, p.ep.out_lo = att.lo, p.ep.ldh = width, p.ep.outh_b0 = d, p.ep.outh_b1 = (int64_t)S * width;
+        p.ep.lo_format = b.out.f8x;
         c.rc = gemm::launch(c.h, p, c.st);
       }
       }
@@ -551,9 +571,9 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
       c.attn(a);
     }
     c.gemm(att, M, b.out, ep_f32(x, width, b.out_b, gemm::ACT_NONE, x));
-    l.gamma = b.ln2_g, l.beta = b.ln2_b;
+    l.gamma = b.ln2_g, l.beta = b.ln2_b, l.lo_format = b.fc.f8x;
     c.ln(l);
-    c.gemm(hsp, M, b.fc, ep_split(hid, b.fc_b, gemm::ACT_QUICKGELU));
+    c.gemm(hsp, M, b.fc, ep_split(hid, b.fc_b, gemm::ACT_QUICKGELU, b.proj.f8x));
     c.gemm(hid, M, b.proj, ep_f32(x, width, b.proj_b, gemm::ACT_NONE, x));
   }
   c.ar.off = mark;  // scratch of the tower is reusable afterwards
@@ -848,7 +868,7 @@ int backbone_forward(oryon_handle* h, const float* rgb_a, const float* rgb_q, in
   const int chunk = std::max(1, std::min(B, m->cfg.max_pairs_per_pass > 0 ? m->cfg.max_pairs_per_pass : 16));
   Outputs o{feat_a, feat_q, mask_a, mask_q, dbg};
   Ctx c{h, m, st, Arena(), true};
-  c.prec = m->cfg.precision;
+  c.prec = m->cfg.precision == 2 ? 3 : m->cfg.precision;   // 2: three products everywhere but the layers whose weights are packed f8x
   forward_chunk(c, rgb_a, rgb_q, 0, chunk, text_emb, o);   // sizing pass
   int rc;
   if ((rc = m->arena.reserve(c.ar.peak + 1024, st))) return rc;
@@ -869,7 +889,7 @@ int text_forward(oryon_handle* h, const int32_t* tokens, int n, float* out, cuda
   ORYON_CUDA_CHECK(cudaSetDevice(h->device));
   const int chunk = std::min(n, 640);
   Ctx c{h, m, st, Arena(), true};
-  c.prec = m->cfg.precision;
+  c.prec = m->cfg.precision == 2 ? 3 : m->cfg.precision;   // 2: three products everywhere but the layers whose weights are packed f8x
   auto run = [&](int s0, int ns) {
     c.ar.off = 0;
     float* x = c.ar.take<float>((size_t)ns * kTxtL * kTxtW);

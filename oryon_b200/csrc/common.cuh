@@ -101,6 +101,7 @@ struct oryon_handle {
   oryon::DeviceBuffer gemm_scratch;
   int64_t gemm_launches = 0;
   double gemm_flops = 0.0;
+  double gemm_tensor_flops = 0.0;           // issued tensor-pipe work in fp16-equivalent FLOPs: 3x / 2x / 1x the algorithmic ones at precision 3 / 2 / 1
   void* backbone = nullptr;                 // oryon::net::Backbone
 
   // ---- evaluator (see eval.cu) ----

@@ -1,7 +1,7 @@
 // gemm_tc_kernel<TN, NPASS>: persistent, warp-specialised tcgen05 GEMM (see gemm.cuh for the contract).
 //
 //   warp 0      TMA producer   cp.async.bulk.tensor.4d (128B swizzle) into a ring of stages; a stage holds one
-//                              64-deep K block of the 256-row A tile and of the TN-row W tile -- for NPASS == 3
+//                              64-deep K block of the 256-row A tile and of the TN-row W tile -- for NPASS >= 2
 //                              both halves (hi, lo) of each, so the three products hi*hi, lo*hi, hi*lo reuse
 //                              what was fetched once
 //   warp 1      MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16 M=128 N=TN K=16, fp32
@@ -12,6 +12,8 @@
 //
 // Grid = min(#SM, tasks); a task is one 256 x TN output tile of one batch matrix, N fastest so that CTAs that run
 // together share the A rows (read once from HBM) and hit L2 for W.
+#include <cmath>
+
 #include "gemm.cuh"
 #include "ptx_sm100.cuh"
 
@@ -29,7 +31,7 @@ constexpr int kEpiWarpFloats = 32 * kEpiLd + 128;           // staging tile + bi
 
 template <int TN, int NPASS>
 struct Cfg {
-  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kHalves = NPASS >= 2 ? 2 : 1;
   static constexpr int kABlock = kTileM * kKB * 2;                    // 16 KB
   static constexpr int kABytes = kABlock * kRowBlocks * kHalves;
   static constexpr int kWBlock = TN * kKB * 2;
@@ -72,6 +74,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   x = fminf(fmaxf(x, -65504.f), 65504.f);
   hi = __float2half_rn(x);
@@ -88,6 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   using L = Cfg<TN, NPASS>;
   constexpr int STAGES = L::kStages;
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kTileM, TN, /*fp16*/ 0);
+  constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(kTileM, TN, ptx::kF8E5M2, ptx::kF8E4M3);   // activations e5m2, weights e4m3
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 0 && lane == 0) {
     if (!GATHER) ptx::prefetch_tensormap(&tm_a_hi);
     ptx::prefetch_tensormap(&tm_w_hi);
-    if (NPASS == 3) {
+    if (NPASS >= 2) {
       if (!GATHER) ptx::prefetch_tensormap(&tm_a_lo);
       ptx::prefetch_tensormap(&tm_w_lo);
     }
@@ -138,12 +142,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
             for (int r = 0; r < kRowBlocks; ++r) {
               tma_load_4d(sa + r * L::kABlock, &tm_a_hi, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
-              if (NPASS == 3)
+              if (NPASS >= 2)
                 tma_load_4d(sa + (kRowBlocks + r) * L::kABlock, &tm_a_lo, &full[stage], kb * kKB, mt * kCtaRows + r * kTileM, b0, b1);
             }
           }
           tma_load_4d(sw, &tm_w_hi, &full[stage], kb * kKB, nt * TN, b0, b1);
-          if (NPASS == 3) tma_load_4d(sw + L::kWBlock, &tm_w_lo, &full[stage], kb * kKB, nt * TN, b0, b1);
+          if (NPASS >= 2) tma_load_4d(sw + L::kWBlock, &tm_w_lo, &full[stage], kb * kKB, nt * TN, b0, b1);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -164,20 +168,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           // ~15 dependent instructions per MMA on the single issuing thread)
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
           const uint32_t sw = sa + L::kABytes;
-          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS == 3 ? L::kWBlock : 0), 128);
+          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS >= 2 ? L::kWBlock : 0), 128);
           const bool leader = ptx::elect_one();
 #pragma unroll
           for (int r = 0; r < kRowBlocks; ++r) {
             const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * TN) + r * TN;
             const uint64_t da_hi = ptx::make_smem_desc_kmajor(sa + r * L::kABlock, 128);
-            const uint64_t da_lo = ptx::make_smem_desc_kmajor(sa + ((NPASS == 3 ? kRowBlocks : 0) + r) * L::kABlock, 128);
-#pragma unroll
-            for (int pass = 0; pass < NPASS; ++pass) {
-              // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
-              const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
+            const uint64_t da_lo = ptx::make_smem_desc_kmajor(sa + ((NPASS >= 2 ? kRowBlocks : 0) + r) * L::kABlock, 128);
+            if (NPASS == 2) {
+              // hi*hi on fp16, then both cross terms as ONE 8-bit product over the 128-byte cross-term blocks (gemm.cuh)
 #pragma unroll
               for (int k = 0; k < kKB / 16; ++k)
-                if (leader) ptx::umma_f16(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);   // +32 bytes >> 4
+                if (leader) ptx::umma_f16(d_tmem, da_hi + 2 * k, dw_hi + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (leader) ptx::umma_f8(d_tmem, da_lo + 2 * k, dw_lo + 2 * k, kIdescF8, 1u);
+            } else {
+#pragma unroll
+              for (int pass = 0; pass < NPASS; ++pass) {
+                // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
+                const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
+#pragma unroll
+                for (int k = 0; k < kKB / 16; ++k)
+                  if (leader) ptx::umma_f16(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);   // +32 bytes >> 4
+              }
             }
           }
           if (leader) {
@@ -266,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&ha)),
                          "r"(*reinterpret_cast<const uint32_t*>(&hb))
                          : "memory");
-            if (NPASS == 3)
+            if (NPASS >= 2)
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kRowBlocks * L::kABlock), "r"(*reinterpret_cast<const uint32_t*>(&la)),
                            "r"(*reinterpret_cast<const uint32_t*>(&lb))
                            : "memory");
@@ -400,7 +414,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
             __half hh[4], ll[4];
             split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
-            if (vec_ok && (ep.ldh & 3) == 0) {
+            if (ep.lo_format == LO_F8X) {   // launch() guarantees N % 4 == 0 and ldh % 4 == 0
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              store_f8x_act4(ep.out_lo + baseh + (int64_t)dr * ep.ldh, col, clamp_h(y.x), clamp_h(y.y), clamp_h(y.z), clamp_h(y.w));
+            } else if (vec_ok && (ep.ldh & 3) == 0) {
               *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
               if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
             } else {
@@ -446,7 +463,7 @@ constexpr int kPairTN = 256;
 
 template <int NPASS>
 struct Cfg2 {
-  static constexpr int kHalves = NPASS == 3 ? 2 : 1;
+  static constexpr int kHalves = NPASS >= 2 ? 2 : 1;
   static constexpr int kABlock = kTileM * kKB * 2;                    // 16 KB: 128 rows x 64 K of one half (hi or lo)
   static constexpr int kABytes = kABlock * kHalves;                   // this CTA's 128 rows of A
   static constexpr int kWBytes = kABlock * kHalves;                   // this CTA's 128 rows (half) of the W tile
@@ -474,6 +491,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   using L = Cfg2<NPASS>;
   constexpr int STAGES = L::kStages;
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kTileM, kPairTN, /*fp16*/ 0);
+  constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(2 * kTileM, kPairTN, ptx::kF8E5M2, ptx::kF8E4M3);   // activations e5m2, weights e4m3
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -489,7 +507,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a_hi);
     ptx::prefetch_tensormap(&tm_w_hi);
-    if (NPASS == 3) ptx::prefetch_tensormap(&tm_a_lo), ptx::prefetch_tensormap(&tm_w_lo);
+    if (NPASS >= 2) ptx::prefetch_tensormap(&tm_a_lo), ptx::prefetch_tensormap(&tm_w_lo);
     for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full[s], 1), ptx::mbar_init(&empty[s], 1);
     for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1), ptx::mbar_init(&t_empty[i], 16);
     ptx::fence_barrier_init();
@@ -522,9 +540,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           uint8_t* sa = smem + stage * L::kStage;
           uint8_t* sw = sa + L::kABytes;
           tma_load_4d_pair(sa, &tm_a_hi, bar, kb * kKB, arow, b0, b1);
-          if (NPASS == 3) tma_load_4d_pair(sa + L::kABlock, &tm_a_lo, bar, kb * kKB, arow, b0, b1);
+          if (NPASS >= 2) tma_load_4d_pair(sa + L::kABlock, &tm_a_lo, bar, kb * kKB, arow, b0, b1);
           tma_load_4d_pair(sw, &tm_w_hi, bar, kb * kKB, wrow, b0, b1);
-          if (NPASS == 3) tma_load_4d_pair(sw + L::kABlock, &tm_w_lo, bar, kb * kKB, wrow, b0, b1);
+          if (NPASS >= 2) tma_load_4d_pair(sw + L::kABlock, &tm_w_lo, bar, kb * kKB, wrow, b0, b1);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -542,16 +560,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStage);
           const uint32_t sw = sa + L::kABytes;
-          const uint64_t da_hi = ptx::make_smem_desc_kmajor(sa, 128), da_lo = ptx::make_smem_desc_kmajor(sa + (NPASS == 3 ? L::kABlock : 0), 128);
-          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS == 3 ? L::kABlock : 0), 128);
+          const uint64_t da_hi = ptx::make_smem_desc_kmajor(sa, 128), da_lo = ptx::make_smem_desc_kmajor(sa + (NPASS >= 2 ? L::kABlock : 0), 128);
+          const uint64_t dw_hi = ptx::make_smem_desc_kmajor(sw, 128), dw_lo = ptx::make_smem_desc_kmajor(sw + (NPASS >= 2 ? L::kABlock : 0), 128);
           const bool leader = ptx::elect_one();
-#pragma unroll
-          for (int pass = 0; pass < NPASS; ++pass) {
-            // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
-            const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
+          if (NPASS == 2) {
+            // hi*hi on fp16, then both cross terms as ONE 8-bit product over the 128-byte cross-term blocks (gemm.cuh)
 #pragma unroll
             for (int k = 0; k < kKB / 16; ++k)
-              if (leader) ptx::umma_f16_pair(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);
+              if (leader) ptx::umma_f16_pair(d_tmem, da_hi + 2 * k, dw_hi + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (leader) ptx::umma_f8_pair(d_tmem, da_lo + 2 * k, dw_lo + 2 * k, kIdescF8, 1u);
+          } else {
+#pragma unroll
+            for (int pass = 0; pass < NPASS; ++pass) {
+              // pass 0: hi*hi   pass 1: lo*hi   pass 2: hi*lo
+              const uint64_t da = pass == 1 ? da_lo : da_hi, dw = pass == 2 ? dw_lo : dw_hi;
+#pragma unroll
+              for (int k = 0; k < kKB / 16; ++k)
+                if (leader) ptx::umma_f16_pair(d_tmem, da + 2 * k, dw + 2 * k, kIdesc, (kb | pass | k) != 0 ? 1u : 0u);
+            }
           }
           if (leader) {
             ptx::umma_commit_pair(&empty[stage], 3);
@@ -668,7 +696,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
             __half hh[4], ll[4];
             split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
-            if (vec_ok && (ep.ldh & 3) == 0) {
+            if (ep.lo_format == LO_F8X) {   // launch() guarantees N % 4 == 0 and ldh % 4 == 0
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              store_f8x_act4(ep.out_lo + baseh + (int64_t)dr * ep.ldh, col, clamp_h(y.x), clamp_h(y.y), clamp_h(y.z), clamp_h(y.w));
+            } else if (vec_ok && (ep.ldh & 3) == 0) {
               *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
               if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
             } else {
@@ -993,6 +1024,12 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+static void count_launch(oryon_handle* h, const Problem& p, int npass) {
+  if (h->gemm_uncounted) return;
+  const double fl = 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  ++h->gemm_launches, h->gemm_flops += fl, h->gemm_tensor_flops += npass * fl;   // the 8-bit cross-term product of precision 2 costs one fp16 product
+}
+
 static int make_map(oryon_handle* h, CUtensorMap* tm, const __half* base, int kpad, int rows, int nb0, int nb1, int64_t ld,
                     int64_t sb0, int64_t sb1, int box_rows) {
   const cuuint64_t gdim[4] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)nb0, (cuuint64_t)nb1};
@@ -1023,12 +1060,12 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
   int rc;
   if ((rc = make_map(h, &tw_hi, p.W.hi, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
   tw_lo = tw_hi;
-  if (NPASS == 3 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
+  if (NPASS >= 2 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, TN))) return rc;
   ta_hi = tw_hi, ta_lo = tw_lo;   // GATHER: the A maps are never touched
   if (!GATHER) {
     if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
     ta_lo = ta_hi;
-    if (NPASS == 3 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+    if (NPASS >= 2 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
   }
   KArgs ka;
   ka.K = p.K;
@@ -1061,7 +1098,7 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
             p.M, p.N, p.K, p.nb0, p.nb1, TN, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
-  if (!h->gemm_uncounted) ++h->gemm_launches, h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  count_launch(h, p, NPASS);
   return ORYON_OK;
 }
 
@@ -1074,10 +1111,10 @@ static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
   int rc;
   if ((rc = make_map(h, &tw_hi, p.W.hi, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
   tw_lo = tw_hi;
-  if (NPASS == 3 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
+  if (NPASS >= 2 && (rc = make_map(h, &tw_lo, p.W.lo, kpad, p.N, p.nb0, p.nb1, p.W.ld, p.W.stride_b0, p.W.stride_b1, kTileM))) return rc;
   if ((rc = make_map(h, &ta_hi, p.A.hi, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
   ta_lo = ta_hi;
-  if (NPASS == 3 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
+  if (NPASS >= 2 && (rc = make_map(h, &ta_lo, p.A.lo, kpad, p.M, p.nb0, p.nb1, p.A.ld, p.A.stride_b0, p.A.stride_b1, kTileM))) return rc;
   KArgs ka;
   ka.K = p.K;
   ka.M = p.M, ka.N = p.N, ka.KB = kpad / kKB;
@@ -1108,7 +1145,7 @@ static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
             p.nb1, NPASS, tasks, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
-  if (!h->gemm_uncounted) ++h->gemm_launches, h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  count_launch(h, p, NPASS);
   return ORYON_OK;
 }
 
@@ -1165,7 +1202,7 @@ static int launch_quad(oryon_handle* h, const Problem& p, cudaStream_t st) {
             p.nb0, p.nb1, NPASS, tasks, clusters, ms * 1e3, 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1 / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0), cudaEventDestroy(e1);
   }
-  if (!h->gemm_uncounted) ++h->gemm_launches, h->gemm_flops += 2.0 * p.M * p.N * p.K * p.nb0 * p.nb1;
+  count_launch(h, p, NPASS);
   return ORYON_OK;
 }
 
@@ -1177,7 +1214,7 @@ static bool use_quad_kernel(const oryon_handle* h, const Problem& p) {
   // QKV 0.249 vs 0.213 ms.  The pair kernel is bound by that round trip with three 64 KB stages in flight, not by L2 bandwidth.
   const char* e = getenv("ORYON_GEMM_QUAD");
   if (!e || e[0] != '1') return false;
-  if (p.gather || h->sm_count < 4 || p.N % (2 * kPairTN) != 0) return false;
+  if (p.gather || h->sm_count < 4 || p.N % (2 * kPairTN) != 0 || p.ep.lo_format != LO_F16) return false;
   const long long tasks = (long long)((p.M + kCtaRows - 1) / kCtaRows) * (p.N / (2 * kPairTN)) * p.nb0 * p.nb1;
   return tasks >= h->sm_count / 4;
 }
@@ -1216,7 +1253,10 @@ int launch(oryon_handle* h, const Problem& p_in, cudaStream_t st) {
   Problem p = p_in;
   if (p.precision == 3 && demoted_by_env(p)) p.precision = 1;
   ORYON_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.nb0 > 0 && p.nb1 > 0, "gemm: empty problem (M=%d N=%d K=%d)", p.M, p.N, p.K);
-  ORYON_REQUIRE(p.precision == 1 || p.precision == 3, "gemm: precision must be 1 or 3");
+  ORYON_REQUIRE(p.precision >= 1 && p.precision <= 3, "gemm: precision must be 1, 2 or 3");
+  ORYON_REQUIRE(p.precision != 2 || (!p.gather && p.K % kKB == 0), "gemm: precision 2 needs K %% 64 == 0 and materialised operands (K=%d)", p.K);
+  ORYON_REQUIRE(p.ep.lo_format == LO_F16 || (p.ep.out_hi && p.ep.out_lo && !p.ep.transpose_h && p.N % 4 == 0 && p.ep.ldh % 4 == 0),
+                "gemm: the 8-bit cross-term output needs a row-major split output with N and ldh multiples of 4");
   const int tn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
   if (p.gather) {
     const ConvGather& g = *p.gather;
@@ -1248,8 +1288,15 @@ int launch(oryon_handle* h, const Problem& p_in, cudaStream_t st) {
   ORYON_REQUIRE(p.A.ld >= round_up(p.K, kKB) || p.A.ld >= p.K, "gemm: A row stride shorter than K");
   ORYON_REQUIRE(!p.ep.row_map || (p.nb0 == 1 && p.nb1 == 1), "gemm: row_map needs an unbatched problem");
   static const bool pairs_off = getenv("ORYON_GEMM_1CTA") != nullptr;
-  if (!pairs_off && use_quad_kernel(h, p)) return p.precision == 3 ? launch_quad<3>(h, p, st) : launch_quad<1>(h, p, st);
-  if (use_pair_kernel(h, p)) return p.precision == 3 ? launch_pair<3>(h, p, st) : launch_pair<1>(h, p, st);
+  if (!pairs_off && p.precision != 2 && use_quad_kernel(h, p)) return p.precision == 3 ? launch_quad<3>(h, p, st) : launch_quad<1>(h, p, st);
+  if (use_pair_kernel(h, p)) return p.precision == 3 ? launch_pair<3>(h, p, st) : (p.precision == 2 ? launch_pair<2>(h, p, st) : launch_pair<1>(h, p, st));
+  if (p.precision == 2) {
+    switch (tn) {
+      case 32: return launch_t<32, 2>(h, p, st);
+      case 64: return launch_t<64, 2>(h, p, st);
+      default: return launch_t<128, 2>(h, p, st);
+    }
+  }
   if (p.precision == 3) {
     switch (tn) {
       case 32: return launch_t<32, 3>(h, p, st);
@@ -1289,6 +1336,58 @@ int split_rows(oryon_handle* h, const float* in, int64_t ld_in, int rows, int co
   return ORYON_OK;
 }
 
+// precision-2 operands (gemm.cuh): hi = fp16(x * scale); lo = the 8-bit cross-term blocks of the row, activation or weight form
+__global__ void __launch_bounds__(256) split_rows_f8x_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols, __half* hi, __half* lo,
+                                                             int64_t ld_out, int is_weight, float scale) {
+  const int q_per_row = cols / 4;
+  const int64_t total = (int64_t)rows * q_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / q_per_row;
+    const int c = (int)(i - r * q_per_row) * 4;
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = clamp_h(in[r * ld_in + c + j] * scale);
+    __half hh[4];
+    float res[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = __float2half_rn(x[j]), res[j] = x[j] - __half2float(hh[j]);
+    *reinterpret_cast<uint2*>(hi + r * ld_out + c) = *reinterpret_cast<const uint2*>(hh);
+    if (is_weight) {
+      uint8_t* p = reinterpret_cast<uint8_t*>(lo + r * ld_out) + f8x_off(c);
+      *reinterpret_cast<uint32_t*>(p) = pack4_f8(res[0] * kF8WLo, res[1] * kF8WLo, res[2] * kF8WLo, res[3] * kF8WLo, __NV_E4M3);
+      *reinterpret_cast<uint32_t*>(p + 64) = pack4_f8(x[0] * kF8WHi, x[1] * kF8WHi, x[2] * kF8WHi, x[3] * kF8WHi, __NV_E4M3);
+    } else {
+      store_f8x_act4(lo + r * ld_out, c, x[0], x[1], x[2], x[3]);
+    }
+  }
+}
+
+int split_rows_f8x(oryon_handle* h, const float* in, int64_t ld_in, int rows, int cols, __half* hi, __half* lo, int64_t ld_out, bool is_weight,
+                   float scale, cudaStream_t st) {
+  ORYON_REQUIRE(cols % kKB == 0 && ld_out == cols, "split_rows_f8x: the row length must be a multiple of 64 without padding (cols=%d ld=%lld)", cols,
+                (long long)ld_out);
+  const int64_t total = (int64_t)rows * (cols / 4);
+  if (total == 0) return ORYON_OK;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+  split_rows_f8x_kernel<<<blocks, 256, 0, st>>>(in, ld_in, rows, cols, hi, lo, ld_out, is_weight ? 1 : 0, scale);
+  ORYON_CUDA_CHECK(cudaGetLastError());
+  return ORYON_OK;
+}
+
+float weight_scale(float absmax) {
+  if (!(absmax > 0.f) || !std::isfinite(absmax)) return 1.f;
+  int e = 0;
+  std::frexp(absmax, &e);          // absmax = f * 2^e, f in [0.5, 1)  ->  absmax * 2^(15 - e) in [2^14, 2^15)
+  return std::ldexp(1.f, 15 - e);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ in, int64_t n, unsigned* out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(in[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+
 // C-ABI test entry (include/oryon_b200.h: oryon_gemm_f32): fp32 operands are split on the device, then the
 // tensor-core kernel runs exactly as it does inside the backbone.
 int run_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N, int K,
@@ -1304,13 +1403,33 @@ int run_gemm_f32(oryon_handle* h, const float* A, const float* W, const float* b
   __half* a_lo = a_hi + a_el;
   __half* w_hi = a_lo + a_el;
   __half* w_lo = w_hi + w_el;
-  if ((rc = split_rows(h, A, K, batch * M, K, a_hi, a_lo, kpad, st))) return rc;
-  if ((rc = split_rows(h, W, K, batch * N, K, w_hi, w_lo, kpad, st))) return rc;
+  float w_unscale = 1.f;
+  if (precision == 2) {
+    // the weight scale of the precision-2 form is fixed per tensor at load time inside the backbone; here it is derived on the fly
+    ORYON_REQUIRE(K % kKB == 0, "oryon_gemm_f32: precision 2 needs K %% 64 == 0");
+    unsigned* d_max = nullptr;
+    unsigned h_max = 0;
+    ORYON_CUDA_CHECK(cudaMalloc(&d_max, 4));
+    cudaMemsetAsync(d_max, 0, 4, st);
+    absmax_kernel<<<h->sm_count * 4, 256, 0, st>>>(W, (int64_t)batch * N * K, d_max);
+    cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st);
+    ORYON_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d_max);
+    float amax;
+    std::memcpy(&amax, &h_max, 4);
+    const float sc = weight_scale(amax);
+    w_unscale = 1.f / sc;
+    if ((rc = split_rows_f8x(h, A, K, batch * M, K, a_hi, a_lo, kpad, false, 1.f, st))) return rc;
+    if ((rc = split_rows_f8x(h, W, K, batch * N, K, w_hi, w_lo, kpad, true, sc, st))) return rc;
+  } else {
+    if ((rc = split_rows(h, A, K, batch * M, K, a_hi, a_lo, kpad, st))) return rc;
+    if ((rc = split_rows(h, W, K, batch * N, K, w_hi, w_lo, kpad, st))) return rc;
+  }
   Problem p;
   p.M = M, p.N = N, p.K = K, p.nb0 = batch, p.nb1 = 1, p.precision = precision;
   p.A.hi = a_hi, p.A.lo = a_lo, p.A.ld = kpad, p.A.stride_b0 = (int64_t)M * kpad;
   p.W.hi = w_hi, p.W.lo = w_lo, p.W.ld = kpad, p.W.stride_b0 = (int64_t)N * kpad;
-  p.ep.alpha = alpha, p.ep.bias = bias, p.ep.act = act, p.ep.residual = residual;
+  p.ep.alpha = alpha * w_unscale, p.ep.bias = bias, p.ep.act = act, p.ep.residual = residual;
   p.ep.out32 = out, p.ep.ld32 = N, p.ep.out_b0 = (int64_t)M * N;
   return launch(h, p, st);
 }

@@ -17,6 +17,7 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -230,7 +231,9 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(LnArgs a) {
           uint2 pk;
           pk.x = *reinterpret_cast<const unsigned*>(&ha), pk.y = *reinterpret_cast<const unsigned*>(&hb);
           *reinterpret_cast<uint2*>(a.out_hi + o + 128 * i + 4 * lane) = pk;
-          if (a.out_lo) {
+          if (a.lo_format == gemm::LO_F8X) {
+            gemm::store_f8x_act4(a.out_lo + o, 128 * i + 4 * lane, clamp_h(v[i].x), clamp_h(v[i].y), clamp_h(v[i].z), clamp_h(v[i].w));
+          } else if (a.out_lo) {
             const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
             pk.x = *reinterpret_cast<const unsigned*>(&la), pk.y = *reinterpret_cast<const unsigned*>(&lb);
             *reinterpret_cast<uint2*>(a.out_lo + o + 128 * i + 4 * lane) = pk;
@@ -318,7 +321,9 @@ __global__ void __launch_bounds__(256) layernorm_vec_rows_kernel(LnArgs a) {
           uint2 pk;
           pk.x = *reinterpret_cast<const unsigned*>(&ha), pk.y = *reinterpret_cast<const unsigned*>(&hb);
           *reinterpret_cast<uint2*>(a.out_hi + o + 128 * i + 4 * lane) = pk;
-          if (a.out_lo) {
+          if (a.lo_format == gemm::LO_F8X) {
+            gemm::store_f8x_act4(a.out_lo + o, 128 * i + 4 * lane, clamp_h(v[j][i].x), clamp_h(v[j][i].y), clamp_h(v[j][i].z), clamp_h(v[j][i].w));
+          } else if (a.out_lo) {
             const __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
             pk.x = *reinterpret_cast<const unsigned*>(&la), pk.y = *reinterpret_cast<const unsigned*>(&lb);
             *reinterpret_cast<uint2*>(a.out_lo + o + 128 * i + 4 * lane) = pk;
@@ -345,6 +350,8 @@ int layernorm(oryon_handle* h, const LnArgs& a, cudaStream_t st) {
   const bool vec = a.C % 128 == 0 && a.gamma && a.beta && al(a.x, 16) && a.ldx % 4 == 0 && al(a.gamma, 16) && al(a.beta, 16) &&
                    (!a.out32 || (al(a.out32, 16) && a.ld32 % 4 == 0)) &&
                    (!a.out_hi || (al(a.out_hi, 8) && a.ldh % 4 == 0 && (!a.out_lo || al(a.out_lo, 8))));
+  ORYON_REQUIRE(a.lo_format == gemm::LO_F16 || (vec && a.out_hi && a.out_lo && a.ldh == a.C && a.cat_C == 0 && a.C % 64 == 0),
+                "layernorm: the 8-bit cross-term output needs the vector path, ldh == C and no concatenated source");
   const int grid = std::min((a.rows + 7) / 8, h->sm_count * 16);
   static const bool rows_v1 = getenv("ORYON_LN_V1") != nullptr;   // A/B switch: one row per warp iteration for every width
   if (vec && !rows_v1 && a.C == 128) layernorm_vec_rows_kernel<1, 4><<<std::min((a.rows + 31) / 32, h->sm_count * 16), 256, 0, st>>>(a);

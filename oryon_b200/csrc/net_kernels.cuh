@@ -5,6 +5,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace oryon {
 namespace net {
@@ -32,6 +33,7 @@ struct LnArgs {
   __half* out_hi = nullptr;       // split output [rows][ldh], zero padded up to ldh
   __half* out_lo = nullptr;
   int64_t ldh = 0;
+  int lo_format = 0;              // gemm::LO_F8X: out_lo receives the 8-bit cross-term blocks (C % 64 == 0, no concat, vector path)
 };
 int layernorm(oryon_handle* h, const LnArgs& a, cudaStream_t st);
 

@@ -158,6 +158,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 with 8-bit operands (e4m3 / e5m2 per the instruction descriptor): 32 K elements (32 bytes per row) per instruction at
+// the cycle cost of a 16-deep kind::f16 instruction, exact products, fp32 accumulate.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Same with the A operand in tensor memory (".ts" form): A[M][K] lives at lanes 0..M-1 of `tmem_a`, K-major, 16-bit elements
 // packed two per 32-bit column (a 16-deep K step = 8 columns).  The four zero registers are the disable-output-lane mask.
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -264,6 +276,16 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the mbarrier at this offset in every CTA of `cta_mask` when all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -308,6 +330,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t smem_a
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int ab_format, int b_mn_major = 0) {
   return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Instruction descriptor, kind::f8f6f4 with 8-bit operands: fp32 accumulator, operand formats 0 = e4m3, 1 = e5m2 (chosen per
+// operand), both K-major, dense.  Same fields as kind::f16.
+constexpr int kF8E4M3 = 0, kF8E5M2 = 1;
+__host__ __device__ constexpr uint32_t make_idesc_f8(int m, int n, int a_format, int b_format) {
+  return (1u << 4) | (static_cast<uint32_t>(a_format) << 7) | (static_cast<uint32_t>(b_format) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -28,7 +28,7 @@ class Oryon:
     with ``model.`` stripped."""
 
     def __init__(self, args=None, device="cuda", *, state_dict: Optional[Dict[str, Tensor]] = None, vis_layers: int = 24,
-                 txt_layers: int = 12, precision: int = 3, max_pairs_per_pass: int = 32, tokenizer=None):
+                 txt_layers: int = 12, precision: int = 2, max_pairs_per_pass: int = 32, tokenizer=None):
         self.args = getattr(args, "model", args)
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -154,8 +154,8 @@ class Oryon:
     __call__ = forward
 
 
-def gemm_counters(device_index: int = 0):
-    """(launches, algorithmic FLOPs) of the tensor-core GEMM since the last call."""
-    n, f = ctypes.c_int64(), ctypes.c_double()
-    _lib.check(_lib.load().oryon_gemm_counters(_lib.handle(device_index), ctypes.byref(n), ctypes.byref(f)))
-    return n.value, f.value
+def gemm_counters(device_index: int = 0, with_tensor_flops: bool = False):
+    """(launches, algorithmic FLOPs[, tensor-pipe FLOPs issued, fp16-equivalent]) of the tensor-core GEMM since the last call."""
+    n, f, t = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.load().oryon_gemm_counters(_lib.handle(device_index), ctypes.byref(n), ctypes.byref(f), ctypes.byref(t)))
+    return (n.value, f.value, t.value) if with_tensor_flops else (n.value, f.value)

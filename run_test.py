@@ -279,7 +279,9 @@ def main(argv=None):
     ap.add_argument("--pairs", type=int, default=2000, help="size of the test split (NOCS / TOYL: 2000 pairs)")
     ap.add_argument("--batch", type=int, default=32, help="configs/config.yaml:17")
     ap.add_argument("--out", default=None, help="prediction CSV written by rank 0")
-    ap.add_argument("--precision", type=int, default=3, choices=[1, 3], help="GEMM products per algorithmic product (3 = float32-equivalent)")
+    ap.add_argument("--precision", type=int, default=2, choices=[1, 2, 3],
+                    help="network GEMM precision: 3 = three fp16 products everywhere, 2 = fp8 cross terms in the CLIP vision linear layers (both "
+                         "hold the 1e-3 gate), 1 = one product")
     ap.add_argument("--distinct-batches", type=int, default=4, help="synthetic batches generated up front and cycled")
     ap.add_argument("--seed", type=int, default=1, help="on_test_start seed (utils/misc.py:186-196)")
     ap.add_argument("--dataset", default=None, help="name of a mounted dataset in the reference's NOCS layout (args.dataset.test.name), e.g. nocs; "

@@ -6,6 +6,9 @@ Tolerances, relative to the magnitude scale ``sqrt(K) * rms(A) * rms(W)`` of one
                                                                   core's truncating fp32 accumulation, ~(K/16) * 2^-24 per
                                                                   output (measured 2e-5 at K = 1024)
   precision 1 (single fp16 product)                        2e-3
+  precision 2 (one fp16 product + both cross terms in      2e-4   cross terms carry ~2^-15 relative error per element: 1/18 of the
+               one 8-bit product, K % 64 == 0)                     single-product error (tools/f8_cross_sim.py), whatever the
+                                                                  magnitude of the activations (e5m2 needs no scale)
 """
 import pytest
 import torch
@@ -76,6 +79,50 @@ def test_gemm_matches_float64(M, N, K, batch, act, use_bias, use_res, precision)
     tol = 1e-4 if precision == 3 else 2e-3
     print(f'scaled err {err:.3e}')
     assert err < tol, f"max scaled error {err:.3e} (tol {tol})"
+
+
+@pytest.mark.parametrize("M,N,K,batch,act,use_bias,use_res", [c for c in CASES if c[2] % 64 == 0])
+def test_gemm_fp8_cross_terms_match_float64(M, N, K, batch, act, use_bias, use_res):
+    """precision 2 on every case whose depth is a multiple of 64: both kernels (single CTA for the small cases, CTA pairs for the
+    large ones), batched operands, every epilogue."""
+    need_gpu()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + batch)
+    shape_a = (batch, M, K) if batch > 1 else (M, K)
+    shape_w = (batch, N, K) if batch > 1 else (N, K)
+    A = torch.randn(shape_a, generator=g)
+    W = torch.randn(shape_w, generator=g) * 0.05
+    bias = torch.randn(N, generator=g) if use_bias else None
+    res = torch.randn(*shape_a[:-1], N, generator=g) if use_res else None
+    alpha = 0.125 if act == "none" and not use_bias else 1.0
+    out = ops.linear(A.cuda(), W.cuda(), None if bias is None else bias.cuda(), None if res is None else res.cuda(), act=act,
+                     alpha=alpha, precision=2).cpu()
+    ref = _ref(A, W, bias, res, act, alpha)
+    scale = alpha * (K ** 0.5) * 1.0 * 0.05 + 1e-3
+    err = (out.double() - ref).abs().max().item() / scale
+    print(f'scaled err {err:.3e}')
+    assert err < 2e-4, f"max scaled error {err:.3e} (tol 2e-4)"
+
+
+@pytest.mark.parametrize("act_scale", [1e-2, 1.0, 1e2])
+def test_gemm_fp8_cross_terms_any_activation_scale(act_scale):
+    """The activation side of the 8-bit product is e5m2 with fixed scales, the weight side e4m3 behind a per-tensor power of two taken
+    from max|W|: the error relative to the output scale must not depend on the magnitude of the activations, nor suffer from one
+    outlier channel (30x) or one outlier weight (75x the rms)."""
+    need_gpu()
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 4864, 1024, 1024
+    A = torch.randn(M, K, generator=g) * torch.exp(0.7 * torch.randn(1, K, generator=g)) * act_scale
+    A[:, 5] *= 30.0
+    W = torch.randn(N, K, generator=g) * 0.02
+    W[3, 7] = 1.5
+    ref = A.double() @ W.double().T
+    out2 = ops.linear(A.cuda(), W.cuda(), precision=2).cpu().double()
+    out1 = ops.linear(A.cuda(), W.cuda(), precision=1).cpu().double()
+    out3 = ops.linear(A.cuda(), W.cuda(), precision=3).cpu().double()
+    rms = ref.pow(2).mean().sqrt()
+    e1, e2, e3 = [((o - ref).pow(2).mean().sqrt() / rms).item() for o in (out1, out2, out3)]
+    print(f"relative rms error: one product {e1:.2e}, fp8 cross terms {e2:.2e}, three products {e3:.2e}")
+    assert e2 < 4e-5 and e2 < e1 / 8, (e1, e2, e3)
 
 
 def test_gemm_large_values_saturate_not_nan():
