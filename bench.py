@@ -565,7 +565,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs of the cpu_baseline sample (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matcher", action="store_true", help="skip the config-2 / config-5 matcher regions (roofline = null)")
-    ap.add_argument("--matcher-only", action="store_true", help="only the config-2 matcher region (used by tools/ncu_traffic.py)")
+    ap.add_argument("--matcher-only", action="store_true", help="only one matcher region (config 2; used by tools/ncu_traffic.py)")
+    ap.add_argument("--matcher-config", type=int, default=2, choices=[2, 5], help="with --matcher-only: BASELINE config 2 or 5")
     ap.add_argument("--matcher-seconds", type=float, default=2.0, help="minimum length of the config-2 roofline region")
     ap.add_argument("--eager-baseline", action="store_true", help="also time the reference's matcher formulation as PyTorch eager ops on the GPU")
     ap.add_argument("--pairs-per-pass", type=int, default=32, help="pairs per network pass inside a step (activation arena size; 16 = round 1's "
@@ -606,7 +607,8 @@ def main():
         pass
 
     if args.matcher_only:
-        m2 = matcher_region(C2, "config2", local, world, rank, barrier, peaks, args.matcher_seconds)
+        m2 = matcher_region(C5 if args.matcher_config == 5 else C2, f"config{args.matcher_config}", local, world, rank, barrier, peaks,
+                            args.matcher_seconds)
         if rank == 0:
             _emit({"matcher_only": True, **m2})
         if world > 1:

@@ -370,6 +370,9 @@ struct TcArgs {
   int32_t* cand_cnt;
   uint32_t* cand_chunk;
   float ambiguity;
+  int dbg_mode;   // timing experiments only (ORYON_MATCH_DEBUG_MODE; results are garbage with bits 1 / 2): 1 = the epilogue releases accumulators
+                  // unread, 2 = the producer loads each query stage once per CTA and re-announces it afterwards; 4 = unit-boundary commits
+                  // issued at the boundary instead of after the next unit's first MMA (valid results, the A/B switch of that placement)
 };
 
 template <int KB_ELEMS, int NUM_KB, int STAGES>
@@ -457,8 +460,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int j = j0; j < j1; ++j) {
           for (int kb = 0; kb < NUM_KB; ++kb) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full[stage], L::kQStage);
-            ptx::tma_load_2d(smem_q + stage * L::kQStage, &tm_q, &full[stage], kb * KB_ELEMS, b * args.npad_q + j * kTileN);
+            if ((args.dbg_mode & 2) && (phase | task_iter) != 0) {
+              ptx::mbar_arrive(&full[stage]);   // experiment: the stage keeps its first contents, no L2 / shared-memory write traffic
+            } else {
+              ptx::mbar_arrive_expect_tx(&full[stage], L::kQStage);
+              ptx::tma_load_2d(smem_q + stage * L::kQStage, &tm_q, &full[stage], kb * KB_ELEMS, b * args.npad_q + j * kTileN);
+            }
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
@@ -469,35 +476,64 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // ============================ MMA issuer ============================
     // Every lane runs the (warp-uniform) control flow; one elected lane issues.  Descriptors are built once per stage /
     // row block and advanced by adding 2 (= 32 bytes >> 4) per 16-element K step.
+    // Commit placement (measured, tools/tmem_ld_bw.cu modes 4-9, profiles/r02_match_commit_placement.md): a tcgen05.commit that is
+    // IMMEDIATELY followed by the first MMA of another accumulator costs ~62 tensor cycles (the new accumulator's MMAs do not overlap
+    // the tail of the old one across the commit) -- 0.94 -> 0.84 tensor duty for 8-MMA accumulations; the same commit issued after
+    // that first MMA costs nothing (0.93).  The commits at a unit boundary (t_full of the finished unit, the release of the query
+    // stage after its second use) are therefore deferred past the first MMA of the next unit; they then also cover that MMA, i.e.
+    // fire 64 cycles later.  They are flushed at once whenever the warp is about to block, so nothing ever waits on a deferred signal.
     uint32_t stage = 0, phase = 0, task_iter = 0, tile_iter = 0;
+    uint64_t* pend_stage = nullptr;   // warp-uniform
+    uint64_t* pend_unit = nullptr;
+    auto flush = [&](bool leader) {
+      if (leader) {
+        if (pend_stage) ptx::umma_commit(pend_stage);
+        if (pend_unit) ptx::umma_commit(pend_unit);
+      }
+      pend_stage = pend_unit = nullptr;
+    };
+    auto wait_flushing = [&](uint64_t* bar, uint32_t parity) {
+      if (ptx::mbar_try_wait(bar, parity)) return;
+      if (pend_stage || pend_unit) {
+        flush(ptx::elect_one());
+        __syncwarp();
+      }
+      ptx::mbar_wait(bar, parity);
+    };
     for (int si = seg_lo; si < seg_hi; ++si) {
       const int4 sg = __ldg(reinterpret_cast<const int4*>(args.segs) + si);   // same address in every lane
       const int j0 = __shfl_sync(0xffffffffu, sg.z, 0), j1 = __shfl_sync(0xffffffffu, sg.w, 0);
-      ptx::mbar_wait(a_full, task_iter & 1);
+      wait_flushing(a_full, task_iter & 1);
       for (int j = j0; j < j1; ++j) {
         const uint32_t buf = tile_iter & 1;
         // row-block-major issue: the NUM_KB stages of this query tile are consumed twice (row block 0, then 1) and released after
         // the second use
 #pragma unroll
         for (int r = 0; r < kRowBlocks; ++r) {
-          ptx::mbar_wait(&t_empty[buf * kRowBlocks + r], ((tile_iter >> 1) & 1) ^ 1);
+          wait_flushing(&t_empty[buf * kRowBlocks + r], ((tile_iter >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * (kRowBlocks * kTileN) + r * kTileN;
           uint32_t st = stage, ph = phase;
           for (int kb = 0; kb < NUM_KB; ++kb) {
             if (r == 0) {
-              ptx::mbar_wait(&full[st], ph);
+              wait_flushing(&full[st], ph);
               ptx::tc_fence_after();
             }
             const uint64_t dq0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_q + st * L::kQStage), kRowBytes);
             const uint64_t da0 = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem_a + (kb * kRowBlocks + r) * L::kABlock), kRowBytes);
             const bool leader = ptx::elect_one();
 #pragma unroll
-            for (int k = 0; k < kKSteps; ++k)
+            for (int k = 0; k < kKSteps; ++k) {
               if (leader) ptx::umma_f16(d_tmem, da0 + 2 * k, dq0 + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
-            if (leader) {
-              if (r == kRowBlocks - 1) ptx::umma_commit(&empty[st]);                      // smem slot reusable when these MMAs retire
-              if (kb == NUM_KB - 1) ptx::umma_commit(&t_full[buf * kRowBlocks + r]);      // this row block's accumulator complete
+              if (k == 0 && kb == 0) flush(leader);   // the previous unit's deferred commits, now behind this unit's first MMA
+            }
+            if (kb == NUM_KB - 1) {
+              // unit boundary: defer (an early flush happens if the warp has to block before the next unit's first MMA)
+              pend_stage = r == kRowBlocks - 1 ? &empty[st] : nullptr;     // smem slot reusable when these MMAs retire
+              pend_unit = &t_full[buf * kRowBlocks + r];                   // this row block's accumulator complete
+              if (args.dbg_mode & 4) flush(leader);                        // A/B switch: commit at the boundary (the round-1 placement)
+            } else if (r == kRowBlocks - 1 && leader) {
+              ptx::umma_commit(&empty[st]);   // mid-unit: followed by MMAs of the same accumulator, free
             }
             __syncwarp();
             if (++st == STAGES) st = 0, ph ^= 1;
@@ -506,7 +542,11 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         ++tile_iter;
       }
-      if (ptx::elect_one()) ptx::umma_commit(a_empty);
+      {
+        const bool leader = ptx::elect_one();
+        flush(leader);
+        if (leader) ptx::umma_commit(a_empty);
+      }
       __syncwarp();
       ++task_iter;
     }
@@ -541,6 +581,13 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         ptx::mbar_wait(&t_full[buf * kRowBlocks + rblk], (tile_iter >> 1) & 1);
         ptx::tc_fence_after();
+        if (args.dbg_mode & 1) {   // experiment: hand the accumulator back unread
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&t_empty[buf * kRowBlocks + rblk]);
+          ++tile_iter;
+          continue;
+        }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * kTileN) + rblk * kTileN;
         const int col_base = j * kTileN;
         const bool ragged = col_base + kTileN > pm.n_q;
@@ -1381,6 +1428,8 @@ int run_match(oryon_handle* h, const float* feat_a, const float* feat_q, int B, 
     ta.B = k.nb, ta.npad_a = npad_a, ta.npad_q = npad_q, ta.splits = k.splits;
     ta.cand_m = cand_m + k.slot_base, ta.cand_cnt = cand_cnt + k.slot_base, ta.cand_chunk = cand_chunk + k.slot_base * kCandCap;
     ta.ambiguity = kAmbiguity;
+    const char* dbg_env = std::getenv("ORYON_MATCH_DEBUG_MODE");
+    ta.dbg_mode = dbg_env ? atoi(dbg_env) : 0;
     CUtensorMap tma, tmq;
     int r;
     if ((r = make_rows_tensor_map(h, &tma, h->rows16_a.as<__half>() + (size_t)k.b0 * npad_a * Dpad, k.nb * npad_a, Dpad, kb_elems, kTileM))) return r;

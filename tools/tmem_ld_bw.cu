@@ -5,7 +5,10 @@
 //   mode 1: W reader warps, two loads in flight per warp
 //   mode 2: as 1, plus the matcher's scan of each 32-column group (four FMNMX chains + one test)
 //   mode 3: as 2, while one more warp issues 128x128x16 fp16 UMMAs back to back into the other half of the columns
-//   mode 4: the UMMAs alone (their rate without readers)
+//   mode 4: the UMMAs alone (their rate without readers), one tcgen05.commit per 64 UMMAs
+//   mode 5 / 6 / 7: the UMMAs alone with one tcgen05.commit (to a barrier nobody waits on) per 8 / 4 / 2 UMMAs: what a commit costs
+//   mode 8: one commit per 8 UMMAs, issued AFTER the first UMMA of the next accumulator instead of at the boundary
+//   mode 9: one commit per 8 UMMAs in the MIDDLE of the accumulation (after the 4th UMMA)
 // Prints bytes per clock and SM for the readers and the tensor-pipe duty of the UMMAs.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I oryon_b200/csrc tools/tmem_ld_bw.cu -o tools/bin/tmem_ld_bw
 #include <cuda_runtime.h>
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(32 * 17) tmem_bw_kernel(int n_readers, int ite
   const uint32_t tmem_base = tmem_slot;
   float sink = 0.f;
 
-  if (warp < n_readers && mode != 4) {
+  if (warp < n_readers && mode < 4) {
     const int quarter = warp & 3;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t va[32], vb[32];
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(32 * 17) tmem_bw_kernel(int n_readers, int ite
     const long long t1 = clock64();
     sink += m_run + cnt;
     if (lane == 0) cyc[warp] = t1 - t0;
-  } else if (warp == mma_warp && (mode == 3 || mode == 4)) {
+  } else if (warp == mma_warp && mode >= 3) {
     constexpr uint32_t idesc = ptx::make_idesc_f16(128, 128, 0);
     const uint64_t da = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem), 128);
     const uint64_t db = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem + 128 * 128), 128);
@@ -109,11 +112,18 @@ __global__ void __launch_bounds__(32 * 17) tmem_bw_kernel(int n_readers, int ite
       const bool leader = ptx::elect_one();
       const uint32_t d = tmem_base + 256 + (b & 1) * 128;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
         if (leader) ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+        if (mode == 7 && (k & 1) && leader) ptx::umma_commit(&bar[1]);
+        if (mode == 8 && k == 0 && b > 0 && leader) ptx::umma_commit(&bar[1]);
+      }
+      if ((mode == 6 || mode == 9) && leader) ptx::umma_commit(&bar[1]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
         if (leader) ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, 1u);
+        if (mode == 7 && (k & 1) && leader) ptx::umma_commit(&bar[1]);
+      }
+      if ((mode == 5 || mode == 6) && leader) ptx::umma_commit(&bar[1]);
       if ((b & 7) == 7) {   // bound the queue: wait for every eighth batch
         if (leader) ptx::umma_commit(&bar[0]);
         __syncwarp();
@@ -148,14 +158,15 @@ int main() {
   cudaMalloc(&d_out, sizeof(Out) * sms);
   const int smem_bytes = 1024 + 2 * 128 * 128;
   using Kern = void (*)(int, int, Out*);
-  const Kern kerns[5] = {tmem_bw_kernel<0>, tmem_bw_kernel<1>, tmem_bw_kernel<2>, tmem_bw_kernel<3>, tmem_bw_kernel<4>};
+  const Kern kerns[10] = {tmem_bw_kernel<0>, tmem_bw_kernel<1>, tmem_bw_kernel<2>, tmem_bw_kernel<3>, tmem_bw_kernel<4>,
+                          tmem_bw_kernel<5>, tmem_bw_kernel<6>, tmem_bw_kernel<7>, tmem_bw_kernel<8>, tmem_bw_kernel<9>};
   for (Kern k : kerns) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   std::vector<Out> h(sms);
   printf("{\"sms\": %d, \"rows\": [\n", sms);
   bool first = true;
-  for (int mode = 0; mode <= 4; ++mode) {
+  for (int mode = 0; mode <= 9; ++mode) {
     for (int readers : {4, 8, 16}) {
-      if (mode == 4 && readers != 4) continue;
+      if (mode >= 4 && readers != 4) continue;
       // mode 3: the readers outlast the UMMAs, so the tensor duty is measured under read load throughout
       const int iters = mode == 3 ? 6 * kIters : kIters;
       for (int rep = 0; rep < 2; ++rep) {
