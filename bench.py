@@ -87,6 +87,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.power_w, self.util, self.power_limit_w = [], [], None
         self._stop = threading.Event()
         self._thr = None
         self._nvml = None
@@ -96,6 +97,10 @@ class ClockSampler:
             self._nvml = pynvml
             self._h = _nvml_handle(pynvml, index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(self._h) / 1e3
+            except Exception:
+                pass
         except Exception:
             self._nvml = None
 
@@ -115,6 +120,11 @@ class ClockSampler:
                     for bit, n in names.items():
                         if mask & bit:
                             self.reasons.add(n)
+                    try:   # board power and the share of the last sampling window with a kernel resident: evidence for "power-capped" / "never idle"
+                        self.power_w.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1e3)
+                        self.util.append(nv.nvmlDeviceGetUtilizationRates(self._h).gpu)
+                    except Exception:
+                        pass
                 else:
                     out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,"
                                           "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -140,8 +150,12 @@ class ClockSampler:
         self._thr.join(timeout=2)
 
     def summary(self):
-        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.power_w:
+            out.update(power_w=round(statistics.median(self.power_w), 1), power_limit_w=self.power_limit_w,
+                       gpu_util_pct=statistics.median(self.util), gpu_util_min_pct=min(self.util))
+        return out
 
 
 def _nvml_handle(pynvml, cuda_index):

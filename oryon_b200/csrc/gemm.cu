@@ -461,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 // `t_empty`.
 constexpr int kPairTN = 256;
 
-template <int NPASS>
+template <int NPASS, int STG = 0>   // STG > 0: a fixed ring depth (the in-flight experiment of ORYON_GEMM_PAIR_STAGES)
 struct Cfg2 {
   static constexpr int kHalves = NPASS >= 2 ? 2 : 1;
   static constexpr int kABlock = kTileM * kKB * 2;                    // 16 KB: 128 rows x 64 K of one half (hi or lo)
@@ -469,7 +469,7 @@ struct Cfg2 {
   static constexpr int kWBytes = kABlock * kHalves;                   // this CTA's 128 rows (half) of the W tile
   static constexpr int kStage = kABytes + kWBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStage;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = STG > 0 ? STG : (kStagesRaw > 8 ? 8 : kStagesRaw);
   static constexpr int kBarBytes = (8 * (2 * kStages + 4) + 16 + 15) / 16 * 16;
   static constexpr int kEpiBytes = 8 * kEpiWarpFloats * 4;
   static constexpr int kTotal = 1024 + kStage * kStages + kBarBytes + kEpiBytes;
@@ -484,11 +484,11 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
-template <int NPASS>
+template <int NPASS, int STG = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const __grid_constant__ KArgs args) {
-  using L = Cfg2<NPASS>;
+  using L = Cfg2<NPASS, STG>;
   constexpr int STAGES = L::kStages;
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kTileM, kPairTN, /*fp16*/ 0);
   constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(2 * kTileM, kPairTN, ptx::kF8E5M2, ptx::kF8E4M3);   // activations e5m2, weights e4m3
@@ -1102,9 +1102,9 @@ static int launch_t(oryon_handle* h, const Problem& p, cudaStream_t st) {
   return ORYON_OK;
 }
 
-template <int NPASS>
+template <int NPASS, int STG = 0>
 static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
-  using L = Cfg2<NPASS>;
+  using L = Cfg2<NPASS, STG>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
   const int kpad = round_up(p.K, kKB);
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
@@ -1124,7 +1124,7 @@ static int launch_pair(oryon_handle* h, const Problem& p, cudaStream_t st) {
   ka.ep = p.ep;
   const long long tasks = (long long)ka.tiles_m * ka.tiles_n * p.nb0 * p.nb1;
   const int pairs = (int)std::min<long long>(h->sm_count / 2, tasks);
-  auto kern = gemm_tc2_kernel<NPASS>;
+  auto kern = gemm_tc2_kernel<NPASS, STG>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     ORYON_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -1289,7 +1289,13 @@ int launch(oryon_handle* h, const Problem& p_in, cudaStream_t st) {
   ORYON_REQUIRE(!p.ep.row_map || (p.nb0 == 1 && p.nb1 == 1), "gemm: row_map needs an unbatched problem");
   static const bool pairs_off = getenv("ORYON_GEMM_1CTA") != nullptr;
   if (!pairs_off && p.precision != 2 && use_quad_kernel(h, p)) return p.precision == 3 ? launch_quad<3>(h, p, st) : launch_quad<1>(h, p, st);
-  if (use_pair_kernel(h, p)) return p.precision == 3 ? launch_pair<3>(h, p, st) : (p.precision == 2 ? launch_pair<2>(h, p, st) : launch_pair<1>(h, p, st));
+  if (use_pair_kernel(h, p)) {
+    // Experiment switch (read per call): ORYON_GEMM_PAIR_STAGES=2 runs the three-stage pair kernels with a two-stage ring, i.e. with
+    // half the operand bytes in flight -- is the L2 -> SM feed bound by bandwidth or by latency x bytes in flight?
+    const char* stg = getenv("ORYON_GEMM_PAIR_STAGES");
+    if (stg && stg[0] == '2' && p.precision >= 2) return p.precision == 3 ? launch_pair<3, 2>(h, p, st) : launch_pair<2, 2>(h, p, st);
+    return p.precision == 3 ? launch_pair<3>(h, p, st) : (p.precision == 2 ? launch_pair<2>(h, p, st) : launch_pair<1>(h, p, st));
+  }
   if (p.precision == 2) {
     switch (tn) {
       case 32: return launch_t<32, 2>(h, p, st);
