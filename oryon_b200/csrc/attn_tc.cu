@@ -710,6 +710,349 @@ attn_online_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// attn_pp_kernel: two softmax warp groups working on ALTERNATING key tiles ("ping-pong"), three products
+// ------------------------------------------------------------------------------------------------
+// attn_online_kernel runs all 16 softmax warps on ONE key tile at a time, in lockstep: accumulator read-out, row maximum, the
+// exchange barrier, the exponentials (MUFU: 16 384 ex2 per tile = 1 024 cycles at 16 per clock), the P store -- ~2 100 cycles per
+// tile of which the MUFU is busy half.  Here the warps form two groups of 8 (thread <-> one row x 64 key columns); group g owns the key
+// tiles j = g (mod 2), its own running reference maximum / row sums and its own O accumulator, so the groups never wait for each
+// other: one group's exponentials run under the other's read-out / exchange / store phases.  The two partial results (O_g, l_g, m_g)
+// are merged once at the end, like a split-KV reduction.
+// Tensor memory (512 columns): three rotating S buffers of 128 columns (tile j -> buffer j mod 3, so Q K^T of tile j + 3 is issued
+// right behind P V of tile j and a group finds its next scores waiting), O_0 and O_1 at 384 / 448.  P overwrites S IN PLACE: a thread
+// reads 32 of its fp32 scores, and stores their 16 packed fp16 hi columns + 16 lo columns into the same 32 columns; the `.ts` MMA
+// takes each 16-key K step from where it lies (hi at column 32 (k / 2) + 8 (k mod 2), lo 16 further).  No s_empty / p_empty
+// barriers: S(j + 3) is ordered behind P V(j) by the in-order tensor pipe.
+// Each thread reads its scores twice (maximum pass, then the exponential pass in two halves of 32 columns): tensor-memory read
+// bandwidth is abundant (tools/tmem_ld_bw.cu) and the second read keeps the live registers at ~64 + 32.
+constexpr uint32_t kPpTmemO = 384;
+struct CfgPp {
+  static constexpr int kQBytes = 2 * kTileBytes;
+  static constexpr int kKStage = 2 * kTileBytes;
+  static constexpr int kVBytes = 2 * kTileBytes;
+  static constexpr int kOffK = kQBytes;
+  static constexpr int kOffV = kOffK + kNK * kKStage;
+  static constexpr int kOffBar = kOffV + 2 * kVBytes;
+  static constexpr int kOffRed = kOffBar + 256;
+  static constexpr int kRedFloats = 2 * 2 * 2 * 128 /* row maxima [group][parity][half][row] */ + 2 * 2 * 128 /* sums */ + 2 * 128 /* maxima */;
+  static constexpr int kTotal = 1024 + kOffRed + kRedFloats * 4;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+template <bool VMN>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv_hi, const __grid_constant__ CUtensorMap tm_qkv_lo,
+               const __grid_constant__ CUtensorMap tm_vt_hi, const __grid_constant__ CUtensorMap tm_vt_lo, Args a, int width) {
+  using L = CfgPp;
+  static_assert(kSmWarps == 16 && kNK == 3, "two groups of 8 softmax warps, three K stages");
+  constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0);
+  constexpr uint32_t kIdescO = ptx::make_idesc_f16(128, 64, 0, VMN ? 1 : 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + L::kOffK;
+  uint8_t* sV = smem + L::kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;             // [3]
+  uint64_t* k_empty = k_full + 3;          // [3]
+  uint64_t* v_full = k_empty + 3;          // [2]
+  uint64_t* v_empty = v_full + 2;          // [2]
+  uint64_t* s_full = v_empty + 2;          // [3] scores of the tile in buffer b complete
+  uint64_t* p_full = s_full + 3;           // [3] probabilities of the tile in buffer b stored (8 warps)
+  uint64_t* pv_done = p_full + 3;          // [2] the group's latest P V has retired: O_g is at rest
+  uint64_t* o_full = pv_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQ, head = blockIdx.y, seq = blockIdx.z;
+  const int T = a.T;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_qkv_hi);
+    ptx::prefetch_tensormap(&tm_qkv_lo);
+    if (!VMN) ptx::prefetch_tensormap(&tm_vt_hi), ptx::prefetch_tensormap(&tm_vt_lo);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1), ptx::mbar_init(&p_full[i], kSmWarps / 2);
+    }
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1), ptx::mbar_init(&pv_done[i], 1);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer: K runs three tiles ahead of V ============================
+    if (lane == 0) {
+      const int row0 = seq * a.S;
+      ptx::mbar_arrive_expect_tx(q_full, L::kQBytes);
+      tma_load_2d_(sQ, &tm_qkv_hi, q_full, head * kD, row0 + q0);
+      tma_load_2d_(sQ + kTileBytes, &tm_qkv_lo, q_full, head * kD, row0 + q0);
+      auto load_k = [&](int j) {
+        const int st = j % 3;
+        ptx::mbar_wait(&k_empty[st], ((j / 3) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[st], L::kKStage);
+        tma_load_2d_(sK + st * L::kKStage, &tm_qkv_hi, &k_full[st], width + head * kD, row0 + j * kKT);
+        tma_load_2d_(sK + st * L::kKStage + kTileBytes, &tm_qkv_lo, &k_full[st], width + head * kD, row0 + j * kKT);
+      };
+      for (int j = 0; j < 3 && j < T; ++j) load_k(j);
+      for (int j = 0; j < T; ++j) {
+        const int vs = j & 1;
+        ptx::mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[vs], L::kVBytes);
+        uint8_t* dst = sV + vs * L::kVBytes;
+        if (VMN) {   // rows past S belong to the next sequence (or are zero-filled past the end): their probabilities are exactly 0
+          tma_load_2d_(dst, &tm_qkv_hi, &v_full[vs], 2 * width + head * kD, row0 + j * kKT);
+          tma_load_2d_(dst + kTileBytes, &tm_qkv_lo, &v_full[vs], 2 * width + head * kD, row0 + j * kKT);
+        } else {
+          const int vrow = (seq * a.heads + head) * kD;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            tma_load_2d_(dst + sub * (kTileBytes / 2), &tm_vt_hi, &v_full[vs], j * kKT + sub * 64, vrow);
+            tma_load_2d_(dst + kTileBytes + sub * (kTileBytes / 2), &tm_vt_lo, &v_full[vs], j * kKT + sub * 64, vrow);
+          }
+        }
+        if (j + 3 < T) load_k(j + 3);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    auto issue_s = [&](int j) {
+      const int b = j % 3;
+      ptx::mbar_wait(&k_full[b], (j / 3) & 1);
+      ptx::tc_fence_after();
+      const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + b * L::kKStage);
+      const bool leader = ptx::elect_one();
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t dq0 = ptx::make_smem_desc_kmajor(q_addr + (pass == 1 ? kTileBytes : 0), 128);
+        const uint64_t dk0 = ptx::make_smem_desc_kmajor(k_addr + (pass == 2 ? kTileBytes : 0), 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (leader) ptx::umma_f16(tmem_base + b * 128, dq0 + 2 * k, dk0 + 2 * k, kIdescS, (pass | k) != 0 ? 1u : 0u);
+      }
+      if (leader) {
+        ptx::umma_commit(&k_empty[b]);
+        ptx::umma_commit(&s_full[b]);
+      }
+      __syncwarp();
+    };
+    ptx::mbar_wait(q_full, 0);
+    for (int j = 0; j < 3 && j < T; ++j) issue_s(j);
+    for (int j = 0; j < T; ++j) {
+      const int b = j % 3, g = j & 1;
+      ptx::mbar_wait(&p_full[b], (j / 3) & 1);
+      ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      {
+        const uint32_t v_addr = ptx::smem_u32(sV + (j & 1) * L::kVBytes);
+        const uint32_t t_o = tmem_base + kPpTmemO + g * 64, t_p = tmem_base + b * 128;
+        const bool leader = ptx::elect_one();
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          // pass 0: P_hi V_hi   pass 1: P_lo V_hi   pass 2: P_hi V_lo
+          const uint32_t va = v_addr + (pass == 2 ? kTileBytes : 0);
+          const uint64_t dv0 = VMN ? ptx::make_smem_desc_mnmajor_sw128(va, 0, 1024) : ptx::make_smem_desc_kmajor(va, 128);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {   // 16 keys per step
+            const uint64_t dv = dv0 + (VMN ? kk * (2048 >> 4) : (kk >> 2) * (kTileBytes >> 5) + 2 * (kk & 3));
+            const uint32_t tp = t_p + 32 * (kk >> 1) + 8 * (kk & 1) + (pass == 1 ? 16 : 0);
+            if (leader) ptx::umma_f16_ts(t_o, tp, dv, kIdescO, (j >= 2 || pass != 0 || kk != 0) ? 1u : 0u);
+          }
+        }
+        if (leader) {
+          ptx::umma_commit(&v_empty[j & 1]);
+          ptx::umma_commit(&pv_done[g]);
+        }
+      }
+      __syncwarp();
+      if (j + 3 < T) issue_s(j + 3);   // into the buffer P V(j) has just read: ordered behind it by the tensor pipe
+    }
+    if (ptx::elect_one()) ptx::umma_commit(o_full);
+    __syncwarp();
+  } else {
+    // ============================ softmax: group g = tiles j = g (mod 2); thread <-> row r x 64 key columns (half h) ============================
+    const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
+    const int idx = (warp - 2) >> 2;                    // 0..3
+    const int g = idx & 1, h = idx >> 1;
+    const int r = quarter * 32 + lane;                  // row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float* red = reinterpret_cast<float*>(smem + L::kOffRed);
+    float* ex_base = red + g * (2 * 2 * 128);           // [parity][half][row]
+    float* sums = red + 2 * 2 * 2 * 128;                // [group][half][row]
+    float* maxs = sums + 2 * 2 * 128;                   // [group][row]
+    const uint32_t t_og = tmem_base + kPpTmemO + g * 64 + lane_addr + h * 32;   // this warp's 32 rows x 32 columns of O_g
+    const int bar_id = 2 + g * 4 + quarter;             // the two warps (h = 0, 1) that share these 32 rows in this group
+    float m_ref = -INFINITY;   // reference maximum of this row for THIS group's tiles, in the scaled log2 domain
+    float l = 0.f;             // this thread's share of the group's row sum, relative to m_ref
+    int n = 0;
+    for (int j = g; j < T; j += 2, ++n) {
+      const int b = j % 3;
+      ptx::mbar_wait(&s_full[b], (j / 3) & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_s = tmem_base + lane_addr + b * 128 + h * 64;
+      const int key0 = j * kKT + h * 64;
+      const bool full = key0 + 64 <= a.S;
+      // ---- pass 1: maximum of this thread's 64 scores ----
+      float m_loc = -INFINITY;
+#pragma unroll
+      for (int sblk = 0; sblk < 2; ++sblk) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_s + sblk * 32, v);
+        ptx::tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) m_loc = fmaxf(m_loc, __uint_as_float(v[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (key0 + sblk * 32 + c < a.S) m_loc = fmaxf(m_loc, __uint_as_float(v[c]));
+        }
+      }
+      float* ex = ex_base + (n & 1) * (2 * 128);
+      ex[h * 128 + r] = m_loc;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      const float m_tile = fmaxf(ex[r], ex[128 + r]);
+      const float mt = m_tile * a.scale_log2e;
+      const bool grow = mt > m_ref + a.tau;     // always on the group's first tile (m_ref = -inf); the same decision in both warps of the row
+      float alpha = 1.f;
+      if (grow) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"(m_ref - mt));   // 0 on the first tile
+        m_ref = mt;
+        l *= alpha;
+      }
+      if (n > 0 && __any_sync(0xffffffffu, grow)) {   // renew the reference of O_g: this warp's 32 rows x 32 columns
+        ptx::mbar_wait(&pv_done[g], (n - 1) & 1);     // the group's previous P V has retired
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t o[16];
+          ptx::tmem_ld_32x32b_x16(t_og + cb * 16, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          ptx::tmem_st_32x32b_x16(t_og + cb * 16, o);
+        }
+      }
+      // ---- pass 2: exponentials, row sums, P = hi + lo stored over the scores just read ----
+      {
+        const uint64_t c2 = ptx::pack_f32x2(a.scale_log2e, a.scale_log2e), nm2 = ptx::pack_f32x2(-m_ref, -m_ref);
+        const uint64_t neg1 = ptx::pack_f32x2(-1.f, -1.f);
+        uint64_t l2 = ptx::pack_f32x2(l, 0.f);
+#pragma unroll
+        for (int sblk = 0; sblk < 2; ++sblk) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_s + sblk * 32, v);
+          ptx::tmem_ld_wait();
+          uint32_t ph[16], pl[16];   // packed half2: element 2c, 2c+1 of these 32 columns
+          const int kb0 = key0 + sblk * 32;
+          auto convert = [&](auto masked) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float x0, x1, p0, p1;
+              ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1])), c2, nm2), x0, x1);
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+              if (decltype(masked)::value) {
+                if (kb0 + 2 * c >= a.S) p0 = 0.f;
+                if (kb0 + 2 * c + 1 >= a.S) p1 = 0.f;
+              }
+              const uint64_t pp = ptx::pack_f32x2(p0, p1);
+              l2 = ptx::add_f32x2(l2, pp);
+              const __half2 h2 = __floats2half2_rn(p0, p1);
+              const float2 back = __half22float2(h2);
+              float r0, r1;
+              ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(back.x, back.y), neg1, pp), r0, r1);   // p - fp16(p), exact
+              const __half2 lo2 = __floats2half2_rn(r0, r1);
+              ph[c] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl[c] = *reinterpret_cast<const uint32_t*>(&lo2);
+            }
+          };
+          if (full) convert(std::false_type{});
+          else convert(std::true_type{});
+          ptx::tmem_st_32x32b_x16(t_s + sblk * 32, ph);        // hi halves: the first 16 of the 32 columns just consumed
+          ptx::tmem_st_32x32b_x16(t_s + sblk * 32 + 16, pl);   // lo halves: the other 16
+        }
+        float la, lb;
+        ptx::unpack_f32x2(l2, la, lb);
+        l = la + lb;
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+    }
+    // ---- merge the two groups: O = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1), w_g = 2^(m_g - max(m_0, m_1)) ----
+    sums[(g * 2 + h) * 128 + r] = l;
+    if (h == 0) maxs[g * 128 + r] = m_ref;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSmWarps) : "memory");
+    const float m0 = maxs[r], m1 = maxs[128 + r];
+    const float l0 = sums[r] + sums[128 + r], l1 = sums[256 + r] + sums[384 + r];
+    const bool has1 = T > 1;                        // group 1 saw at least one tile: O_1 is defined
+    const float mm = has1 ? fmaxf(m0, m1) : m0;
+    float w0, w1 = 0.f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w0) : "f"(m0 - mm));
+    if (has1) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w1) : "f"(m1 - mm));
+    const float inv = 1.f / (l0 * w0 + l1 * w1);
+    w0 *= inv, w1 *= inv;
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const int q = q0 + r;
+    {
+      constexpr int kOutCols = kD / 4;   // 16 columns per warp: idx selects them
+      const uint32_t t_o0 = tmem_base + kPpTmemO + lane_addr + idx * kOutCols;
+      uint32_t v0[16], v1[16];
+      ptx::tmem_ld_32x32b_x16(t_o0, v0);
+      if (has1) ptx::tmem_ld_32x32b_x16(t_o0 + 64, v1);
+      ptx::tmem_ld_wait();
+      if (q < a.S) {
+        float x[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) x[c] = has1 ? fmaf(__uint_as_float(v0[c]), w0, __uint_as_float(v1[c]) * w1) : __uint_as_float(v0[c]) * w0;
+        uint32_t oh[8], ol[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const __half2 h2 = __floats2half2_rn(x[2 * c], x[2 * c + 1]);
+          const float2 back = __half22float2(h2);
+          const __half2 l2 = __floats2half2_rn(x[2 * c] - back.x, x[2 * c + 1] - back.y);
+          oh[c] = *reinterpret_cast<const uint32_t*>(&h2), ol[c] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const int64_t o = ((int64_t)seq * a.S + q) * a.ldh + head * kD + idx * kOutCols;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) reinterpret_cast<uint4*>(a.out_hi + o)[c] = make_uint4(oh[4 * c], oh[4 * c + 1], oh[4 * c + 2], oh[4 * c + 3]);
+        if (a.lo_format == gemm::LO_F8X) {
+          uint32_t f[4], gg[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) gemm::f8x_act4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3], f[c], gg[c]);
+          uint8_t* pb = reinterpret_cast<uint8_t*>(a.out_lo + ((int64_t)seq * a.S + q) * a.ldh) + gemm::f8x_off(head * kD + idx * kOutCols);
+          *reinterpret_cast<uint4*>(pb) = make_uint4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<uint4*>(pb + 64) = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+        } else if (a.out_lo) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) reinterpret_cast<uint4*>(a.out_lo + o)[c] = make_uint4(ol[4 * c], ol[4 * c + 1], ol[4 * c + 2], ol[4 * c + 3]);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int make_map_2d(oryon_handle* h, CUtensorMap* tm, const __half* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
@@ -775,7 +1118,13 @@ int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __
     kernel<<<grid, kThreads, smem, st>>>(tq_hi, tq_lo, tv_hi, tv_lo, a, width);
     return ORYON_OK;
   };
-  if (two_pass) {
+  // Default at three products: the ping-pong kernel (two softmax groups on alternating key tiles); ORYON_ATTN_LOCKSTEP=1 (read per
+  // call) selects the one-group online kernel, ORYON_ATTN_TWOPASS the two-pass one.
+  const char* lockstep_env = getenv("ORYON_ATTN_LOCKSTEP");
+  const bool lockstep = lockstep_env && lockstep_env[0] == '1';
+  if (precision == 3 && !two_pass && !lockstep) {
+    rc = vmn ? run(attn_pp_kernel<true>, CfgPp::kTotal) : run(attn_pp_kernel<false>, CfgPp::kTotal);
+  } else if (two_pass) {
     if (precision == 3) rc = vmn ? run(attn_tc_kernel<3, true>, Cfg<3>::kTotal) : run(attn_tc_kernel<3, false>, Cfg<3>::kTotal);
     else rc = vmn ? run(attn_tc_kernel<1, true>, Cfg<1>::kTotal) : run(attn_tc_kernel<1, false>, Cfg<1>::kTotal);
   } else {
