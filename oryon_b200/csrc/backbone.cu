@@ -21,8 +21,9 @@
 namespace oryon {
 namespace attn {
 int launch(oryon_handle* h, const __half* qkv_hi, const __half* qkv_lo, const __half* vt_hi, const __half* vt_lo, int ld_vt, int n_seq, int S,
-           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st, int out_lo_format = 0);
+           int heads, int width, int precision, __half* out_hi, __half* out_lo, int64_t ldh, cudaStream_t st, int out_lo_format = 0, int qk_f8x = 0);
 bool v_from_qkv();
+bool pp_active();
 }
 namespace net {
 
@@ -538,11 +539,15 @@ void clip_blocks(Ctx& c, float* x, int n_seq, int S, int width, int heads, bool 
     l.lo_format = b.qkv.f8x;   // each producer writes the `lo` form its consumer's weights were packed for
     c.ln(l);
     if (tc_attn) {
-      c.gemm(hsp, M, b.qkv, ep_split(qkvh, b.qkv_b, gemm::ACT_NONE));
+      // precision 2: the Q and K columns leave the projection as 8-bit cross-term blocks too, for the attention kernel's Q K^T
+      const bool qk8 = b.qkv.f8x && !materialized && c.prec == 3 && attn::pp_active();
+      gemm::Epilogue eq = ep_split(qkvh, b.qkv_b, gemm::ACT_NONE, qk8 ? gemm::LO_QKV : gemm::LO_F16);
+      eq.qkv_width = width;
+      c.gemm(hsp, M, b.qkv, eq);
       if (need_vt && !c.dry && !c.rc) c.rc = transpose_v(c.h, qkvh.hi, qkvh.lo, 3 * width, 2 * width, n_seq, S, heads, d, vt.hi, vt.lo, ldP, c.st);
       if (!materialized) {
         if (!c.dry && !c.rc)
-          c.rc = attn::launch(c.h, qkvh.hi, qkvh.lo, vt.hi, vt.lo, ldP, n_seq, S, heads, width, c.prec, att.hi, att.lo, width, c.st, b.out.f8x);
+          c.rc = attn::launch(c.h, qkvh.hi, qkvh.lo, vt.hi, vt.lo, ldP, n_seq, S, heads, width, c.prec, att.hi, att.lo, width, c.st, b.out.f8x, qk8 ? 1 : 0);
       } else {
       if (!c.dry && !c.rc) {  // scores[seq][head] = scale * Q K^T
         gemm::Problem p;

@@ -414,9 +414,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
             __half hh[4], ll[4];
             split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
-            if (ep.lo_format == LO_F8X) {   // launch() guarantees N % 4 == 0 and ldh % 4 == 0
+            if (ep.lo_format == LO_F8X || (ep.lo_format == LO_QKV && col < ep.qkv_width)) {   // launch() guarantees N % 4 == 0 and ldh % 4 == 0
               *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
               store_f8x_act4(ep.out_lo + baseh + (int64_t)dr * ep.ldh, col, clamp_h(y.x), clamp_h(y.y), clamp_h(y.z), clamp_h(y.w));
+            } else if (ep.lo_format == LO_QKV && col < 2 * ep.qkv_width) {                   // K columns: the B-operand blocks
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              uint32_t fa, fb;
+              f8x_actb4(clamp_h(y.x), clamp_h(y.y), clamp_h(y.z), clamp_h(y.w), fa, fb);
+              uint8_t* pb = reinterpret_cast<uint8_t*>(ep.out_lo + baseh + (int64_t)dr * ep.ldh) + f8x_off(col);
+              *reinterpret_cast<uint32_t*>(pb) = fa;
+              *reinterpret_cast<uint32_t*>(pb + 64) = fb;
             } else if (vec_ok && (ep.ldh & 3) == 0) {
               *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
               if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
@@ -696,9 +703,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int64_t oh = baseh + (int64_t)dr * ep.ldh + col;
             __half hh[4], ll[4];
             split_half(y.x, hh[0], ll[0]), split_half(y.y, hh[1], ll[1]), split_half(y.z, hh[2], ll[2]), split_half(y.w, hh[3], ll[3]);
-            if (ep.lo_format == LO_F8X) {   // launch() guarantees N % 4 == 0 and ldh % 4 == 0
+            if (ep.lo_format == LO_F8X || (ep.lo_format == LO_QKV && col < ep.qkv_width)) {   // launch() guarantees N % 4 == 0 and ldh % 4 == 0
               *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
               store_f8x_act4(ep.out_lo + baseh + (int64_t)dr * ep.ldh, col, clamp_h(y.x), clamp_h(y.y), clamp_h(y.z), clamp_h(y.w));
+            } else if (ep.lo_format == LO_QKV && col < 2 * ep.qkv_width) {                   // K columns: the B-operand blocks
+              *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
+              uint32_t fa, fb;
+              f8x_actb4(clamp_h(y.x), clamp_h(y.y), clamp_h(y.z), clamp_h(y.w), fa, fb);
+              uint8_t* pb = reinterpret_cast<uint8_t*>(ep.out_lo + baseh + (int64_t)dr * ep.ldh) + f8x_off(col);
+              *reinterpret_cast<uint32_t*>(pb) = fa;
+              *reinterpret_cast<uint32_t*>(pb + 64) = fb;
             } else if (vec_ok && (ep.ldh & 3) == 0) {
               *reinterpret_cast<uint2*>(ep.out_hi + oh) = *reinterpret_cast<const uint2*>(hh);
               if (ep.out_lo) *reinterpret_cast<uint2*>(ep.out_lo + oh) = *reinterpret_cast<const uint2*>(ll);
@@ -1257,6 +1271,8 @@ int launch(oryon_handle* h, const Problem& p_in, cudaStream_t st) {
   ORYON_REQUIRE(p.precision != 2 || (!p.gather && p.K % kKB == 0), "gemm: precision 2 needs K %% 64 == 0 and materialised operands (K=%d)", p.K);
   ORYON_REQUIRE(p.ep.lo_format == LO_F16 || (p.ep.out_hi && p.ep.out_lo && !p.ep.transpose_h && p.N % 4 == 0 && p.ep.ldh % 4 == 0),
                 "gemm: the 8-bit cross-term output needs a row-major split output with N and ldh multiples of 4");
+  ORYON_REQUIRE(p.ep.lo_format != LO_QKV || (p.ep.qkv_width > 0 && p.ep.qkv_width % 64 == 0 && p.N == 3 * p.ep.qkv_width),
+                "gemm: LO_QKV needs N = 3 * qkv_width, qkv_width a multiple of 64");
   const int tn = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
   if (p.gather) {
     const ConvGather& g = *p.gather;

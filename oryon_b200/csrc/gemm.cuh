@@ -29,7 +29,11 @@ namespace oryon {
 namespace gemm {
 
 enum Act { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU = 2, ACT_RELU = 3 };
-enum LoFormat { LO_F16 = 0, LO_F8X = 1 };   // what the `lo` matrix of a split pair holds: fp16 residuals / the 8-bit cross-term blocks
+// What the `lo` matrix of a split pair holds: fp16 residuals / the 8-bit cross-term blocks of an activation (A operand) /
+// LO_QKV: the output of a fused Q | K | V projection for the attention kernel, which multiplies two ACTIVATIONS: columns [0, w) (Q) get
+// the A-operand blocks, columns [w, 2w) (K) the B-operand blocks [e5m2((k - hi) * 2^4) x 64 | e5m2(k * 2^-7) x 64], columns [2w, 3w)
+// (V) stay fp16 residuals (w = Epilogue::qkv_width, a multiple of 64).
+enum LoFormat { LO_F16 = 0, LO_F8X = 1, LO_QKV = 2 };
 
 constexpr float kF8ActHi = 0.0625f, kF8ActLo = 128.f;      // activation block scales (2^-4, 2^7)
 constexpr float kF8WLo = 16.f, kF8WHi = 0.0078125f;         // weight block scales (2^4, 2^-7); products: 2^-4 * 2^4 = 2^7 * 2^-7 = 1
@@ -48,6 +52,13 @@ __device__ __forceinline__ void f8x_act4(float x0, float x1, float x2, float x3,
   const float r2 = x2 - __half2float(__float2half_rn(x2)), r3 = x3 - __half2float(__float2half_rn(x3));
   first = pack4_f8(x0 * kF8ActHi, x1 * kF8ActHi, x2 * kF8ActHi, x3 * kF8ActHi, __NV_E5M2);
   second = pack4_f8(r0 * kF8ActLo, r1 * kF8ActLo, r2 * kF8ActLo, r3 * kF8ActLo, __NV_E5M2);
+}
+// The B-operand form of four consecutive activation values (the K side of Q K^T): same scales as a weight row, e5m2.
+__device__ __forceinline__ void f8x_actb4(float x0, float x1, float x2, float x3, uint32_t& first, uint32_t& second) {
+  const float r0 = x0 - __half2float(__float2half_rn(x0)), r1 = x1 - __half2float(__float2half_rn(x1));
+  const float r2 = x2 - __half2float(__float2half_rn(x2)), r3 = x3 - __half2float(__float2half_rn(x3));
+  first = pack4_f8(r0 * kF8WLo, r1 * kF8WLo, r2 * kF8WLo, r3 * kF8WLo, __NV_E5M2);
+  second = pack4_f8(x0 * kF8WHi, x1 * kF8WHi, x2 * kF8WHi, x3 * kF8WHi, __NV_E5M2);
 }
 // ... stored into row `lo_row` (pointer to the row's first element) at columns c .. c+3, c % 4 == 0
 __device__ __forceinline__ void store_f8x_act4(__half* lo_row, int c, float x0, float x1, float x2, float x3) {
@@ -83,6 +94,7 @@ struct Epilogue {
   int64_t outh_b0 = 0, outh_b1 = 0;   // batch strides of out_hi / out_lo
   int transpose_h = 0;                // write out_hi/out_lo transposed: element (m, n) at n * ldh + m
   int lo_format = LO_F16;             // LO_F8X: out_lo receives the activation cross-term blocks (the consumer runs at precision 2)
+  int qkv_width = 0;                  // LO_QKV: width of each of the three column ranges
 };
 
 // Implicit-GEMM A operand of a k x k convolution (stride 1, zero padding k / 2) over NHWC fp32 activations: row m is output

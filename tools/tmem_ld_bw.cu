@@ -9,6 +9,8 @@
 //   mode 5 / 6 / 7: the UMMAs alone with one tcgen05.commit (to a barrier nobody waits on) per 8 / 4 / 2 UMMAs: what a commit costs
 //   mode 8: one commit per 8 UMMAs, issued AFTER the first UMMA of the next accumulator instead of at the boundary
 //   mode 9: one commit per 8 UMMAs in the MIDDLE of the accumulation (after the 4th UMMA)
+//   mode 10 / 11: UMMAs alone, M = 128, N = 64 (the P V shape of d = 64 attention): both operands in shared memory / A in tensor memory
+//   mode 12: M = 128, N = 128 with A in tensor memory          (tensor_duty of modes 10-12 is relative to N / 256 * 128 cycles per UMMA)
 // Prints bytes per clock and SM for the readers and the tensor-pipe duty of the UMMAs.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I oryon_b200/csrc tools/tmem_ld_bw.cu -o tools/bin/tmem_ld_bw
 #include <cuda_runtime.h>
@@ -102,7 +104,9 @@ __global__ void __launch_bounds__(32 * 17) tmem_bw_kernel(int n_readers, int ite
     sink += m_run + cnt;
     if (lane == 0) cyc[warp] = t1 - t0;
   } else if (warp == mma_warp && mode >= 3) {
-    constexpr uint32_t idesc = ptx::make_idesc_f16(128, 128, 0);
+    constexpr int kN = (mode == 10 || mode == 11) ? 64 : 128;
+    constexpr bool kTs = mode == 11 || mode == 12;
+    constexpr uint32_t idesc = ptx::make_idesc_f16(128, kN, 0);
     const uint64_t da = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem), 128);
     const uint64_t db = ptx::make_smem_desc_kmajor(ptx::smem_u32(smem + 128 * 128), 128);
     __syncwarp();
@@ -113,14 +117,22 @@ __global__ void __launch_bounds__(32 * 17) tmem_bw_kernel(int n_readers, int ite
       const uint32_t d = tmem_base + 256 + (b & 1) * 128;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (leader) ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+        if (kTs) {
+          if (leader) ptx::umma_f16_ts(d, tmem_base + 8 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);   // A: columns 0 .. 31 of tensor memory
+        } else {
+          if (leader) ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : 0u);
+        }
         if (mode == 7 && (k & 1) && leader) ptx::umma_commit(&bar[1]);
         if (mode == 8 && k == 0 && b > 0 && leader) ptx::umma_commit(&bar[1]);
       }
       if ((mode == 6 || mode == 9) && leader) ptx::umma_commit(&bar[1]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (leader) ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, 1u);
+        if (kTs) {
+          if (leader) ptx::umma_f16_ts(d, tmem_base + 8 * k, db + 2 * k, idesc, 1u);
+        } else {
+          if (leader) ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, 1u);
+        }
         if (mode == 7 && (k & 1) && leader) ptx::umma_commit(&bar[1]);
       }
       if ((mode == 5 || mode == 6) && leader) ptx::umma_commit(&bar[1]);
@@ -158,13 +170,14 @@ int main() {
   cudaMalloc(&d_out, sizeof(Out) * sms);
   const int smem_bytes = 1024 + 2 * 128 * 128;
   using Kern = void (*)(int, int, Out*);
-  const Kern kerns[10] = {tmem_bw_kernel<0>, tmem_bw_kernel<1>, tmem_bw_kernel<2>, tmem_bw_kernel<3>, tmem_bw_kernel<4>,
-                          tmem_bw_kernel<5>, tmem_bw_kernel<6>, tmem_bw_kernel<7>, tmem_bw_kernel<8>, tmem_bw_kernel<9>};
+  const Kern kerns[13] = {tmem_bw_kernel<0>, tmem_bw_kernel<1>, tmem_bw_kernel<2>, tmem_bw_kernel<3>, tmem_bw_kernel<4>,
+                          tmem_bw_kernel<5>, tmem_bw_kernel<6>, tmem_bw_kernel<7>, tmem_bw_kernel<8>, tmem_bw_kernel<9>,
+                          tmem_bw_kernel<10>, tmem_bw_kernel<11>, tmem_bw_kernel<12>};
   for (Kern k : kerns) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   std::vector<Out> h(sms);
   printf("{\"sms\": %d, \"rows\": [\n", sms);
   bool first = true;
-  for (int mode = 0; mode <= 9; ++mode) {
+  for (int mode = 0; mode <= 12; ++mode) {
     for (int readers : {4, 8, 16}) {
       if (mode >= 4 && readers != 4) continue;
       // mode 3: the readers outlast the UMMAs, so the tensor duty is measured under read load throughout
@@ -185,7 +198,7 @@ int main() {
       std::sort(mc.begin(), mc.end());
       const double r_med = (double)rc[sms / 2], m_med = (double)mc[sms / 2];
       const double bytes = (double)readers * iters * 4096.0;
-      const double mma_ideal = (double)kMmaBatches * 8 * 64;   // 128x128x16 fp16 = 64 tensor cycles
+      const double mma_ideal = (double)kMmaBatches * 8 * ((mode == 10 || mode == 11) ? 32 : 64);   // 128 x N x 16 fp16 = N / 2 tensor cycles
       printf("%s  {\"mode\": %d, \"reader_warps\": %d, \"reader_cycles\": %.0f, \"ld_bytes_per_clk_sm\": %.1f, \"cycles_per_4KB_load_per_warp\": %.1f, "
              "\"mma_cycles\": %.0f, \"tensor_duty\": %.3f}",
              first ? "" : ",\n", mode, readers, r_med, r_med > 0 ? bytes / r_med : 0.0, r_med > 0 ? r_med / iters : 0.0, m_med,
