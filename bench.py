@@ -121,6 +121,8 @@ class ClockSampler:
                         if mask & bit:
                             self.reasons.add(n)
                     try:   # board power and the share of the last sampling window with a kernel resident: evidence for "power-capped" / "never idle"
+                        if os.environ.get("ORYON_BENCH_NO_POWER"):
+                            raise RuntimeError("disabled")
                         self.power_w.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1e3)
                         self.util.append(nv.nvmlDeviceGetUtilizationRates(self._h).gpu)
                     except Exception:

@@ -34,9 +34,9 @@ def _fingerprint() -> str:
     h = hashlib.sha256()
     root = os.path.dirname(PKG)
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(root, "include", "oryon_b200.h")]
-    for f in files:
+    for f in files:   # names relative to the package: the fingerprint must not depend on where the tree is checked out
         with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 

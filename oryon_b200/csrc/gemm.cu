@@ -65,9 +65,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// x * sigmoid(1.702 x) with the hardware exponential and reciprocal (5 instructions, ~3e-7 relative error; expf + an IEEE division cost ~25
+// and made the epilogue of the CLIP up-projection -- 151 M activations per launch -- slower than its mainloop once that ran at two
+// tensor-pipe units per product, profiles/r02_gemm_epilogue.md)
+__device__ __forceinline__ float quick_gelu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (-1.702f * 1.4426950408889634f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
-    case ACT_QUICKGELU: return x / (1.f + expf(-1.702f * x));
+    case ACT_QUICKGELU: return quick_gelu(x);
     case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
     case ACT_RELU: return fmaxf(x, 0.f);
     default: return x;
@@ -338,13 +348,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       else ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * TN) + rblk * TN;
+      uint32_t vn[16];
+      ptx::tmem_ld_32x32b_x16(taddr, vn);   // group 0: every group's accumulators are requested one group ahead of their use
 #pragma unroll 1
       for (int g = 0; g < TN / 16; ++g) {
         const int col0 = nt * TN + g * 16;
         if (col0 >= args.N) break;   // warp-uniform
         uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(taddr + g * 16, v);
+        // The residual of this group's four row chunks is requested BEFORE the accumulators are waited for: with the load next to its
+        // use, every 16-column group paid a global-memory round trip (out-projection 205 us in the step against 112 us without residual).
+        int dr_k[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+        float4 rq[4];
+        const bool pre_res = ep.residual && (ep.ld32 & 3) == 0 && col0 + (lane & 3) * 4 + 3 < args.N;
+        if (pre_res) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            rq[k] = dr_k[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(ep.residual + base32 + (int64_t)dr_k[k] * ep.ld32 + col0 + (lane & 3) * 4))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = vn[i];
+        if (g + 1 < TN / 16) ptx::tmem_ld_32x32b_x16(taddr + (g + 1) * 16, vn);
         float x[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -355,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         switch (ep.act) {  // hoisted: one branch per chunk, straight-line math inside
           case ACT_QUICKGELU:
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.f + expf(-1.702f * x[i]));
+            for (int i = 0; i < 16; ++i) x[i] = quick_gelu(x[i]);
             break;
           case ACT_GELU:
 #pragma unroll
@@ -392,13 +419,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int r = k * 8 + sub_row;
-          const int dr = __shfl_sync(0xffffffffu, drow, r);
+          const int dr = dr_k[k];
           if (dr < 0 || col >= args.N) continue;
           float4 y = ptx::ld_shared_f4(stage_f + (r * kEpiLd + cg * 4) * 4);
           const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
           if (vec_ok && (ep.ld32 & 3) == 0) {
             if (ep.residual) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(ep.residual + o32));
+              const float4 q = rq[k];   // pre_res holds exactly here
               y.x += q.x, y.y += q.y, y.z += q.z, y.w += q.w;
             }
             if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o32) = y;
@@ -437,6 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           }
         }
       }
+      ptx::tmem_ld_wait();   // a group requested ahead and not used (N ends inside the tile)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
@@ -628,13 +656,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       ptx::mbar_wait(&t_full[buf], (tile_iter >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kPairTN + half * (kPairTN / 2);
+      uint32_t vn[16];
+      ptx::tmem_ld_32x32b_x16(taddr, vn);   // group 0: every group's accumulators are requested one group ahead of their use
 #pragma unroll 1
       for (int g = 0; g < kPairTN / 32; ++g) {
         const int col0 = ncol0 + g * 16;
         if (col0 >= args.N) break;   // warp-uniform
         uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(taddr + g * 16, v);
+        // The residual of this group's four row chunks is requested BEFORE the accumulators are waited for: with the load next to its
+        // use, every 16-column group paid a global-memory round trip (out-projection 205 us in the step against 112 us without residual).
+        int dr_k[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+        float4 rq[4];
+        const bool pre_res = ep.residual && (ep.ld32 & 3) == 0 && col0 + (lane & 3) * 4 + 3 < args.N;
+        if (pre_res) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            rq[k] = dr_k[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(ep.residual + base32 + (int64_t)dr_k[k] * ep.ld32 + col0 + (lane & 3) * 4))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = vn[i];
+        if (g + 1 < kPairTN / 32) ptx::tmem_ld_32x32b_x16(taddr + (g + 1) * 16, vn);
         float x[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -645,7 +690,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         switch (ep.act) {
           case ACT_QUICKGELU:
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.f + expf(-1.702f * x[i]));
+            for (int i = 0; i < 16; ++i) x[i] = quick_gelu(x[i]);
             break;
           case ACT_GELU:
 #pragma unroll
@@ -681,13 +726,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int r = k * 8 + sub_row;
-          const int dr = __shfl_sync(0xffffffffu, drow, r);
+          const int dr = dr_k[k];
           if (dr < 0 || col >= args.N) continue;
           float4 y = ptx::ld_shared_f4(stage_f + (r * kEpiLd + cg * 4) * 4);
           const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
           if (vec_ok && (ep.ld32 & 3) == 0) {
             if (ep.residual) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(ep.residual + o32));
+              const float4 q = rq[k];   // pre_res holds exactly here
               y.x += q.x, y.y += q.y, y.z += q.z, y.w += q.w;
             }
             if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o32) = y;
@@ -726,6 +771,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           }
         }
       }
+      ptx::tmem_ld_wait();   // a group requested ahead and not used (N ends inside the tile)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(buf ? t_empty_leader1 : t_empty_leader0);
@@ -939,6 +985,19 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (col0 >= args.N) break;
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(taddr + g * 16, v);
+        // The residual of this group's four row chunks is requested BEFORE the accumulators are waited for: with the load next to its
+        // use, every 16-column group paid a global-memory round trip (out-projection 205 us in the step against 112 us without residual).
+        int dr_k[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+        float4 rq[4];
+        const bool pre_res = ep.residual && (ep.ld32 & 3) == 0 && col0 + (lane & 3) * 4 + 3 < args.N;
+        if (pre_res) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            rq[k] = dr_k[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(ep.residual + base32 + (int64_t)dr_k[k] * ep.ld32 + col0 + (lane & 3) * 4))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         ptx::tmem_ld_wait();
         float x[16];
 #pragma unroll
@@ -950,7 +1009,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         switch (ep.act) {
           case ACT_QUICKGELU:
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = x[i] / (1.f + expf(-1.702f * x[i]));
+            for (int i = 0; i < 16; ++i) x[i] = quick_gelu(x[i]);
             break;
           case ACT_GELU:
 #pragma unroll
@@ -986,13 +1045,13 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int r = k * 8 + sub_row;
-          const int dr = __shfl_sync(0xffffffffu, drow, r);
+          const int dr = dr_k[k];
           if (dr < 0 || col >= args.N) continue;
           float4 y = ptx::ld_shared_f4(stage_f + (r * kEpiLd + cg * 4) * 4);
           const int64_t o32 = base32 + (int64_t)dr * ep.ld32 + col;
           if (vec_ok && (ep.ld32 & 3) == 0) {
             if (ep.residual) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(ep.residual + o32));
+              const float4 q = rq[k];   // pre_res holds exactly here
               y.x += q.x, y.y += q.y, y.z += q.z, y.w += q.w;
             }
             if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o32) = y;

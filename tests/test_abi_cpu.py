@@ -50,3 +50,21 @@ def test_product_code_never_imports_the_oracle_or_the_reference():
                 if re.search(r"^\s*(import|from)\s+(oryon_oracle|backbone_oracle|eval_oracle|stage_oracle|vsd_oracle|oracle|ref_shims)\b", txt, flags=re.M) or "/root/reference" in txt:
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_build_fingerprint_does_not_depend_on_the_checkout_path(tmp_path):
+    """The GPU box runs the tree from a scratch path: a fingerprint over absolute file names would call the shipped library stale there
+    and rebuild it on every first import (and crash under ncu, which follows the nvcc children)."""
+    import shutil
+    from oryon_b200 import build as b
+    fp = b._fingerprint()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(b.__file__)))
+    copy = tmp_path / "elsewhere"
+    shutil.copytree(os.path.join(root, "oryon_b200", "csrc"), copy / "oryon_b200" / "csrc")
+    shutil.copytree(os.path.join(root, "include"), copy / "include")
+    old = (b.PKG, b.CSRC)
+    try:
+        b.PKG, b.CSRC = str(copy / "oryon_b200"), str(copy / "oryon_b200" / "csrc")
+        assert b._fingerprint() == fp
+    finally:
+        b.PKG, b.CSRC = old
