@@ -323,6 +323,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int ew = warp - 2, rblk = ew >> 2, quarter = warp & 3;
     const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
     const Epilogue& ep = args.ep;
+    // split-pair outputs only, 16-byte aligned rows: the direct store path of the group loop
+    const bool direct_split = ep.out_hi && !ep.out32 && !ep.residual && !ep.transpose_h && (ep.ldh & 7) == 0 && ((ep.outh_b0 | ep.outh_b1) & 7) == 0 &&
+                              (reinterpret_cast<uintptr_t>(ep.out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.out_lo) & 15) == 0;
     // explicit shared-space addresses: generic pointers into dynamic shared memory compile to LD.E / ST.E
     const uint32_t stage_f = ptx::smem_u32(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats * 4;   // [32][kEpiLd] floats
     const uint32_t bias_s = stage_f + 32 * kEpiLd * 4;                                                             // [TN] floats
@@ -393,6 +396,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
             break;
           default: break;
+        }
+        if (direct_split && col0 + 16 <= args.N) {
+          // Split-pair outputs only (no fp32 copy, no residual): every thread stores the 16 columns of ITS row straight from registers --
+          // 32 bytes of hi halves and 32 bytes of lo halves / 8-bit cross-term values, whole sectors -- instead of going through the
+          // per-warp transposition tile (4 shared-memory stores and loads, 4 shuffles, 12 narrow global stores per group).
+          if (drow >= 0) {
+            uint32_t hh2[8];
+            float rr[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a0 = clamp_h(x[2 * i]), a1 = clamp_h(x[2 * i + 1]);
+              const __half2 h2 = __floats2half2_rn(a0, a1);
+              const float2 back = __half22float2(h2);
+              hh2[i] = *reinterpret_cast<const uint32_t*>(&h2);
+              x[2 * i] = a0, x[2 * i + 1] = a1, rr[2 * i] = a0 - back.x, rr[2 * i + 1] = a1 - back.y;
+            }
+            __half* hrow = ep.out_hi + baseh + (int64_t)drow * ep.ldh;
+            reinterpret_cast<uint4*>(hrow + col0)[0] = make_uint4(hh2[0], hh2[1], hh2[2], hh2[3]);
+            reinterpret_cast<uint4*>(hrow + col0)[1] = make_uint4(hh2[4], hh2[5], hh2[6], hh2[7]);
+            if (ep.out_lo) {
+              __half* lrow = ep.out_lo + baseh + (int64_t)drow * ep.ldh;
+              const int form = ep.lo_format == LO_F8X ? 1 : (ep.lo_format == LO_QKV ? (col0 < ep.qkv_width ? 1 : (col0 < 2 * ep.qkv_width ? 2 : 0)) : 0);
+              if (form == 0) {
+                uint32_t ll2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const __half2 l2 = __floats2half2_rn(rr[2 * i], rr[2 * i + 1]);
+                  ll2[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                reinterpret_cast<uint4*>(lrow + col0)[0] = make_uint4(ll2[0], ll2[1], ll2[2], ll2[3]);
+                reinterpret_cast<uint4*>(lrow + col0)[1] = make_uint4(ll2[4], ll2[5], ll2[6], ll2[7]);
+              } else {
+                // form 1: activation (A operand) blocks [x 2^-4 | (x - hi) 2^7]; form 2: B-operand blocks [(x - hi) 2^4 | x 2^-7]
+                const float s_first = form == 1 ? kF8ActHi : kF8WLo, s_second = form == 1 ? kF8ActLo : kF8WHi;
+                uint32_t fa[4], fb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float* pa = form == 1 ? x + 4 * i : rr + 4 * i;     // what the first half of the block holds
+                  const float* pb = form == 1 ? rr + 4 * i : x + 4 * i;
+                  fa[i] = pack4_f8(pa[0] * s_first, pa[1] * s_first, pa[2] * s_first, pa[3] * s_first, __NV_E5M2);
+                  fb[i] = pack4_f8(pb[0] * s_second, pb[1] * s_second, pb[2] * s_second, pb[3] * s_second, __NV_E5M2);
+                }
+                uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
+                *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
+                *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+              }
+            }
+          }
+          continue;
         }
         if (ep.transpose_h) {
           // out_h element (m, n) lives at n * ldh + m: lanes are consecutive m, already coalesced
@@ -631,6 +683,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int ew = warp - 2, half = ew >> 2, quarter = warp & 3;
     const int row_in_tile = (int)rank * kTileM + quarter * 32 + lane;
     const Epilogue& ep = args.ep;
+    // split-pair outputs only, 16-byte aligned rows: the direct store path of the group loop
+    const bool direct_split = ep.out_hi && !ep.out32 && !ep.residual && !ep.transpose_h && (ep.ldh & 7) == 0 && ((ep.outh_b0 | ep.outh_b1) & 7) == 0 &&
+                              (reinterpret_cast<uintptr_t>(ep.out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.out_lo) & 15) == 0;
     const uint32_t stage_f = ptx::smem_u32(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats * 4;   // [32][kEpiLd] floats
     const uint32_t bias_s = stage_f + 32 * kEpiLd * 4;                                                             // [128] floats
     const uint32_t t_empty_leader0 = ptx::mapa_shared(ptx::smem_u32(&t_empty[0]), 0), t_empty_leader1 = ptx::mapa_shared(ptx::smem_u32(&t_empty[1]), 0);
@@ -701,6 +756,55 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
             break;
           default: break;
+        }
+        if (direct_split && col0 + 16 <= args.N) {
+          // Split-pair outputs only (no fp32 copy, no residual): every thread stores the 16 columns of ITS row straight from registers --
+          // 32 bytes of hi halves and 32 bytes of lo halves / 8-bit cross-term values, whole sectors -- instead of going through the
+          // per-warp transposition tile (4 shared-memory stores and loads, 4 shuffles, 12 narrow global stores per group).
+          if (drow >= 0) {
+            uint32_t hh2[8];
+            float rr[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a0 = clamp_h(x[2 * i]), a1 = clamp_h(x[2 * i + 1]);
+              const __half2 h2 = __floats2half2_rn(a0, a1);
+              const float2 back = __half22float2(h2);
+              hh2[i] = *reinterpret_cast<const uint32_t*>(&h2);
+              x[2 * i] = a0, x[2 * i + 1] = a1, rr[2 * i] = a0 - back.x, rr[2 * i + 1] = a1 - back.y;
+            }
+            __half* hrow = ep.out_hi + baseh + (int64_t)drow * ep.ldh;
+            reinterpret_cast<uint4*>(hrow + col0)[0] = make_uint4(hh2[0], hh2[1], hh2[2], hh2[3]);
+            reinterpret_cast<uint4*>(hrow + col0)[1] = make_uint4(hh2[4], hh2[5], hh2[6], hh2[7]);
+            if (ep.out_lo) {
+              __half* lrow = ep.out_lo + baseh + (int64_t)drow * ep.ldh;
+              const int form = ep.lo_format == LO_F8X ? 1 : (ep.lo_format == LO_QKV ? (col0 < ep.qkv_width ? 1 : (col0 < 2 * ep.qkv_width ? 2 : 0)) : 0);
+              if (form == 0) {
+                uint32_t ll2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const __half2 l2 = __floats2half2_rn(rr[2 * i], rr[2 * i + 1]);
+                  ll2[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                reinterpret_cast<uint4*>(lrow + col0)[0] = make_uint4(ll2[0], ll2[1], ll2[2], ll2[3]);
+                reinterpret_cast<uint4*>(lrow + col0)[1] = make_uint4(ll2[4], ll2[5], ll2[6], ll2[7]);
+              } else {
+                // form 1: activation (A operand) blocks [x 2^-4 | (x - hi) 2^7]; form 2: B-operand blocks [(x - hi) 2^4 | x 2^-7]
+                const float s_first = form == 1 ? kF8ActHi : kF8WLo, s_second = form == 1 ? kF8ActLo : kF8WHi;
+                uint32_t fa[4], fb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float* pa = form == 1 ? x + 4 * i : rr + 4 * i;     // what the first half of the block holds
+                  const float* pb = form == 1 ? rr + 4 * i : x + 4 * i;
+                  fa[i] = pack4_f8(pa[0] * s_first, pa[1] * s_first, pa[2] * s_first, pa[3] * s_first, __NV_E5M2);
+                  fb[i] = pack4_f8(pb[0] * s_second, pb[1] * s_second, pb[2] * s_second, pb[3] * s_second, __NV_E5M2);
+                }
+                uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
+                *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
+                *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+              }
+            }
+          }
+          continue;
         }
         if (ep.transpose_h) {
           if (drow >= 0) {
