@@ -75,6 +75,25 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return x * r;
 }
 
+// Two neighbouring lanes hold 32 bytes (8 words) of two different rows each.  Storing them as they are costs two 16-byte stores per
+// lane whose 32 addresses per instruction lie in 32 different sectors (ncu of the CLIP up-projection: 32 sectors per store request,
+// the next write of the source registers waiting on the store queue).  After one exchange of 16 bytes the pair writes row `mine_even`
+// with one instruction (even lane bytes 0-15, odd lane bytes 16-31) and row `mine_odd` with the next: whole 32-byte sectors, half the
+// sector operations.  `mine` / `other` are the destination of this lane's row and of its neighbour's (null: that row is dropped).
+__device__ __forceinline__ void store_row_pair(__half* mine, __half* other, const uint32_t (&w)[8], int lane) {
+  const bool odd = lane & 1;
+  uint32_t s[4], r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = odd ? w[i] : w[4 + i];        // even lanes give away their second half, odd lanes their first
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = __shfl_xor_sync(0xffffffffu, s[i], 1);
+  // the even lane's row: [even: own first half][odd: the even lane's second half]; the odd lane's row: [even: the odd lane's first half][odd: own second half]
+  __half* even_row = odd ? other : mine;
+  __half* odd_row = odd ? mine : other;
+  if (even_row) reinterpret_cast<uint4*>(even_row)[odd ? 1 : 0] = odd ? make_uint4(r[0], r[1], r[2], r[3]) : make_uint4(w[0], w[1], w[2], w[3]);
+  if (odd_row) reinterpret_cast<uint4*>(odd_row)[odd ? 1 : 0] = odd ? make_uint4(w[4], w[5], w[6], w[7]) : make_uint4(r[0], r[1], r[2], r[3]);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case ACT_QUICKGELU: return quick_gelu(x);
@@ -361,8 +380,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // The residual of this group's four row chunks is requested BEFORE the accumulators are waited for: with the load next to its
         // use, every 16-column group paid a global-memory round trip (out-projection 205 us in the step against 112 us without residual).
         int dr_k[4];
+        if (!direct_split) {   // warp-uniform; the direct store path below needs neither the row exchange nor a residual
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+          for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+        }
         float4 rq[4];
         const bool pre_res = ep.residual && (ep.ld32 & 3) == 0 && col0 + (lane & 3) * 4 + 3 < args.N;
         if (pre_res) {
@@ -401,7 +422,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           // Split-pair outputs only (no fp32 copy, no residual): every thread stores the 16 columns of ITS row straight from registers --
           // 32 bytes of hi halves and 32 bytes of lo halves / 8-bit cross-term values, whole sectors -- instead of going through the
           // per-warp transposition tile (4 shared-memory stores and loads, 4 shuffles, 12 narrow global stores per group).
-          if (drow >= 0) {
+          const int drow_pair = __shfl_xor_sync(0xffffffffu, drow, 1);   // the row of the neighbouring lane (rows 2i, 2i + 1 share their stores)
+          {
             uint32_t hh2[8];
             float rr[16];
 #pragma unroll
@@ -413,10 +435,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               x[2 * i] = a0, x[2 * i + 1] = a1, rr[2 * i] = a0 - back.x, rr[2 * i + 1] = a1 - back.y;
             }
             __half* hrow = ep.out_hi + baseh + (int64_t)drow * ep.ldh;
-            reinterpret_cast<uint4*>(hrow + col0)[0] = make_uint4(hh2[0], hh2[1], hh2[2], hh2[3]);
-            reinterpret_cast<uint4*>(hrow + col0)[1] = make_uint4(hh2[4], hh2[5], hh2[6], hh2[7]);
+            store_row_pair(drow >= 0 ? hrow + col0 : nullptr, drow_pair >= 0 ? ep.out_hi + baseh + (int64_t)drow_pair * ep.ldh + col0 : nullptr, hh2, lane);
             if (ep.out_lo) {
-              __half* lrow = ep.out_lo + baseh + (int64_t)drow * ep.ldh;
+              __half* lrow = ep.out_lo + baseh + (int64_t)drow * ep.ldh;   // dereferenced only where drow >= 0
               const int form = ep.lo_format == LO_F8X ? 1 : (ep.lo_format == LO_QKV ? (col0 < ep.qkv_width ? 1 : (col0 < 2 * ep.qkv_width ? 2 : 0)) : 0);
               if (form == 0) {
                 uint32_t ll2[8];
@@ -425,8 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                   const __half2 l2 = __floats2half2_rn(rr[2 * i], rr[2 * i + 1]);
                   ll2[i] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
-                reinterpret_cast<uint4*>(lrow + col0)[0] = make_uint4(ll2[0], ll2[1], ll2[2], ll2[3]);
-                reinterpret_cast<uint4*>(lrow + col0)[1] = make_uint4(ll2[4], ll2[5], ll2[6], ll2[7]);
+                store_row_pair(drow >= 0 ? lrow + col0 : nullptr, drow_pair >= 0 ? ep.out_lo + baseh + (int64_t)drow_pair * ep.ldh + col0 : nullptr, ll2, lane);
               } else {
                 // form 1: activation (A operand) blocks [x 2^-4 | (x - hi) 2^7]; form 2: B-operand blocks [(x - hi) 2^4 | x 2^-7]
                 const float s_first = form == 1 ? kF8ActHi : kF8WLo, s_second = form == 1 ? kF8ActLo : kF8WHi;
@@ -438,9 +458,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                   fa[i] = pack4_f8(pa[0] * s_first, pa[1] * s_first, pa[2] * s_first, pa[3] * s_first, __NV_E5M2);
                   fb[i] = pack4_f8(pb[0] * s_second, pb[1] * s_second, pb[2] * s_second, pb[3] * s_second, __NV_E5M2);
                 }
-                uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
-                *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
-                *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+                if (drow >= 0) {
+                  uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
+                  *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
+                  *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+                }
               }
             }
           }
@@ -721,8 +743,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         // The residual of this group's four row chunks is requested BEFORE the accumulators are waited for: with the load next to its
         // use, every 16-column group paid a global-memory round trip (out-projection 205 us in the step against 112 us without residual).
         int dr_k[4];
+        if (!direct_split) {   // warp-uniform; the direct store path below needs neither the row exchange nor a residual
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+          for (int k = 0; k < 4; ++k) dr_k[k] = __shfl_sync(0xffffffffu, drow, k * 8 + (lane >> 2));
+        }
         float4 rq[4];
         const bool pre_res = ep.residual && (ep.ld32 & 3) == 0 && col0 + (lane & 3) * 4 + 3 < args.N;
         if (pre_res) {
@@ -761,7 +785,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           // Split-pair outputs only (no fp32 copy, no residual): every thread stores the 16 columns of ITS row straight from registers --
           // 32 bytes of hi halves and 32 bytes of lo halves / 8-bit cross-term values, whole sectors -- instead of going through the
           // per-warp transposition tile (4 shared-memory stores and loads, 4 shuffles, 12 narrow global stores per group).
-          if (drow >= 0) {
+          const int drow_pair = __shfl_xor_sync(0xffffffffu, drow, 1);   // the row of the neighbouring lane (rows 2i, 2i + 1 share their stores)
+          {
             uint32_t hh2[8];
             float rr[16];
 #pragma unroll
@@ -773,10 +798,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               x[2 * i] = a0, x[2 * i + 1] = a1, rr[2 * i] = a0 - back.x, rr[2 * i + 1] = a1 - back.y;
             }
             __half* hrow = ep.out_hi + baseh + (int64_t)drow * ep.ldh;
-            reinterpret_cast<uint4*>(hrow + col0)[0] = make_uint4(hh2[0], hh2[1], hh2[2], hh2[3]);
-            reinterpret_cast<uint4*>(hrow + col0)[1] = make_uint4(hh2[4], hh2[5], hh2[6], hh2[7]);
+            store_row_pair(drow >= 0 ? hrow + col0 : nullptr, drow_pair >= 0 ? ep.out_hi + baseh + (int64_t)drow_pair * ep.ldh + col0 : nullptr, hh2, lane);
             if (ep.out_lo) {
-              __half* lrow = ep.out_lo + baseh + (int64_t)drow * ep.ldh;
+              __half* lrow = ep.out_lo + baseh + (int64_t)drow * ep.ldh;   // dereferenced only where drow >= 0
               const int form = ep.lo_format == LO_F8X ? 1 : (ep.lo_format == LO_QKV ? (col0 < ep.qkv_width ? 1 : (col0 < 2 * ep.qkv_width ? 2 : 0)) : 0);
               if (form == 0) {
                 uint32_t ll2[8];
@@ -785,8 +809,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                   const __half2 l2 = __floats2half2_rn(rr[2 * i], rr[2 * i + 1]);
                   ll2[i] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
-                reinterpret_cast<uint4*>(lrow + col0)[0] = make_uint4(ll2[0], ll2[1], ll2[2], ll2[3]);
-                reinterpret_cast<uint4*>(lrow + col0)[1] = make_uint4(ll2[4], ll2[5], ll2[6], ll2[7]);
+                store_row_pair(drow >= 0 ? lrow + col0 : nullptr, drow_pair >= 0 ? ep.out_lo + baseh + (int64_t)drow_pair * ep.ldh + col0 : nullptr, ll2, lane);
               } else {
                 // form 1: activation (A operand) blocks [x 2^-4 | (x - hi) 2^7]; form 2: B-operand blocks [(x - hi) 2^4 | x 2^-7]
                 const float s_first = form == 1 ? kF8ActHi : kF8WLo, s_second = form == 1 ? kF8ActLo : kF8WHi;
@@ -798,9 +821,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                   fa[i] = pack4_f8(pa[0] * s_first, pa[1] * s_first, pa[2] * s_first, pa[3] * s_first, __NV_E5M2);
                   fb[i] = pack4_f8(pb[0] * s_second, pb[1] * s_second, pb[2] * s_second, pb[3] * s_second, __NV_E5M2);
                 }
-                uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
-                *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
-                *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+                if (drow >= 0) {
+                  uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
+                  *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
+                  *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
+                }
               }
             }
           }
