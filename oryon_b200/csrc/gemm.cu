@@ -371,6 +371,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * (kRowBlocks * TN) + rblk * TN;
       uint32_t vn[16];
+      uint32_t keep_a[4], keep_b[4];   // 8-bit cross-term words of an even group, stored together with the next group's (direct path)
+      bool kept = false;
       ptx::tmem_ld_32x32b_x16(taddr, vn);   // group 0: every group's accumulators are requested one group ahead of their use
 #pragma unroll 1
       for (int g = 0; g < TN / 16; ++g) {
@@ -458,7 +460,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                   fa[i] = pack4_f8(pa[0] * s_first, pa[1] * s_first, pa[2] * s_first, pa[3] * s_first, __NV_E5M2);
                   fb[i] = pack4_f8(pb[0] * s_second, pb[1] * s_second, pb[2] * s_second, pb[3] * s_second, __NV_E5M2);
                 }
-                if (drow >= 0) {
+                // A 16-column group fills 16 bytes of each half of a block: an even group keeps its words, the odd group behind it stores
+                // both as 32-byte runs through the lane-pair exchange (whole sectors, 16 rows per request)
+                if ((g & 1) == 0 && col0 + 32 <= args.N) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) keep_a[i] = fa[i], keep_b[i] = fb[i];
+                  kept = true;
+                } else if ((g & 1) && kept) {
+                  const uint32_t wa[8] = {keep_a[0], keep_a[1], keep_a[2], keep_a[3], fa[0], fa[1], fa[2], fa[3]};
+                  const uint32_t wb[8] = {keep_b[0], keep_b[1], keep_b[2], keep_b[3], fb[0], fb[1], fb[2], fb[3]};
+                  const int64_t off = f8x_off(col0 - 16);
+                  uint8_t* mine = drow >= 0 ? reinterpret_cast<uint8_t*>(lrow) + off : nullptr;
+                  uint8_t* other = drow_pair >= 0 ? reinterpret_cast<uint8_t*>(ep.out_lo + baseh + (int64_t)drow_pair * ep.ldh) + off : nullptr;
+                  store_row_pair(reinterpret_cast<__half*>(mine), reinterpret_cast<__half*>(other), wa, lane);
+                  store_row_pair(reinterpret_cast<__half*>(mine ? mine + 64 : nullptr), reinterpret_cast<__half*>(other ? other + 64 : nullptr), wb, lane);
+                  kept = false;
+                } else if (drow >= 0) {
                   uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
                   *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
                   *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
@@ -734,6 +751,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * kPairTN + half * (kPairTN / 2);
       uint32_t vn[16];
+      uint32_t keep_a[4], keep_b[4];   // 8-bit cross-term words of an even group, stored together with the next group's (direct path)
+      bool kept = false;
       ptx::tmem_ld_32x32b_x16(taddr, vn);   // group 0: every group's accumulators are requested one group ahead of their use
 #pragma unroll 1
       for (int g = 0; g < kPairTN / 32; ++g) {
@@ -821,7 +840,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                   fa[i] = pack4_f8(pa[0] * s_first, pa[1] * s_first, pa[2] * s_first, pa[3] * s_first, __NV_E5M2);
                   fb[i] = pack4_f8(pb[0] * s_second, pb[1] * s_second, pb[2] * s_second, pb[3] * s_second, __NV_E5M2);
                 }
-                if (drow >= 0) {
+                // A 16-column group fills 16 bytes of each half of a block: an even group keeps its words, the odd group behind it stores
+                // both as 32-byte runs through the lane-pair exchange (whole sectors, 16 rows per request)
+                if ((g & 1) == 0 && col0 + 32 <= args.N) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) keep_a[i] = fa[i], keep_b[i] = fb[i];
+                  kept = true;
+                } else if ((g & 1) && kept) {
+                  const uint32_t wa[8] = {keep_a[0], keep_a[1], keep_a[2], keep_a[3], fa[0], fa[1], fa[2], fa[3]};
+                  const uint32_t wb[8] = {keep_b[0], keep_b[1], keep_b[2], keep_b[3], fb[0], fb[1], fb[2], fb[3]};
+                  const int64_t off = f8x_off(col0 - 16);
+                  uint8_t* mine = drow >= 0 ? reinterpret_cast<uint8_t*>(lrow) + off : nullptr;
+                  uint8_t* other = drow_pair >= 0 ? reinterpret_cast<uint8_t*>(ep.out_lo + baseh + (int64_t)drow_pair * ep.ldh) + off : nullptr;
+                  store_row_pair(reinterpret_cast<__half*>(mine), reinterpret_cast<__half*>(other), wa, lane);
+                  store_row_pair(reinterpret_cast<__half*>(mine ? mine + 64 : nullptr), reinterpret_cast<__half*>(other ? other + 64 : nullptr), wb, lane);
+                  kept = false;
+                } else if (drow >= 0) {
                   uint8_t* pbytes = reinterpret_cast<uint8_t*>(lrow) + f8x_off(col0);
                   *reinterpret_cast<uint4*>(pbytes) = make_uint4(fa[0], fa[1], fa[2], fa[3]);
                   *reinterpret_cast<uint4*>(pbytes + 64) = make_uint4(fb[0], fb[1], fb[2], fb[3]);
