@@ -125,6 +125,16 @@ def test_gemm_fp8_cross_terms_any_activation_scale(act_scale):
     assert e2 < 4e-5 and e2 < e1 / 8, (e1, e2, e3)
 
 
+def test_gemm_fp8_cross_terms_need_a_depth_multiple_of_64():
+    """The 8-bit cross-term blocks cover whole 64-deep K blocks: other depths are refused, not padded silently."""
+    need_gpu()
+    from oryon_b200._lib import OryonError
+    A, W = torch.randn(64, 100).cuda(), torch.randn(32, 100).cuda()
+    with pytest.raises(OryonError):
+        ops.linear(A, W, precision=2)
+    assert torch.isfinite(ops.linear(A, W, precision=3)).all()     # the handle stays usable
+
+
 def test_gemm_large_values_saturate_not_nan():
     need_gpu()
     A = torch.full((128, 64), 300.0)
