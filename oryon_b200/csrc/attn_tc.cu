@@ -1,6 +1,10 @@
-// attn_tc_kernel<NPASS>: fused softmax attention for long sequences on tcgen05 (CLIP vision tower, S = 577, d = 64;
-// reference call site models/vlm.py:54 -> nn.MultiheadAttention inside clip's ResidualAttentionBlock).
+// Fused softmax attention for long sequences on tcgen05 (CLIP vision tower, S = 577, d = 64; reference call site models/vlm.py:54 ->
+// nn.MultiheadAttention inside clip's ResidualAttentionBlock).  Three kernels, in the order they were written; launch() picks
+//   attn_pp_kernel      (default at three products) 256 queries per CTA, two softmax groups out of phase, P over S in place
+//   attn_online_kernel  (ORYON_ATTN_LOCKSTEP=1, and precision 1) one pass over the key tiles, lazily renewed reference maximum
+//   attn_tc_kernel      (ORYON_ATTN_TWOPASS) two passes, described first:
 //
+// attn_tc_kernel<NPASS>:
 // One CTA = 128 queries of one (sequence, head).  Scores never leave the SM:
 //   warp 0      TMA producer   Q tile once; K tiles and V^T tiles through 2-stage rings (both requested two tiles ahead:
 //                              a single V^T stage exposed one full TMA latency per key tile, 37k -> cycles per CTA)

@@ -2,7 +2,8 @@
 //
 //   warp 0      TMA producer   cp.async.bulk.tensor.4d (128B swizzle) into a ring of stages; a stage holds one
 //                              64-deep K block of the 256-row A tile and of the TN-row W tile -- for NPASS >= 2
-//                              both halves (hi, lo) of each, so the three products hi*hi, lo*hi, hi*lo reuse
+//                              both halves (hi, lo) of each, so the three products hi*hi, lo*hi, hi*lo (NPASS = 3) or
+//                              hi*hi + the 8-bit cross-term product over the lo blocks (NPASS = 2, gemm.cuh) reuse
 //                              what was fetched once
 //   warp 1      MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16 M=128 N=TN K=16, fp32
 //                              accumulators in TMEM, two 128-row blocks per CTA tile, double-buffered so the

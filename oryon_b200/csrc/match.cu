@@ -656,9 +656,11 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA-pair version (cluster of 2, tcgen05 cta_group::2): the default tensor-core pass
+// CTA-pair version (cluster of 2, tcgen05 cta_group::2): opt-in (ORYON_MATCH_PAIR=1) -- bit-exact and SLOWER than the single-CTA kernel
+// (2.74 vs 2.53 ms at config 2, profiles/r02_match_pair_vs_1cta.md); kept as the record of the experiment and as a tested alternative.
 // ------------------------------------------------------------------------------------------------
-// ncu of match_tc_kernel (profiles/r01_match_tc_ncu_v4.md): tensor pipe 68.5 % active, and the reason is operand bandwidth -- a
+// The hypothesis it was written to test: ncu of match_tc_kernel (profiles/r01_match_tc_ncu_v4.md) showed the tensor pipe 68.5 % active,
+// and the presumed reason was operand bandwidth -- a
 // 128x128x16 UMMA reads 8 KB of shared memory in its 64 cycles (128 B/clk, all an SM delivers) while TMA refills 32 B/clk.  Here the
 // two SMs of a TPC work as a pair on ONE 256-row anchor block: each CTA keeps ITS 128 anchor rows resident and stages HALF of every
 // 256-column query tile; one tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16, issued by the leader CTA) multiplies the pair's
