@@ -264,13 +264,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         rowinfo[2 * t] = yx, rowinfo[2 * t + 1] = pix;
         asm volatile("bar.sync 2, 256;" ::: "memory");
       }
-      // this lane's 16 rows (two per step) stay in registers for all K blocks of the tile
-      int ry[16], rp[16];
-#pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int r = pw * 32 + it * 2 + hrow;
-        ry[it] = rowinfo[2 * r], rp[it] = rowinfo[2 * r + 1];
-      }
+      // Row coordinates are re-read from the shared-memory table at every use (two LDS per load): keeping this lane's 16 rows in 32
+      // registers capped the loads in flight at 8 per lane = 32 KB per SM, and at ~1.5 us of loaded latency that is the ~11 B/clk per
+      // SM these kernels ran at (profiles/r02_network_launches_final.txt: the 192 x 192 convolutions 10x off their HBM roofline).
+      // Without them twelve loads of a stage are in flight at once.
       for (int kb = 0; kb < args.KB; ++kb) {
         const int k0 = kb * kKB + e;
         const bool k_ok = k0 < args.K;
@@ -287,13 +284,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int it = b * 4 + j;
-            const int yy = (ry[it] & 0xffff) + dy, xx = (ry[it] >> 16) + dx;
+            const int2 ri = *reinterpret_cast<const int2*>(rowinfo + 2 * (pw * 32 + it * 2 + hrow));   // (y | x << 16, pixel base)
+            const int ry_ = ri.x, rp_ = ri.y;
+            const int yy = (ry_ & 0xffff) + dy, xx = (ry_ >> 16) + dx;
             // branch-free: out-of-image taps / padding rows / padded K columns read a valid dummy address and are zeroed
-            const bool ok = k_ok && ry[it] >= 0 && (unsigned)yy < (unsigned)gH && (unsigned)xx < (unsigned)gW;
+            const bool ok = k_ok && ry_ >= 0 && (unsigned)yy < (unsigned)gH && (unsigned)xx < (unsigned)gW;
             int off;
-            if (shuf) off = ((rp[it] + (yy >> 1) * (gW >> 1) + (xx >> 1)) * 4 + (yy & 1) * 2 + (xx & 1)) * gC0 + c;   // [n][H/2][W/2][2][2][C0]
-            else if (shuffle0) off = (rp[it] * 4 + yy * gW + xx) * Csel + csel;                                      // src1 next to a shuffled src0
-            else off = rp[it] * Csel + delta;
+            if (shuf) off = ((rp_ + (yy >> 1) * (gW >> 1) + (xx >> 1)) * 4 + (yy & 1) * 2 + (xx & 1)) * gC0 + c;   // [n][H/2][W/2][2][2][C0]
+            else if (shuffle0) off = (rp_ * 4 + yy * gW + xx) * Csel + csel;                                      // src1 next to a shuffled src0
+            else off = rp_ * Csel + delta;
             const float4 ld = __ldg(reinterpret_cast<const float4*>(sbase + (ok ? (unsigned)off : 0u)));
             v[j] = ok ? ld : make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -303,6 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           for (int j = 0; j < 4; ++j) {
             const int it = b * 4 + j;
             const int r = pw * 32 + it * 2 + hrow, rr = r & 127;
+            // (tried: cvt.rn.satfinite.f16x2.f32 for the pairs -- F2FP.SATFINITE in SASS -- instead of clamp + cvt per value: the
+            // 192 x 192 convolutions went from 1.25 to 2.48 ms, the saturating pack is a slow instruction on this part)
             __half h0, l0, h1, l1, h2, l2, h3, l3;
             split_half(v[j].x, h0, l0), split_half(v[j].y, h1, l1), split_half(v[j].z, h2, l2), split_half(v[j].w, h3, l3);
             const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3), la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
@@ -316,18 +317,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                            : "memory");
           }
         };
-        // software pipeline over four batches of four rows: eight loads in flight, and the first eight are issued before the
-        // wait for the shared-memory slot (global loads do not need it)
-        float4 va[4], vb[4];
+        // twelve loads of the stage are issued before the wait for the shared-memory slot (global loads do not need it), the last four
+        // as soon as the first batch has been stored (sixteen at once spill: the kernel is capped at 96 registers by its 576 threads)
+        float4 va[4], vb[4], vc[4];
         load4(va, 0);
         load4(vb, 1);
+        load4(vc, 2);
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         store4(va, 0);
-        load4(va, 2);
+        load4(va, 3);
         store4(vb, 1);
-        load4(vb, 3);
-        store4(va, 2);
-        store4(vb, 3);
+        store4(vc, 2);
+        store4(va, 3);
         ptx::fence_proxy_async_smem();                 // generic-proxy stores -> visible to the tensor core
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&full[stage]);
@@ -344,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int row_in_cta = rblk * kTileM + quarter * 32 + lane;
     const Epilogue& ep = args.ep;
     // split-pair outputs only, 16-byte aligned rows: the direct store path of the group loop
-    const bool direct_split = ep.out_hi && !ep.out32 && !ep.residual && !ep.transpose_h && (ep.ldh & 7) == 0 && ((ep.outh_b0 | ep.outh_b1) & 7) == 0 &&
+    const bool direct_split = !GATHER /* the convolutions write fp32: keep their 96-register kernels lean */ && ep.out_hi && !ep.out32 && !ep.residual && !ep.transpose_h && (ep.ldh & 7) == 0 && ((ep.outh_b0 | ep.outh_b1) & 7) == 0 &&
                               (reinterpret_cast<uintptr_t>(ep.out_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.out_lo) & 15) == 0;
     // explicit shared-space addresses: generic pointers into dynamic shared memory compile to LD.E / ST.E
     const uint32_t stage_f = ptx::smem_u32(smem + L::kStage * STAGES + L::kBarBytes) + ew * kEpiWarpFloats * 4;   // [32][kEpiLd] floats
