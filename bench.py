@@ -572,7 +572,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", type=int, default=2, choices=[1, 2, 3],
                     help="network GEMM precision (include/oryon_b200.h): 3 = three fp16 products everywhere; 2 (default, parity-tested to the same "
